@@ -1,0 +1,153 @@
+"""Generates tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE -- TEST INFRASTRUCTURE.
+
+Run in the build container (needs /root/reference):   python oracle/gen_golden.py
+The fixtures are data (inputs + the reference's outputs); no reference source is copied.
+
+Two families:
+  mt_seed<S>.npz      the reference exactly as shipped: random.seed(S); SimulatedNetworkEnv();
+                      episodes of reset() + 400 step()s with N(0,1) actions (Python floats).
+                      Link parameters are whatever the reference drew from its global stream.
+  philox_<name>.npz   the reference with `network_sim.random` replaced by a per-env Philox
+                      stream (oracle/philox_py.py) and scripted link parameters, covering edge
+                      cases (no loss, tiny/huge queue, rate >> bw, rate clamps, long/short
+                      history, all 12 features).
+Per step the fixture stores: action, obs, reward, done, sent/acked/lost, cur_time, run_dur,
+rate, and the event-log fields of network_sim.py:422-436.
+"""
+import math
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refharness as rh  # noqa: E402
+from philox_py import PhiloxStream  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+ALL_FEATURES = ("send rate,recv rate,recv dur,send dur,avg latency,loss ratio,"
+                "ack latency inflation,sent latency inflation,conn min latency,"
+                "latency increase,latency ratio,send ratio")
+DEFAULT_FEATURES = "sent latency inflation,latency ratio,send ratio"
+
+
+def _record_step(env, action, obs, reward, done, rec):
+    s = env.senders[0]
+    ev = env.event_record["Events"][-1]
+    rec["action"].append(action)
+    rec["obs"].append(np.asarray(obs, dtype=np.float64))
+    rec["reward"].append(float(reward))
+    rec["done"].append(bool(done))
+    rec["counts"].append((s.sent, s.acked, s.lost))
+    rec["cur_time"].append(env.net.cur_time)
+    rec["run_dur"].append(float(env.run_dur))
+    rec["rate"].append(float(s.rate))
+    rec["info"].append((ev["Send Rate"], ev["Throughput"], ev["Latency"], ev["Loss Rate"],
+                        ev["Latency Inflation"], ev["Latency Ratio"], ev["Send Ratio"]))
+
+
+def _new_rec():
+    return {k: [] for k in ("action", "obs", "reward", "done", "counts", "cur_time", "run_dur",
+                            "rate", "info", "ep_params", "ep_obs0", "ep_cur_time0")}
+
+
+def _record_reset(env, obs0, rec):
+    l, s = env.links[0], env.senders[0]
+    queue = int(round(l.max_queue_delay * l.bw))
+    rec["ep_params"].append((l.bw, l.dl, float(queue), l.lr, s.starting_rate))
+    rec["ep_obs0"].append(np.asarray(obs0, dtype=np.float64))
+    rec["ep_cur_time0"].append(env.net.cur_time)
+
+
+def _save(name, rec, **meta):
+    arrs = dict(
+        action=np.array(rec["action"]), obs=np.array(rec["obs"]), reward=np.array(rec["reward"]),
+        done=np.array(rec["done"]), counts=np.array(rec["counts"], dtype=np.int64),
+        cur_time=np.array(rec["cur_time"]), run_dur=np.array(rec["run_dur"]),
+        rate=np.array(rec["rate"]), info=np.array(rec["info"]),
+        ep_params=np.array(rec["ep_params"]), ep_obs0=np.array(rec["ep_obs0"]),
+        ep_cur_time0=np.array(rec["ep_cur_time0"]))
+    for k, v in meta.items():
+        arrs[k] = np.array(v)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print("wrote %s: %d steps" % (name, len(rec["action"])))
+
+
+def gen_mt(ns, seed, n_eps, action_seed, zero_actions=False):
+    rec = _new_rec()
+    arng = random.Random(action_seed)
+    with rh.quiet_tmp_cwd():
+        random.seed(seed)
+        env = ns.SimulatedNetworkEnv()
+        for _ in range(n_eps):
+            obs0 = env.reset()
+            _record_reset(env, obs0, rec)
+            done = False
+            while not done:
+                a = 0.0 if zero_actions else arng.gauss(0.0, 1.0)
+                obs, r, done, _ = env.step([a])
+                _record_step(env, a, obs, r, done, rec)
+    _save("mt_seed%d" % seed, rec, seed=seed, rng="mt19937", history_len=10,
+          features=DEFAULT_FEATURES, steps_per_episode=400)
+
+
+def gen_philox(ns, name, seed, params, n_steps, actions, history_len=10,
+               features=DEFAULT_FEATURES, n_eps=1):
+    """params: list (one per episode) of (bw, lat, queue, loss, start_factor)."""
+    rec = _new_rec()
+    stream = PhiloxStream(seed)
+    shim = rh.StreamShim([stream])
+    real_random = ns.random
+    ns.random = shim
+    try:
+        with rh.quiet_tmp_cwd():
+            shim.script = [100.0, 0.1, 0.0, 0.0, 1.0]  # __init__ builds a throw-away link
+            env = ns.SimulatedNetworkEnv(history_len=history_len, features=features)
+            k = 0
+            for ep in range(n_eps):
+                bw, lat, queue, loss, factor = params[ep]
+                shim.script = [bw, lat, math.log(queue - 1 + 0.5), loss, factor]
+                obs0 = env.reset()
+                assert not shim.script
+                _record_reset(env, obs0, rec)
+                assert rec["ep_params"][-1][2] == queue, (rec["ep_params"][-1], queue)
+                for t in range(n_steps):
+                    a = float(actions[k]); k += 1
+                    obs, r, done, _ = env.step([a])
+                    _record_step(env, a, obs, r, done, rec)
+    finally:
+        ns.random = real_random
+    _save("philox_" + name, rec, seed=seed, rng="philox", history_len=history_len,
+          features=features, steps_per_episode=n_steps)
+
+
+def main():
+    ns = rh.load_reference()
+    # --- the reference exactly as shipped (global MT19937 stream) ---
+    gen_mt(ns, 1234, 2, 7)            # the KAT seed of SURVEY.md §8a
+    gen_mt(ns, 100, 2, 101)           # BASELINE.md's benchmark seeds
+    gen_mt(ns, 2019, 1, 3, zero_actions=True)
+    gen_mt(ns, 987654321987, 1, 5)    # a seed wider than 32 bits (two init_by_array limbs)
+    # --- scripted edge cases on Philox streams ---
+    g = random.Random(42)
+    acts = lambda n, s=1.0: [g.gauss(0.0, s) for _ in range(n)]
+    gen_philox(ns, "noloss", 11, [(300.0, 0.1, 50, 0.0, 0.5)], 120, acts(120))
+    gen_philox(ns, "tinyqueue_overdrive", 12, [(100.0, 0.05, 2, 0.01, 1.5)], 120, [4.0] * 60 + acts(60, 3.0))
+    gen_philox(ns, "hugequeue_bufferbloat", 13, [(100.0, 0.2, 2981, 0.0, 1.5)], 100, [6.0] * 40 + [-6.0] * 60)
+    gen_philox(ns, "maxrate_clamp", 14, [(500.0, 0.05, 10, 0.05, 1.5)], 100, [20.0] * 100)
+    gen_philox(ns, "minrate_clamp", 15, [(100.0, 0.5, 5, 0.02, 0.3)], 80, [-20.0] * 80)
+    gen_philox(ns, "heavyloss", 16, [(200.0, 0.08, 20, 0.6, 1.0)], 100, acts(100, 2.0))
+    gen_philox(ns, "allfeatures", 17, [(250.0, 0.12, 8, 0.03, 1.2), (120.0, 0.3, 100, 0.0, 0.9)], 100,
+               acts(200, 2.0), features=ALL_FEATURES, n_eps=2)
+    gen_philox(ns, "hist1", 18, [(400.0, 0.06, 3, 0.04, 1.4)], 60, acts(60, 2.0), history_len=1)
+    gen_philox(ns, "hist25_rates", 19, [(150.0, 0.25, 30, 0.01, 0.7)], 60, acts(60, 2.0), history_len=25,
+               features="send rate,recv rate,avg latency,loss ratio")
+    gen_philox(ns, "highbw_idle", 20, [(83333.0, 0.001, 1000, 0.0, 0.01)], 100, acts(100, 2.0))
+    gen_philox(ns, "bigseed", 0xFEDCBA9876543210, [(333.0, 0.07, 6, 0.05, 1.3)], 60, acts(60, 2.0))
+
+
+if __name__ == "__main__":
+    main()

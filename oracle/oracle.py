@@ -1,0 +1,194 @@
+"""ctypes wrapper over oracle/libpcc_oracle.so -- TEST INFRASTRUCTURE, not product code.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (pcc-rl_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpcc_oracle.so")
+
+# metric ids = position in the reference's SENDER_MI_METRICS (sender_obs.py:193-206)
+METRIC_NAMES = ["send rate", "recv rate", "recv dur", "send dur", "avg latency", "loss ratio",
+                "ack latency inflation", "sent latency inflation", "conn min latency",
+                "latency increase", "latency ratio", "send ratio"]
+DEFAULT_FEATURES = "sent latency inflation,latency ratio,send ratio"
+
+
+def feature_ids(features=DEFAULT_FEATURES):
+    names = features.split(",") if isinstance(features, str) else list(features)
+    return [METRIC_NAMES.index(n) for n in names]
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("pcc_oracle.c", "pcc_oracle_batch.c", "Makefile")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-B", "libpcc_oracle.so"],
+                          stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        build()
+    L = C.CDLL(_LIB_PATH)
+    vp, d, i, l = C.c_void_p, C.c_double, C.c_int, C.c_long
+    pd, pi, pl = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_long)
+    L.pcco_create.restype = vp
+    L.pcco_create.argtypes = [i, pi, i]
+    L.pcco_destroy.argtypes = [vp]
+    L.pcco_set_max_steps.argtypes = [vp, l]
+    L.pcco_seed_mt.argtypes = [vp, C.c_uint64]
+    L.pcco_seed_philox.argtypes = [vp, C.c_uint64]
+    L.pcco_mt_getstate.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.pcco_mt_setstate.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.pcco_philox_draws.restype = C.c_uint64
+    L.pcco_philox_draws.argtypes = [vp]
+    L.pcco_random.restype = d
+    L.pcco_random.argtypes = [vp]
+    L.pcco_reset.argtypes = [vp, d, d, l, d, d]
+    L.pcco_get_obs.argtypes = [vp, pd]
+    L.pcco_step.argtypes = [vp, d, pd, pd, pi, pl, pd]
+    for name in ("pcco_cur_time", "pcco_run_dur", "pcco_rate"):
+        getattr(L, name).restype = d
+        getattr(L, name).argtypes = [vp]
+    L.pcco_queue_len.restype = l
+    L.pcco_queue_len.argtypes = [vp]
+    L.pcco_total_events.restype = C.c_longlong
+    L.pcco_total_events.argtypes = [vp]
+    L.pcco_np_mean.restype = d
+    L.pcco_np_mean.argtypes = [pd, l]
+    L.pcco_batch_run.restype = d
+    L.pcco_batch_run.argtypes = [l, l, i, i, pi, i, pd, pd, pl, pd, pd,
+                                 C.POINTER(C.c_uint64), pd, pd, pd, pl]
+    _lib = L
+    return L
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def np_mean(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return lib().pcco_np_mean(_p(a, C.c_double), a.size)
+
+
+class OracleEnv(object):
+    """One env of the restated reference (1 sender, 2 links, network_sim.py:344-496)."""
+
+    def __init__(self, history_len=10, features=DEFAULT_FEATURES):
+        self.L = lib()
+        ids = np.asarray(feature_ids(features), dtype=np.int32)
+        self.history_len, self.n_features = history_len, len(ids)
+        self.h = self.L.pcco_create(history_len, _p(ids, C.c_int), len(ids))
+        if not self.h:
+            raise ValueError("bad history_len / features")
+        self._obs = np.zeros(history_len * len(ids))
+        self._info = np.zeros(8)
+        self._counts = np.zeros(3, dtype=np.int64)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.pcco_destroy(self.h)
+            self.h = None
+
+    def seed_mt(self, seed):
+        self.L.pcco_seed_mt(self.h, int(seed))
+
+    def seed_philox(self, seed):
+        self.L.pcco_seed_philox(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+    def mt_getstate(self):
+        s = np.zeros(625, dtype=np.uint32)
+        self.L.pcco_mt_getstate(self.h, _p(s, C.c_uint32))
+        return s
+
+    def mt_setstate(self, s):
+        s = np.ascontiguousarray(s, dtype=np.uint32)
+        assert s.size == 625
+        self.L.pcco_mt_setstate(self.h, _p(s, C.c_uint32))
+
+    def random(self):
+        return self.L.pcco_random(self.h)
+
+    def uniform(self, a, b):
+        return a + (b - a) * self.random()
+
+    def set_max_steps(self, n):
+        self.L.pcco_set_max_steps(self.h, n)
+
+    def sample_params(self, bw=(100, 500), lat=(0.05, 0.5), queue=(0, 8), loss=(0.0, 0.05)):
+        """The five draws of create_new_links_and_senders (network_sim.py:455-466), taken from
+        this env's own stream, in the reference's order."""
+        b = self.uniform(*bw)
+        l = self.uniform(*lat)
+        q = 1 + int(np.exp(self.uniform(*queue)))
+        lo = self.uniform(*loss)
+        r = self.uniform(0.3, 1.5) * b
+        return b, l, q, lo, r
+
+    def reset(self, bw, lat, queue, loss, start_rate):
+        self.L.pcco_reset(self.h, bw, lat, int(queue), loss, start_rate)
+        self.L.pcco_get_obs(self.h, _p(self._obs, C.c_double))
+        return self._obs.copy()
+
+    def step(self, action):
+        r, dn = C.c_double(), C.c_int()
+        self.L.pcco_step(self.h, float(action), _p(self._obs, C.c_double), C.byref(r), C.byref(dn),
+                         _p(self._counts, C.c_long), _p(self._info, C.c_double))
+        return self._obs.copy(), r.value, bool(dn.value), self._counts.copy(), self._info.copy()
+
+    @property
+    def cur_time(self):
+        return self.L.pcco_cur_time(self.h)
+
+    @property
+    def run_dur(self):
+        return self.L.pcco_run_dur(self.h)
+
+    @property
+    def rate(self):
+        return self.L.pcco_rate(self.h)
+
+    @property
+    def total_events(self):
+        return self.L.pcco_total_events(self.h)
+
+
+def batch_run(bw, lat, queue, loss, start_rate, seeds, n_steps, actions=None, n_threads=1,
+              history_len=10, features=DEFAULT_FEATURES):
+    """Reset + n_steps steps for every env on n_threads host threads (Philox streams).
+    Returns dict(seconds, obs[N,H*F] of the last step, reward_sum[N], count_sum[N,3])."""
+    L = lib()
+    n = len(bw)
+    ids = np.asarray(feature_ids(features), dtype=np.int32)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    bw, lat, loss, start_rate = f64(bw), f64(lat), f64(loss), f64(start_rate)
+    queue = np.ascontiguousarray(queue, dtype=np.int64)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    obs = np.zeros((n, history_len * len(ids)))
+    rs = np.zeros(n)
+    cs = np.zeros((n, 3), dtype=np.int64)
+    if actions is not None:
+        actions = f64(actions)
+        assert actions.shape == (n_steps, n)
+    secs = L.pcco_batch_run(n, n_steps, n_threads, history_len, _p(ids, C.c_int), len(ids),
+                            _p(bw, C.c_double), _p(lat, C.c_double), _p(queue, C.c_long),
+                            _p(loss, C.c_double), _p(start_rate, C.c_double),
+                            _p(seeds, C.c_uint64),
+                            _p(actions, C.c_double) if actions is not None else None,
+                            _p(obs, C.c_double), _p(rs, C.c_double), _p(cs, C.c_long))
+    return dict(seconds=secs, obs=obs, reward_sum=rs, count_sum=cs)
