@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched MI simulator on N B200s, next to the CPU oracle.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config3]
+
+One "step" = one monitor interval for every env of the batch (one pcc_step launch), auto-reset
+included (a 400-step episode ends inside the default window, so the amortised reset cost is
+in the number).  Workloads (BASELINE.json `configs`):
+    config2: 4 096 envs per GPU,  default (ICML'19) link-parameter ranges, history_len 10   [default]
+    config3: 65 536 envs per GPU, same ranges, fresh parameters at every per-env reset
+Weak scaling: every rank owns --envs envs (global ids are contiguous, parameters and RNG streams
+are functions of the global id); no data-path collective; one all-gather of episode returns.
+
+Timing: W untimed warm-up steps, then K steps, each bracketed by CUDA events on the launching
+stream, with a 256 MiB L2-flush write between steps (outside the brackets); the timed region as
+a whole is bracketed by barrier + torch.cuda.synchronize(); time = sum of the K brackets, max
+over ranks.  A second pass runs K steps back to back without flushes (`back_to_back`).  `e2e`
+is the same K steps through pcc_step_host: pinned HOST actions in, obs/reward/done out, copies
+and synchronisation inside the wall-clock timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "config2": dict(envs=4096, desc="4 096 envs on 1xB200, link params sampled from ICML'19 ranges, history_len=10"),
+    "config3": dict(envs=65536, desc="65 536 envs on 1xB200, per-reset randomized bw/lat/queue/loss, 1 sender per env"),
+}
+ACTION_SIGMA = 1.0   # a ~ N(0,1), BASELINE.md §3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (overrides the workload's)")
+    ap.add_argument("--seed", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(n_env_steps, sent, acked, hist_len=10, n_feat=3):
+    """(221 + 8*H*F + 8*(H-1)*F) + 48*sent + 8*acked bytes per env-step."""
+    fixed = 221 + 8 * hist_len * n_feat + 8 * (hist_len - 1) * n_feat
+    return fixed * n_env_steps + 48 * sent + 8 * acked
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the CPU restatement of the reference (oracle/, the Python reference itself cannot
+    travel to the GPU box) on all host threads, same workload, same metric.  Rank 0 only."""
+    if rank != 0:
+        return
+    import oracle
+    from pcc_rl_b200 import sample_link_params
+    n = args.envs or WORKLOADS[args.workload]["envs"]
+    cores = os.cpu_count() or 1
+    seeds = (np.uint64(args.seed) + np.arange(n, dtype=np.uint64))
+    ob = oracle.OracleBatch(seeds, n_threads=cores)
+    episode = 1
+    ob.reset(sample_link_params(args.seed, episode, np.arange(n), n))
+    g = np.random.default_rng(args.seed + 1)
+    steps_in_ep = 0
+
+    def one():
+        nonlocal steps_in_ep, episode
+        ob.step(g.normal(0, ACTION_SIGMA, n))
+        steps_in_ep += 1
+        if steps_in_ep >= 400:
+            episode += 1
+            ob.reset(sample_link_params(args.seed, episode, np.arange(n), n))
+            steps_in_ep = 0
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    line = {"impl": "reference", "metric": "env-steps/sec (batched MI sim)", "value": v, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "envs": n,
+                       "actions": "N(0,1)", "auto_reset": True},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": "%d envs x %d steps, all host threads (C restatement of the Python reference; "
+                                       "the unmodified Python reference measured 1.3-1.5k env-steps/s on one core, "
+                                       "BASELINE.md §2)" % (n, args.steps)},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    import torch
+    import pcc_rl_b200
+    from pcc_rl_b200 import distributed as D
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    rank, local_rank, world = D.init_from_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n = args.envs or WORKLOADS[args.workload]["envs"]
+    n_global = n * world
+    K, W = args.steps, args.warmup
+
+    def make_env():
+        return pcc_rl_b200.PccBatchEnv(n_envs=n, device=dev, seed=args.seed, global_offset=rank * n,
+                                       n_global=n_global, auto_reset=True)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(args.seed + 1 + rank)
+    # pre-generate the actions (the policy is outside the path): [W+K, n] float64 on the device
+    actions = torch.randn((W + K, n), generator=gen, device=dev, dtype=torch.float64) * ACTION_SIGMA
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    # ---------------- pass 1: device-resident inputs, per-step CUDA-event brackets ----------------
+    env = make_env()
+    env.reset()
+    tot = torch.zeros(3, dtype=torch.int64, device=dev)
+    finished = []
+    for t in range(W):
+        env.step(actions[t])
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    barrier()
+    launches0 = env.launches
+    sampler.start()
+    wall0 = time.perf_counter()
+    for t in range(K):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        ev_s[t].record()
+        obs, rew, done, info = env.step(actions[W + t])
+        ev_e[t].record()
+        tot += info["counts"].sum(0)
+        if bool(env._steps.max() == 0):  # a synchronized auto-reset just happened
+            finished.append(env.column("last_episode_return"))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = env.launches - launches0
+    env.check()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))
+    dev_ms = D.max_over_ranks(dev_ms, dev)
+    sent, acked, lost = [int(x) for x in tot.cpu().tolist()]
+    g_sent, g_acked = D.sum_over_ranks(sent, dev), D.sum_over_ranks(acked, dev)
+    rets = torch.cat(finished) if finished else torch.zeros(0, dtype=torch.float64, device=dev)
+    ret_stats = D.gather_episode_returns(rets)   # the path's only collective (NCCL all-gather, a few bytes)
+    value = n_global * K / (dev_ms * 1e-3)
+
+    # ---------------- pass 2: back to back, no flush, one bracket around all K steps ----------------
+    del env
+    env = make_env()
+    env.reset()
+    for t in range(W):
+        env.step(actions[t])
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for t in range(K):
+        env.step(actions[W + t])
+    e.record()
+    barrier()
+    b2b_ms = D.max_over_ranks(s.elapsed_time(e), dev)
+    env.check()
+
+    # ---------------- pass 3: end to end through host buffers (pcc_step_host) ----------------
+    del env
+    env = make_env()
+    env.reset()
+    hf = env.obs_dim
+    h_act = torch.empty((W + K, n), dtype=torch.float64).pin_memory()
+    h_act.copy_(actions.cpu())
+    h_obs = torch.empty((n, hf), dtype=torch.float64).pin_memory()
+    h_rew = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    a_np, o_np, r_np, d_np = h_act.numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy()
+
+    def host_step(t):
+        env.step_host(a_np[t], o_np, r_np, d_np)
+        if env._steps[0] >= env.max_steps:      # the caller resets finished envs, as PPO does
+            env.reset()
+    for t in range(W):
+        host_step(t)
+    barrier()
+    t0 = time.perf_counter()
+    ret_acc = 0.0
+    for t in range(K):
+        host_step(W + t)
+        ret_acc += float(r_np[0])               # the result is really read on the host
+    barrier()
+    e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = n_global * K / e2e_s
+    env.check()
+    del env
+
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak_gbs()
+    bytes_total = algorithmic_bytes(n_global * K, g_sent, g_acked)
+    achieved = bytes_total / (dev_ms * 1e-3) / 1e9 / world   # per GPU
+    line = {
+        "metric": "env-steps/sec (batched MI sim)", "value": value, "unit": "env-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "envs_per_gpu": n,
+                   "global_envs": n_global, "history_len": 10, "features": 3, "rng": "philox4x32-10",
+                   "actions": "N(0,1) pre-generated on device", "auto_reset": True,
+                   "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB write outside the event brackets)",
+                   "parallelism": "env-batch sharding x%d, no data-path collective" % world},
+        "back_to_back": {"value": n_global * K / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K,
+                         "note": "K steps enqueued back to back, one event bracket, warm L2"},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 8 * n,
+                "d2h_bytes_per_step": n * (8 * hf + 8 + 1), "ms_per_step": 1e3 * e2e_s / K,
+                "api": "PccBatchEnv.step_host -> pcc_step_host (pinned host buffers, synchronous)"},
+        "gpu_launches": int(launches),
+        "wall_s_timed_region": wall,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                     "traffic": None, "kernel": "pcc_step_kernel",
+                     "algorithmic_bytes_per_env_step": bytes_total / (n_global * K),
+                     "packets_sent_per_env_step": g_sent / (n_global * K)},
+        "clocks": clocks,
+        "episode_returns": {"count": ret_stats["count"], "mean": ret_stats["mean"]},
+    }
+    if not args.no_cpu_baseline:
+        import oracle
+        from pcc_rl_b200 import sample_link_params
+        cores = os.cpu_count() or 1
+        ns, ks = min(n, 4096), 100
+        p = sample_link_params(args.seed, 1, np.arange(ns), n_global)
+        acts = np.random.default_rng(args.seed + 1).normal(0, ACTION_SIGMA, (ks, ns))
+        r = oracle.batch_run(p["bw"], p["lat"], p["queue"], p["loss"], p["start_rate"],
+                             np.uint64(args.seed) + np.arange(ns, dtype=np.uint64), ks, actions=acts, n_threads=cores)
+        line["cpu_baseline"] = {"value": ns * ks / r["seconds"], "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                "sample": "%d envs x (reset + %d steps) of the same workload on %d host threads; "
+                                          "C restatement of the reference (oracle/), the Python reference itself "
+                                          "measured 1.3-1.5k env-steps/s on one core (BASELINE.md)" % (ns, ks, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

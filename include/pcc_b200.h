@@ -1,0 +1,180 @@
+/*
+ * pcc_b200.h -- C ABI of libpcc_b200.so: a batched, B200-native replacement for the hot path
+ * of PCC-RL's gym environment (one monitor interval of packet/link simulation + MI feature,
+ * history and reward computation per env per call).
+ *
+ * The reference is 100 % Python and has no FFI of its own; this header is the boundary a
+ * maintainer would bind with ctypes.  Each entry point names the
+ * reference interface it replaces (file:line under /root/reference/src):
+ *
+ *   pcc_create / pcc_destroy   SimulatedNetworkEnv.__init__ / close     gym/network_sim.py:346-394, 489-492
+ *   pcc_seed                   random.seed() feeding network_sim.py:73 (the per-packet loss draw)
+ *   pcc_reset                  SimulatedNetworkEnv.reset                gym/network_sim.py:469-484
+ *                              (create_new_links_and_senders :454-467 stays on the host: link
+ *                              parameters and the start rate are inputs)
+ *   pcc_step / pcc_step_host   SimulatedNetworkEnv.step                 gym/network_sim.py:406-444
+ *                                -> Sender.apply_rate_delta             :235-241, 275-281
+ *                                -> Network.run_for_dur                 :123-205
+ *                                -> Sender.record_run / SenderHistory   :291-293; common/sender_obs.py:56-73
+ *                                -> MI metrics                          common/sender_obs.py:110-191
+ *   pcc_get_mt_state / pcc_set_mt_state   random.getstate() / random.setstate()
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a negative PCC_E* code otherwise; the message is
+ *     available from pcc_last_error() (thread-local).  Nothing throws across the ABI.
+ *   - Pointers named *_dev are CUDA device pointers on the handle's device, borrowed for the
+ *     duration of the stream work the call enqueues.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = legacy default stream).  Calls are asynchronous unless stated otherwise.
+ *   - All floating point is IEEE binary64, evaluated in the reference's operation order.
+ *   - One host thread per handle; no global state.
+ *   - There is no CPU fallback: without a CUDA device pcc_create fails.
+ */
+#ifndef PCC_B200_H
+#define PCC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCC_ABI_VERSION 1
+
+/* error codes */
+#define PCC_OK 0
+#define PCC_EINVAL (-1)   /* bad argument */
+#define PCC_ECUDA (-2)    /* CUDA runtime error */
+#define PCC_EOVERFLOW (-3)/* an env's in-flight ring overflowed (results of that env are invalid) */
+#define PCC_ENODEV (-4)   /* no usable CUDA device */
+
+/* metric ids = position in the reference's SENDER_MI_METRICS (common/sender_obs.py:193-206) */
+#define PCC_M_SEND_RATE 0
+#define PCC_M_RECV_RATE 1
+#define PCC_M_RECV_DUR 2
+#define PCC_M_SEND_DUR 3
+#define PCC_M_AVG_LATENCY 4
+#define PCC_M_LOSS_RATIO 5
+#define PCC_M_ACK_LATENCY_INFLATION 6
+#define PCC_M_SENT_LATENCY_INFLATION 7
+#define PCC_M_CONN_MIN_LATENCY 8
+#define PCC_M_LATENCY_INCREASE 9
+#define PCC_M_LATENCY_RATIO 10
+#define PCC_M_SEND_RATIO 11
+#define PCC_N_METRICS 12
+#define PCC_MAX_FEATURES 12
+#define PCC_MAX_HISTORY 64
+
+/* RNG feeding the per-packet loss draw (network_sim.py:73) */
+#define PCC_RNG_MT19937 0 /* CPython's `random`: bit-compatible state, for drop-in fidelity */
+#define PCC_RNG_PHILOX 1  /* Philox4x32-10, counter = draw index, key = per-env seed (fast path) */
+
+/* width of one row of the optional `info` output of pcc_step:
+ *  0 send rate  1 throughput (recv rate)  2 avg latency  3 loss ratio  4 latency inflation
+ *  5 latency ratio  6 send ratio          (the event-log fields of network_sim.py:422-436)
+ *  7 MI duration  8 cur_time after the MI  9 sending rate  10 next run_dur  11 conn min latency */
+#define PCC_INFO_WIDTH 12
+
+/* Simulation constants (gym/network_sim.py:33-54, common/config.py:17). */
+typedef struct pcc_consts {
+    double max_rate;          /* MAX_RATE          1000  */
+    double min_rate;          /* MIN_RATE          40    */
+    double delta_scale;       /* DELTA_SCALE       0.025 */
+    double reward_scale;      /* REWARD_SCALE      0.001 */
+    int32_t max_steps;        /* MAX_STEPS         400   */
+    int32_t bytes_per_packet; /* BYTES_PER_PACKET  1500  */
+} pcc_consts;
+
+typedef struct pcc_config {
+    int32_t abi_version;      /* PCC_ABI_VERSION */
+    int32_t device;           /* CUDA device ordinal */
+    int64_t n_envs;           /* independent environments stepped in lock step */
+    int32_t history_len;      /* --history-len, network_sim.py:347 (default 10) */
+    int32_t n_features;       /* --input-features, network_sim.py:348-351 (default 3) */
+    int32_t feature_ids[PCC_MAX_FEATURES];
+    int32_t rng_kind;         /* PCC_RNG_* */
+    int32_t reserved0;
+    int64_t ring_capacity;    /* in-flight records per env (16 B each), power of two; must cover
+                                 packets in flight + packets sent in one MI (see pcc_ring_capacity_for) */
+    pcc_consts consts;
+} pcc_config;
+
+typedef struct pcc_handle_s *pcc_handle;
+
+/* Fills `c` with the reference's constants. */
+void pcc_default_consts(pcc_consts *c);
+
+/* Fills `cfg` with the reference's defaults (history 10, the three default features, Philox,
+ * reference constants); n_envs, device and ring_capacity are left for the caller. */
+void pcc_default_config(pcc_config *cfg);
+
+/* Smallest power-of-two ring capacity that cannot overflow for link parameters within the given
+ * bounds: 1.5 * max_rate * (2*max_delay + max_queue/min_bw), plus the warm-up MIs of reset. */
+int64_t pcc_ring_capacity_for(double max_rate, double min_bw, double max_delay, double max_queue);
+
+/* Bytes of device memory the caller must provide to pcc_create: `state_bytes` for the
+ * structure-of-arrays env state (+ history, RNG state), `ring_bytes` for the in-flight rings.
+ * The two blocks together are a complete checkpoint of the simulator. */
+int pcc_workspace_bytes(const pcc_config *cfg, uint64_t *state_bytes, uint64_t *ring_bytes);
+
+/* Creates a handle over caller-owned device memory (256-byte aligned; e.g. torch.empty(uint8)).
+ * The state block is zero-initialised by this call (asynchronously on the default stream,
+ * followed by a device synchronise). */
+int pcc_create(pcc_handle *out, const pcc_config *cfg, void *state_dev, void *ring_dev);
+void pcc_destroy(pcc_handle h);
+
+/* Attaches a handle to workspaces that already hold a checkpoint (no initialisation). */
+int pcc_attach(pcc_handle *out, const pcc_config *cfg, void *state_dev, void *ring_dev);
+
+/* Seeds the per-env loss-draw streams.  seeds_dev: uint64[n_envs].  mask_dev: uint8[n_envs] or
+ * NULL (= all).  PHILOX: key = seed, draw counter = 0.  MT19937: CPython's random.seed(int). */
+int pcc_seed(pcc_handle h, const uint64_t *seeds_dev, const uint8_t *mask_dev, void *stream);
+
+/* Synchronous transfer of one env's MT19937 state in random.getstate()[1] layout: 624 words +
+ * position (uint32[625], host memory). */
+int pcc_get_mt_state(pcc_handle h, int64_t env, uint32_t *state_host);
+int pcc_set_mt_state(pcc_handle h, int64_t env, const uint32_t *state_host);
+
+/* reset(): builds a fresh link pair + sender for every env selected by mask_dev (NULL = all) and
+ * runs the two discarded warm-up MIs.  Parameter arrays are double[n_envs] / int64[n_envs] on the
+ * device, in the reference's units (bw: packets/s, delay: s, queue: packets, loss: probability,
+ * start_rate: packets/s).  obs_dev (optional): double[n_envs][history_len*n_features]; rows of
+ * unselected envs are left untouched. */
+int pcc_reset(pcc_handle h, const uint8_t *mask_dev, const double *bw_dev, const double *delay_dev,
+              const int64_t *queue_dev, const double *loss_dev, const double *start_rate_dev,
+              double *obs_dev, void *stream);
+
+/* step(): one monitor interval for every env.
+ *   actions_dev  double[n_envs]                        (action[0] of the reference; finite)
+ *   obs_dev      double[n_envs][history_len*n_features] oldest MI first, feature-minor
+ *   reward_dev   double[n_envs]
+ *   done_dev     uint8[n_envs]    steps_taken >= max_steps   (the env is NOT reset automatically)
+ *   counts_dev   int32[n_envs][3] packets sent / acked / lost in this MI      (optional)
+ *   info_dev     double[n_envs][PCC_INFO_WIDTH]                               (optional) */
+int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *reward_dev,
+             uint8_t *done_dev, int32_t *counts_dev, double *info_dev, void *stream);
+
+/* The same step through HOST buffers (the call a gym-style user makes): copies actions to the
+ * device, steps, copies obs / reward / done (/ counts) back and synchronises the stream.  Host
+ * buffers should be page-locked for full copy bandwidth. */
+int pcc_step_host(pcc_handle h, const double *actions_host, double *obs_host, double *reward_host,
+                  uint8_t *done_host, int32_t *counts_host, void *stream);
+
+/* Synchronises `stream` and reports sticky device-side errors (PCC_EOVERFLOW). */
+int pcc_check(pcc_handle h, void *stream);
+
+/* Copies one per-env scalar column of the state to dst_dev (double[n_envs]); names: "cur_time",
+ * "run_dur", "rate", "next_send", "queue_delay", "conn_min", "bw", "delay", "loss", "max_queue_delay",
+ * "episode_return" (reward_sum of the running episode, network_sim.py:443) and "last_episode_return".
+ * For tests and checkpoints of derived quantities. */
+int pcc_get_column(pcc_handle h, const char *name, double *dst_dev, void *stream);
+
+/* Number of kernel launches issued by this handle so far (pcc_step = 1 launch). */
+int64_t pcc_launch_count(pcc_handle h);
+
+const char *pcc_last_error(void);
+int pcc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCC_B200_H */

@@ -72,7 +72,7 @@ def lib():
     L.pcco_np_mean.argtypes = [pd, l]
     L.pcco_batch_run.restype = d
     L.pcco_batch_run.argtypes = [l, l, i, i, pi, i, pd, pd, pl, pd, pd,
-                                 C.POINTER(C.c_uint64), pd, pd, pd, pl]
+                                 C.POINTER(C.c_uint64), pd, pd, pd, pl, pd, pi]
     _lib = L
     return L
 
@@ -169,7 +169,7 @@ class OracleEnv(object):
 
 
 def batch_run(bw, lat, queue, loss, start_rate, seeds, n_steps, actions=None, n_threads=1,
-              history_len=10, features=DEFAULT_FEATURES):
+              history_len=10, features=DEFAULT_FEATURES, trajectories=False):
     """Reset + n_steps steps for every env on n_threads host threads (Philox streams).
     Returns dict(seconds, obs[N,H*F] of the last step, reward_sum[N], count_sum[N,3])."""
     L = lib()
@@ -185,10 +185,56 @@ def batch_run(bw, lat, queue, loss, start_rate, seeds, n_steps, actions=None, n_
     if actions is not None:
         actions = f64(actions)
         assert actions.shape == (n_steps, n)
+    rt = np.zeros((n_steps, n)) if trajectories else None
+    ct = np.zeros((n_steps, n, 3), dtype=np.int32) if trajectories else None
     secs = L.pcco_batch_run(n, n_steps, n_threads, history_len, _p(ids, C.c_int), len(ids),
                             _p(bw, C.c_double), _p(lat, C.c_double), _p(queue, C.c_long),
                             _p(loss, C.c_double), _p(start_rate, C.c_double),
                             _p(seeds, C.c_uint64),
                             _p(actions, C.c_double) if actions is not None else None,
-                            _p(obs, C.c_double), _p(rs, C.c_double), _p(cs, C.c_long))
-    return dict(seconds=secs, obs=obs, reward_sum=rs, count_sum=cs)
+                            _p(obs, C.c_double), _p(rs, C.c_double), _p(cs, C.c_long),
+                            _p(rt, C.c_double) if trajectories else None,
+                            _p(ct, C.c_int) if trajectories else None)
+    return dict(seconds=secs, obs=obs, reward_sum=rs, count_sum=cs, reward_traj=rt, count_traj=ct)
+
+
+class OracleBatch(object):
+    """Persistent batch of oracle envs on host threads (the CPU arm of bench.py)."""
+
+    def __init__(self, seeds, history_len=10, features=DEFAULT_FEATURES, n_threads=1):
+        L = self.L = lib()
+        L.pcco_batch_create.restype = C.c_void_p
+        L.pcco_batch_create.argtypes = [C.c_long, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_uint64)]
+        L.pcco_batch_destroy.argtypes = [C.c_void_p]
+        vp = C.c_void_p
+        L.pcco_batch_reset.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+        L.pcco_batch_step.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int]
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        ids = np.asarray(feature_ids(features), dtype=np.int32)
+        self.n, self.hf, self.n_threads = len(seeds), history_len * len(ids), n_threads
+        self.b = L.pcco_batch_create(self.n, history_len, _p(ids, C.c_int), len(ids), _p(seeds, C.c_uint64))
+        self.obs = np.zeros((self.n, self.hf))
+        self.reward = np.zeros(self.n)
+        self.done = np.zeros(self.n, dtype=np.uint8)
+        self.counts = np.zeros((self.n, 3), dtype=np.int32)
+
+    def __del__(self):
+        if getattr(self, "b", None):
+            self.L.pcco_batch_destroy(self.b)
+            self.b = None
+
+    def reset(self, params, mask=None):
+        v = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        bw, lat, loss, sr = (v(params[k], np.float64) for k in ("bw", "lat", "loss", "start_rate"))
+        q = v(params["queue"], np.int64)
+        m = None if mask is None else v(mask, np.uint8)
+        self.L.pcco_batch_reset(self.b, m.ctypes.data if m is not None else None, bw.ctypes.data, lat.ctypes.data,
+                                q.ctypes.data, loss.ctypes.data, sr.ctypes.data, self.obs.ctypes.data,
+                                self.n_threads)
+        return self.obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        self.L.pcco_batch_step(self.b, a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data,
+                               self.done.ctypes.data, self.counts.ctypes.data, self.n_threads)
+        return self.obs, self.reward, self.done, self.counts

@@ -1,0 +1,24 @@
+"""pcc_rl_b200 -- B200-native batched congestion-control simulator: the gym hot path of
+PCCproject/PCC-RL (network_sim.py + sender_obs.py) as one hand-written sm_100a CUDA kernel
+behind the reference's gym.Env surface.  Import name: `pcc_rl_b200` (this directory is
+`pcc-rl_b200/`; the alias module pcc_rl_b200.py at the repo root maps the import name to it)."""
+from . import build as build_mod
+from . import _lib, sender_obs, params
+from .params import LinkRanges, sample_link_params
+from .batch_env import PccBatchEnv
+
+
+def build(force=False, verbose=False):
+    """Compiles libpcc_b200.so for sm_100a with nvcc (no GPU needed)."""
+    return build_mod.build(force=force, verbose=verbose)
+
+
+def load_library():
+    return _lib.load()
+
+
+def __getattr__(name):  # lazy: importing network_sim touches gym registration
+    if name in ("SimulatedNetworkEnv", "network_sim"):
+        from . import network_sim as ns
+        return ns if name == "network_sim" else ns.SimulatedNetworkEnv
+    raise AttributeError(name)

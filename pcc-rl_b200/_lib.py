@@ -1,0 +1,90 @@
+"""ctypes binding of include/pcc_b200.h (libpcc_b200.so).  No CPU fallback: if the library or a
+CUDA device is missing, loading / pcc_create fails loudly."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+PCC_ABI_VERSION = 1
+PCC_OK, PCC_EINVAL, PCC_ECUDA, PCC_EOVERFLOW, PCC_ENODEV = 0, -1, -2, -3, -4
+PCC_RNG_MT19937, PCC_RNG_PHILOX = 0, 1
+PCC_MAX_FEATURES = 12
+PCC_INFO_WIDTH = 12
+
+
+class PccConsts(C.Structure):
+    _fields_ = [("max_rate", C.c_double), ("min_rate", C.c_double), ("delta_scale", C.c_double),
+                ("reward_scale", C.c_double), ("max_steps", C.c_int32), ("bytes_per_packet", C.c_int32)]
+
+
+class PccConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_envs", C.c_int64),
+                ("history_len", C.c_int32), ("n_features", C.c_int32),
+                ("feature_ids", C.c_int32 * PCC_MAX_FEATURES), ("rng_kind", C.c_int32),
+                ("reserved0", C.c_int32), ("ring_capacity", C.c_int64), ("consts", PccConsts)]
+
+
+class PccError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libpcc_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+# every symbol include/pcc_b200.h declares
+EXPORTS = ["pcc_default_consts", "pcc_default_config", "pcc_ring_capacity_for", "pcc_workspace_bytes",
+           "pcc_create", "pcc_destroy", "pcc_attach", "pcc_seed", "pcc_get_mt_state", "pcc_set_mt_state",
+           "pcc_reset", "pcc_step", "pcc_step_host", "pcc_check", "pcc_get_column", "pcc_launch_count",
+           "pcc_last_error", "pcc_abi_version"]
+
+_lib = None
+
+
+def load(rebuild_if_stale=True):
+    """Loads libpcc_b200.so (building it with nvcc first if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if rebuild_if_stale and not _build.up_to_date():
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    if not os.path.exists(path):
+        raise RuntimeError("libpcc_b200.so is missing (run `python __graft_entry__.py build`); "
+                           "there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, u8p, dp = C.c_void_p, C.c_void_p, C.c_void_p
+    L.pcc_default_consts.argtypes = [C.POINTER(PccConsts)]
+    L.pcc_default_consts.restype = None
+    L.pcc_default_config.argtypes = [C.POINTER(PccConfig)]
+    L.pcc_default_config.restype = None
+    L.pcc_ring_capacity_for.argtypes = [C.c_double] * 4
+    L.pcc_ring_capacity_for.restype = C.c_int64
+    L.pcc_workspace_bytes.argtypes = [C.POINTER(PccConfig), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.pcc_create.argtypes = [C.POINTER(vp), C.POINTER(PccConfig), vp, vp]
+    L.pcc_attach.argtypes = [C.POINTER(vp), C.POINTER(PccConfig), vp, vp]
+    L.pcc_destroy.argtypes = [vp]
+    L.pcc_destroy.restype = None
+    L.pcc_seed.argtypes = [vp, vp, u8p, vp]
+    L.pcc_get_mt_state.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32)]
+    L.pcc_set_mt_state.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32)]
+    L.pcc_reset.argtypes = [vp, u8p, dp, dp, vp, dp, dp, dp, vp]
+    L.pcc_step.argtypes = [vp, dp, dp, dp, u8p, vp, dp, vp]
+    L.pcc_step_host.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
+    L.pcc_check.argtypes = [vp, vp]
+    L.pcc_get_column.argtypes = [vp, C.c_char_p, dp, vp]
+    L.pcc_launch_count.argtypes = [vp]
+    L.pcc_launch_count.restype = C.c_int64
+    L.pcc_last_error.restype = C.c_char_p
+    L.pcc_abi_version.restype = C.c_int
+    if L.pcc_abi_version() != PCC_ABI_VERSION:
+        raise RuntimeError("libpcc_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise PccError(rc, load().pcc_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,41 @@
+"""Builds libpcc_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+SRC = os.path.join(PKG_DIR, "csrc", "pcc_b200.cu")
+DEPS = [SRC, os.path.join(PKG_DIR, "csrc", "pcc_core.cuh"), os.path.join(ROOT, "include", "pcc_b200.h")]
+LIB = os.path.join(PKG_DIR, "libpcc_b200.so")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-fmad=false",  # REQUIRED for parity: every binary64 op rounds separately
+              "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include")]
+
+
+def nvcc_path():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found: cannot build libpcc_b200.so")
+    return p
+
+
+def up_to_date():
+    return os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout)
+    if verbose:
+        print(r.stdout)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,562 @@
+// pcc_b200.cu -- libpcc_b200.so: CUDA kernels (sm_100a) + the C ABI of include/pcc_b200.h.
+//
+// Build (pcc-rl_b200/build.py):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
+//        -Xcompiler -fPIC -shared -Iinclude -o pcc-rl_b200/libpcc_b200.so pcc-rl_b200/csrc/pcc_b200.cu
+// -fmad=false is REQUIRED: the reference rounds every binary64 operation separately and the
+// integer packet counts depend on float comparisons.
+//
+// Data layout in HBM (all owned by the caller, see pcc_workspace_bytes):
+//   state block : structure-of-arrays, one column of n_envs elements per scalar of
+//                 pcc::EnvState (coalesced: lane == env), then the MI-feature history
+//                 hist[slot][feature][env] (a ring over `slot` with a handle-global head, so
+//                 a step writes one new row instead of shifting H rows), then (MT19937 mode
+//                 only) uint32[n_envs][625] generator states, then a small meta block.
+//   ring block  : Rec[n_envs][ring_capacity], 16 B per in-flight packet (arrival time at
+//                 hop 1, +-link-0 latency), addressed by monotonically increasing u32 cursors.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "pcc_b200.h"
+#include "pcc_core.cuh"
+
+using namespace pcc;
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess) return fail(PCC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// device-side view of the workspaces
+// ---------------------------------------------------------------------------------------
+struct DevState {
+    double *d_bw, *bw, *dl, *lr, *max_qd, *qd, *t_upd, *rate, *next_send, *cur_time, *run_dur, *conn_min;
+    double *ret_acc, *ret_last;  // reward_sum of the running / of the last finished episode (network_sim.py:390,443,483)
+    unsigned long long *seed, *draws;
+    uint32_t *tail, *h1, *h2;
+    int32_t *steps;
+    double *hist;              // [H][F][n]
+    uint32_t *mt;              // [n][625] or null
+    unsigned long long *meta;  // [0] steps issued (history head), [1] overflow count, [2] first overflowed env + 1
+    Rec *rings;                // [n][cap]
+    uint32_t cap;
+    int64_t n;
+    int32_t H, F;
+    int32_t ids[PCC_MAX_FEATURES];
+    int32_t need_inc;
+    Consts c;
+};
+
+enum { META_HEAD = 0, META_OVF_COUNT = 1, META_OVF_ENV = 2, META_WORDS = 8 };
+
+struct DevRing {
+    Rec *base;
+    uint32_t mask;
+    __device__ __forceinline__ uint32_t capacity() const { return mask + 1u; }
+    __device__ __forceinline__ Rec load(uint32_t i) const
+    {
+        const double2 v = *reinterpret_cast<const double2 *>(base + (i & mask));
+        Rec r; r.a = v.x; r.l = v.y;
+        return r;
+    }
+    __device__ __forceinline__ void store(uint32_t i, Rec r)
+    {
+        *reinterpret_cast<double2 *>(base + (i & mask)) = make_double2(r.a, r.l);
+    }
+    __device__ __forceinline__ void store_a(uint32_t i, double a) { base[i & mask].a = a; }
+};
+
+__device__ __forceinline__ void load_env(const DevState &p, int64_t e, EnvState &s)
+{
+    s.d_bw = p.d_bw[e]; s.dl = p.dl[e]; s.lr = p.lr[e]; s.max_qd = p.max_qd[e];
+    s.qd = p.qd[e]; s.t_upd = p.t_upd[e]; s.rate = p.rate[e]; s.next_send = p.next_send[e];
+    s.cur_time = p.cur_time[e]; s.run_dur = p.run_dur[e]; s.conn_min = p.conn_min[e];
+    s.tail = p.tail[e]; s.h1 = p.h1[e]; s.h2 = p.h2[e]; s.steps = p.steps[e];
+}
+__device__ __forceinline__ void store_env_dynamic(const DevState &p, int64_t e, const EnvState &s)
+{
+    p.qd[e] = s.qd; p.t_upd[e] = s.t_upd; p.rate[e] = s.rate; p.next_send[e] = s.next_send;
+    p.cur_time[e] = s.cur_time; p.run_dur[e] = s.run_dur; p.conn_min[e] = s.conn_min;
+    p.tail[e] = s.tail; p.h1[e] = s.h1; p.h2[e] = s.h2; p.steps[e] = s.steps;
+}
+__device__ __forceinline__ void flag_overflow(const DevState &p, int64_t e)
+{
+    atomicAdd(&p.meta[META_OVF_COUNT], 1ull);
+    atomicCAS(&p.meta[META_OVF_ENV], 0ull, (unsigned long long)(e + 1));
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels (v1: one thread per env, every phase scalar; see DESIGN.md for the roofline)
+// ---------------------------------------------------------------------------------------
+template <int RNG>
+__global__ void pcc_step_kernel(DevState p, unsigned long long head_step,
+                                const double *__restrict__ actions, double *__restrict__ obs,
+                                double *__restrict__ reward, uint8_t *__restrict__ done,
+                                int32_t *__restrict__ counts, double *__restrict__ info)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) p.meta[META_HEAD] = head_step + 1ull;
+    if (e >= p.n) return;
+    EnvState s;
+    load_env(p, e, s);
+    DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
+    StepOut o;
+    const double action = actions[e];
+    if (RNG == PCC_RNG_PHILOX) {
+        PhiloxRng rng;
+        rng.init(p.seed[e], p.draws[e]);
+        step_env(s, ring, rng, action, p.c, p.need_inc != 0, o);
+        p.draws[e] = rng.draws;
+    } else {
+        Mt19937Rng rng;
+        rng.init(p.mt + (size_t)e * 625);
+        step_env(s, ring, rng, action, p.c, p.need_inc != 0, o);
+    }
+    store_env_dynamic(p, e, s);
+    if (o.mi.overflow) flag_overflow(p, e);
+
+    // history ring: the new row replaces the oldest slot; obs = oldest -> newest
+    const int H = p.H, F = p.F;
+    const int slot_new = (int)(head_step % (unsigned long long)H);
+    double row[PCC_MAX_FEATURES];
+#pragma unroll
+    for (int f = 0; f < PCC_MAX_FEATURES; f++)
+        if (f < F) row[f] = metric_value(o.st, p.ids[f]);
+    double *ob = obs + (size_t)e * (size_t)(H * F);
+    for (int h = 0; h < H - 1; h++) {
+        int slot = slot_new + 1 + h;
+        if (slot >= H) slot -= H;
+        for (int f = 0; f < F; f++) ob[h * F + f] = p.hist[((size_t)slot * F + f) * p.n + e];
+    }
+#pragma unroll
+    for (int f = 0; f < PCC_MAX_FEATURES; f++)
+        if (f < F) {
+            ob[(H - 1) * F + f] = row[f];
+            p.hist[((size_t)slot_new * F + f) * p.n + e] = row[f];
+        }
+    reward[e] = o.st.reward;
+    done[e] = o.done ? 1 : 0;
+    {
+        const double acc = p.ret_acc[e] + o.st.reward;   // self.reward_sum += reward  (:443)
+        p.ret_acc[e] = acc;
+        if (o.done) p.ret_last[e] = acc;
+    }
+    if (counts) {
+        counts[3 * e + 0] = o.mi.sent; counts[3 * e + 1] = o.mi.acked; counts[3 * e + 2] = o.mi.lost;
+    }
+    if (info) {
+        double *q = info + (size_t)e * PCC_INFO_WIDTH;
+        q[0] = o.st.send_rate; q[1] = o.st.recv_rate; q[2] = o.st.avg_lat; q[3] = o.st.loss_ratio;
+        q[4] = o.st.lat_infl; q[5] = o.st.lat_ratio; q[6] = o.st.send_ratio; q[7] = o.st.dur;
+        q[8] = s.cur_time; q[9] = s.rate; q[10] = s.run_dur; q[11] = s.conn_min;
+    }
+}
+
+template <int RNG>
+__global__ void pcc_reset_kernel(DevState p, const uint8_t *__restrict__ mask,
+                                 const double *__restrict__ bw, const double *__restrict__ delay,
+                                 const long long *__restrict__ queue, const double *__restrict__ loss,
+                                 const double *__restrict__ start_rate, double *__restrict__ obs)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    if (mask && !mask[e]) return;
+    EnvState s;
+    s.tail = p.tail[e];
+    DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
+    bool ovf;
+    if (RNG == PCC_RNG_PHILOX) {
+        PhiloxRng rng;
+        rng.init(p.seed[e], p.draws[e]);
+        ovf = reset_env(s, ring, rng, bw[e], delay[e], loss[e], (int64_t)queue[e], start_rate[e]);
+        p.draws[e] = rng.draws;
+    } else {
+        Mt19937Rng rng;
+        rng.init(p.mt + (size_t)e * 625);
+        ovf = reset_env(s, ring, rng, bw[e], delay[e], loss[e], (int64_t)queue[e], start_rate[e]);
+    }
+    p.d_bw[e] = s.d_bw; p.bw[e] = bw[e]; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd;
+    store_env_dynamic(p, e, s);
+    p.ret_acc[e] = 0.0;                                 // self.reward_sum = 0.0  (:483)
+    if (ovf) flag_overflow(p, e);
+    const int H = p.H, F = p.F;
+    for (int h = 0; h < H; h++)
+        for (int f = 0; f < F; f++) {
+            double v = metric_empty(p.ids[f]);
+            p.hist[((size_t)h * F + f) * p.n + e] = v;
+            if (obs) obs[(size_t)e * (size_t)(H * F) + h * F + f] = v;
+        }
+}
+
+__global__ void pcc_seed_philox_kernel(DevState p, const unsigned long long *__restrict__ seeds,
+                                       const uint8_t *__restrict__ mask)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n || (mask && !mask[e])) return;
+    p.seed[e] = seeds[e];
+    p.draws[e] = 0ull;
+}
+
+// CPython random.seed(int): init_by_array over the 32-bit limbs of the (non-negative) seed.
+__global__ void pcc_seed_mt_kernel(DevState p, const unsigned long long *__restrict__ seeds,
+                                   const uint8_t *__restrict__ mask)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n || (mask && !mask[e])) return;
+    uint32_t *mt = p.mt + (size_t)e * 625;
+    const unsigned long long sd = seeds[e];
+    const uint32_t key[2] = {(uint32_t)sd, (uint32_t)(sd >> 32)};
+    const int len = key[1] ? 2 : 1;
+    mt[0] = 19650218u;
+    for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1, j = 0;
+    for (int k = 624; k; k--) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        i++; j++;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+        if (j >= len) j = 0;
+    }
+    for (int k = 623; k; k--) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        i++;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+    mt[624] = 624u;
+    p.seed[e] = sd;
+    p.draws[e] = 0ull;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct pcc_handle_s {
+    pcc_config cfg;
+    DevState d;
+    unsigned long long head;  // steps issued so far (history ring head)
+    int64_t launches;
+    int block;
+    // staging for pcc_step_host
+    double *st_actions, *st_obs, *st_reward;
+    uint8_t *st_done;
+    int32_t *st_counts;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Layout {
+    size_t off_d[14], off_u64[2], off_u32[4], off_hist, off_mt, off_meta, total;
+};
+
+static Layout make_layout(const pcc_config *c)
+{
+    Layout L;
+    size_t o = 0, n = (size_t)c->n_envs;
+    for (int i = 0; i < 14; i++) { L.off_d[i] = o; o = align_up(o + 8 * n); }
+    for (int i = 0; i < 2; i++) { L.off_u64[i] = o; o = align_up(o + 8 * n); }
+    for (int i = 0; i < 4; i++) { L.off_u32[i] = o; o = align_up(o + 4 * n); }
+    L.off_hist = o; o = align_up(o + 8 * n * (size_t)c->history_len * (size_t)c->n_features);
+    L.off_mt = o;
+    if (c->rng_kind == PCC_RNG_MT19937) o = align_up(o + 4 * n * 625);
+    L.off_meta = o; o = align_up(o + 8 * META_WORDS);
+    L.total = o;
+    return L;
+}
+
+static int validate(const pcc_config *c)
+{
+    if (!c) return fail(PCC_EINVAL, "null config");
+    if (c->abi_version != PCC_ABI_VERSION) return fail(PCC_EINVAL, "abi_version mismatch");
+    if (c->n_envs < 1 || c->n_envs > (int64_t)1 << 31) return fail(PCC_EINVAL, "n_envs out of range");
+    if (c->history_len < 1 || c->history_len > PCC_MAX_HISTORY) return fail(PCC_EINVAL, "history_len out of range");
+    if (c->n_features < 1 || c->n_features > PCC_MAX_FEATURES) return fail(PCC_EINVAL, "n_features out of range");
+    for (int i = 0; i < c->n_features; i++)
+        if (c->feature_ids[i] < 0 || c->feature_ids[i] >= PCC_N_METRICS) return fail(PCC_EINVAL, "bad feature id");
+    if (c->rng_kind != PCC_RNG_MT19937 && c->rng_kind != PCC_RNG_PHILOX) return fail(PCC_EINVAL, "bad rng_kind");
+    if (c->ring_capacity < 16 || c->ring_capacity > ((int64_t)1 << 30) || (c->ring_capacity & (c->ring_capacity - 1)))
+        return fail(PCC_EINVAL, "ring_capacity must be a power of two in [16, 2^30]");
+    if (!(c->consts.max_rate > 0) || !(c->consts.min_rate > 0) || c->consts.max_steps < 1 || c->consts.bytes_per_packet < 1)
+        return fail(PCC_EINVAL, "bad consts");
+    return PCC_OK;
+}
+
+extern "C" {
+
+const char *pcc_last_error(void) { return g_err; }
+int pcc_abi_version(void) { return PCC_ABI_VERSION; }
+
+void pcc_default_consts(pcc_consts *c)
+{
+    c->max_rate = 1000.0; c->min_rate = 40.0; c->delta_scale = 0.025; c->reward_scale = 0.001;
+    c->max_steps = 400; c->bytes_per_packet = 1500;
+}
+
+void pcc_default_config(pcc_config *cfg)
+{
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = PCC_ABI_VERSION;
+    cfg->history_len = 10;
+    cfg->n_features = 3;
+    cfg->feature_ids[0] = PCC_M_SENT_LATENCY_INFLATION;
+    cfg->feature_ids[1] = PCC_M_LATENCY_RATIO;
+    cfg->feature_ids[2] = PCC_M_SEND_RATIO;
+    cfg->rng_kind = PCC_RNG_PHILOX;
+    pcc_default_consts(&cfg->consts);
+}
+
+int64_t pcc_ring_capacity_for(double max_rate, double min_bw, double max_delay, double max_queue)
+{
+    // packets in flight <= max_rate * max RTT; an MI lasts at most max(0.5 * max RTT, 3 * delay)
+    double rtt = 2.0 * max_delay + max_queue / min_bw;
+    double mi = 0.5 * rtt > 3.0 * max_delay ? 0.5 * rtt : 3.0 * max_delay;
+    double need = max_rate * (rtt + mi) + 64.0;
+    int64_t cap = 16;
+    while ((double)cap < need && cap < ((int64_t)1 << 30)) cap <<= 1;
+    return cap;
+}
+
+int pcc_workspace_bytes(const pcc_config *cfg, uint64_t *state_bytes, uint64_t *ring_bytes)
+{
+    int rc = validate(cfg);
+    if (rc) return rc;
+    Layout L = make_layout(cfg);
+    if (state_bytes) *state_bytes = L.total;
+    if (ring_bytes) *ring_bytes = (uint64_t)cfg->n_envs * (uint64_t)cfg->ring_capacity * sizeof(Rec);
+    return PCC_OK;
+}
+
+static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev, void *ring_dev, bool init)
+{
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!out || !state_dev || !ring_dev) return fail(PCC_EINVAL, "null pointer");
+    if (((uintptr_t)state_dev & 255) || ((uintptr_t)ring_dev & 15)) return fail(PCC_EINVAL, "workspace misaligned");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(PCC_ENODEV, "no CUDA device: libpcc_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(PCC_EINVAL, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    pcc_handle h = new (std::nothrow) pcc_handle_s();
+    if (!h) return fail(PCC_EINVAL, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    Layout L = make_layout(cfg);
+    char *b = (char *)state_dev;
+    DevState &d = h->d;
+    double **dcols[14] = {&d.d_bw, &d.bw, &d.dl, &d.lr, &d.max_qd, &d.qd, &d.t_upd, &d.rate,
+                          &d.next_send, &d.cur_time, &d.run_dur, &d.conn_min, &d.ret_acc, &d.ret_last};
+    for (int i = 0; i < 14; i++) *dcols[i] = (double *)(b + L.off_d[i]);
+    d.seed = (unsigned long long *)(b + L.off_u64[0]);
+    d.draws = (unsigned long long *)(b + L.off_u64[1]);
+    d.tail = (uint32_t *)(b + L.off_u32[0]);
+    d.h1 = (uint32_t *)(b + L.off_u32[1]);
+    d.h2 = (uint32_t *)(b + L.off_u32[2]);
+    d.steps = (int32_t *)(b + L.off_u32[3]);
+    d.hist = (double *)(b + L.off_hist);
+    d.mt = cfg->rng_kind == PCC_RNG_MT19937 ? (uint32_t *)(b + L.off_mt) : nullptr;
+    d.meta = (unsigned long long *)(b + L.off_meta);
+    d.rings = (Rec *)ring_dev;
+    d.cap = (uint32_t)cfg->ring_capacity;
+    d.n = cfg->n_envs;
+    d.H = cfg->history_len;
+    d.F = cfg->n_features;
+    for (int i = 0; i < PCC_MAX_FEATURES; i++) d.ids[i] = i < cfg->n_features ? cfg->feature_ids[i] : 0;
+    d.need_inc = features_need_increase(d.ids, d.F) ? 1 : 0;
+    d.c.max_rate = cfg->consts.max_rate; d.c.min_rate = cfg->consts.min_rate;
+    d.c.delta_scale = cfg->consts.delta_scale; d.c.reward_scale = cfg->consts.reward_scale;
+    d.c.max_steps = cfg->consts.max_steps; d.c.bytes_per_packet = cfg->consts.bytes_per_packet;
+    const char *blk = getenv("PCC_B200_BLOCK");
+    h->block = blk ? atoi(blk) : 32;
+    if (h->block < 32 || h->block > 1024 || (h->block & 31)) h->block = 32;
+    if (init) {
+        cudaError_t e = cudaMemset(state_dev, 0, L.total);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "state init: %s", cudaGetErrorString(e)); }
+        h->head = 0;
+    } else {
+        unsigned long long head = 0;
+        cudaError_t e = cudaMemcpy(&head, d.meta + META_HEAD, 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "attach: %s", cudaGetErrorString(e)); }
+        h->head = head;
+    }
+    *out = h;
+    return PCC_OK;
+}
+
+int pcc_create(pcc_handle *out, const pcc_config *cfg, void *state_dev, void *ring_dev)
+{
+    return build_handle(out, cfg, state_dev, ring_dev, true);
+}
+int pcc_attach(pcc_handle *out, const pcc_config *cfg, void *state_dev, void *ring_dev)
+{
+    return build_handle(out, cfg, state_dev, ring_dev, false);
+}
+
+void pcc_destroy(pcc_handle h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_reward);
+    cudaFree(h->st_done); cudaFree(h->st_counts);
+    delete h;
+}
+
+static inline unsigned grid_for(pcc_handle h) { return (unsigned)((h->cfg.n_envs + h->block - 1) / h->block); }
+
+int pcc_seed(pcc_handle h, const uint64_t *seeds_dev, const uint8_t *mask_dev, void *stream)
+{
+    if (!h || !seeds_dev) return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->cfg.rng_kind == PCC_RNG_PHILOX)
+        pcc_seed_philox_kernel<<<grid_for(h), h->block, 0, st>>>(h->d, (const unsigned long long *)seeds_dev, mask_dev);
+    else
+        pcc_seed_mt_kernel<<<grid_for(h), h->block, 0, st>>>(h->d, (const unsigned long long *)seeds_dev, mask_dev);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PCC_OK;
+}
+
+int pcc_get_mt_state(pcc_handle h, int64_t env, uint32_t *state_host)
+{
+    if (!h || !state_host) return fail(PCC_EINVAL, "null pointer");
+    if (h->cfg.rng_kind != PCC_RNG_MT19937) return fail(PCC_EINVAL, "handle is not in MT19937 mode");
+    if (env < 0 || env >= h->cfg.n_envs) return fail(PCC_EINVAL, "env out of range");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(state_host, h->d.mt + (size_t)env * 625, 625 * 4, cudaMemcpyDeviceToHost));
+    return PCC_OK;
+}
+
+int pcc_set_mt_state(pcc_handle h, int64_t env, const uint32_t *state_host)
+{
+    if (!h || !state_host) return fail(PCC_EINVAL, "null pointer");
+    if (h->cfg.rng_kind != PCC_RNG_MT19937) return fail(PCC_EINVAL, "handle is not in MT19937 mode");
+    if (env < 0 || env >= h->cfg.n_envs) return fail(PCC_EINVAL, "env out of range");
+    if (state_host[624] > 624u) return fail(PCC_EINVAL, "bad MT position");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(h->d.mt + (size_t)env * 625, state_host, 625 * 4, cudaMemcpyHostToDevice));
+    return PCC_OK;
+}
+
+int pcc_reset(pcc_handle h, const uint8_t *mask_dev, const double *bw_dev, const double *delay_dev,
+              const int64_t *queue_dev, const double *loss_dev, const double *start_rate_dev,
+              double *obs_dev, void *stream)
+{
+    if (!h || !bw_dev || !delay_dev || !queue_dev || !loss_dev || !start_rate_dev)
+        return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->cfg.rng_kind == PCC_RNG_PHILOX)
+        pcc_reset_kernel<PCC_RNG_PHILOX><<<grid_for(h), h->block, 0, st>>>(
+            h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rate_dev, obs_dev);
+    else
+        pcc_reset_kernel<PCC_RNG_MT19937><<<grid_for(h), h->block, 0, st>>>(
+            h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rate_dev, obs_dev);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PCC_OK;
+}
+
+int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *reward_dev,
+             uint8_t *done_dev, int32_t *counts_dev, double *info_dev, void *stream)
+{
+    if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->cfg.rng_kind == PCC_RNG_PHILOX)
+        pcc_step_kernel<PCC_RNG_PHILOX><<<grid_for(h), h->block, 0, st>>>(
+            h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
+    else
+        pcc_step_kernel<PCC_RNG_MT19937><<<grid_for(h), h->block, 0, st>>>(
+            h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
+    h->head++;
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PCC_OK;
+}
+
+int pcc_step_host(pcc_handle h, const double *actions_host, double *obs_host, double *reward_host,
+                  uint8_t *done_host, int32_t *counts_host, void *stream)
+{
+    if (!h || !actions_host || !obs_host || !reward_host || !done_host) return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.n_envs, hf = (size_t)h->cfg.history_len * h->cfg.n_features;
+    if (!h->st_actions) {
+        CUDA_TRY(cudaMalloc(&h->st_actions, 8 * n));
+        CUDA_TRY(cudaMalloc(&h->st_obs, 8 * n * hf));
+        CUDA_TRY(cudaMalloc(&h->st_reward, 8 * n));
+        CUDA_TRY(cudaMalloc(&h->st_done, n));
+        CUDA_TRY(cudaMalloc(&h->st_counts, 12 * n));
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->st_actions, actions_host, 8 * n, cudaMemcpyHostToDevice, st));
+    int rc = pcc_step(h, h->st_actions, h->st_obs, h->st_reward, h->st_done,
+                      counts_host ? h->st_counts : nullptr, nullptr, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(obs_host, h->st_obs, 8 * n * hf, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(reward_host, h->st_reward, 8 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(done_host, h->st_done, n, cudaMemcpyDeviceToHost, st));
+    if (counts_host) CUDA_TRY(cudaMemcpyAsync(counts_host, h->st_counts, 12 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCC_OK;
+}
+
+int pcc_check(pcc_handle h, void *stream)
+{
+    if (!h) return fail(PCC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned long long meta[META_WORDS];
+    CUDA_TRY(cudaMemcpy(meta, h->d.meta, sizeof(meta), cudaMemcpyDeviceToHost));
+    if (meta[META_OVF_COUNT]) {
+        snprintf(g_err, sizeof(g_err),
+                 "in-flight ring overflow in %llu env-MI(s), first env %llu: ring_capacity %lld is too small "
+                 "for these link parameters (see pcc_ring_capacity_for)",
+                 meta[META_OVF_COUNT], meta[META_OVF_ENV] - 1, (long long)h->cfg.ring_capacity);
+        return PCC_EOVERFLOW;
+    }
+    return PCC_OK;
+}
+
+int pcc_get_column(pcc_handle h, const char *name, double *dst_dev, void *stream)
+{
+    if (!h || !name || !dst_dev) return fail(PCC_EINVAL, "null pointer");
+    const DevState &d = h->d;
+    const double *src = nullptr;
+    if (!strcmp(name, "cur_time")) src = d.cur_time;
+    else if (!strcmp(name, "run_dur")) src = d.run_dur;
+    else if (!strcmp(name, "rate")) src = d.rate;
+    else if (!strcmp(name, "next_send")) src = d.next_send;
+    else if (!strcmp(name, "queue_delay")) src = d.qd;
+    else if (!strcmp(name, "conn_min")) src = d.conn_min;
+    else if (!strcmp(name, "bw")) src = d.bw;
+    else if (!strcmp(name, "delay")) src = d.dl;
+    else if (!strcmp(name, "loss")) src = d.lr;
+    else if (!strcmp(name, "max_queue_delay")) src = d.max_qd;
+    else if (!strcmp(name, "episode_return")) src = d.ret_acc;
+    else if (!strcmp(name, "last_episode_return")) src = d.ret_last;
+    else return fail(PCC_EINVAL, "unknown column %s", name);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(dst_dev, src, 8 * (size_t)h->cfg.n_envs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PCC_OK;
+}
+
+int64_t pcc_launch_count(pcc_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+"""The product's per-env MI code (pcc_core.cuh), compiled for the host, against (a) the golden
+outputs of the unmodified reference and (b) the heap-based oracle on randomized episodes.
+This is where the three-cursor streaming algorithm and its tie handling are proven before
+the same header is compiled into the CUDA kernels."""
+import numpy as np
+import pytest
+
+import oracle
+from golden_util import assert_step_equal, golden_names, load_golden
+from twin_util import TwinEnv
+
+
+@pytest.mark.parametrize("name", golden_names("mt_"))
+def test_twin_matches_reference_as_shipped(name):
+    g = load_golden(name)
+    o = oracle.OracleEnv()  # only as the host-side MT parameter sampler (random.uniform order)
+    o.seed_mt(g["seed"])
+    o.sample_params()
+    t = TwinEnv(g["history_len"], g["features"])
+    k = 0
+    for ep in range(len(g["ep_params"])):
+        bw, lat, q, loss, rate = o.sample_params()
+        assert (bw, lat, float(q), loss, rate) == tuple(g["ep_params"][ep])
+        t.mt_setstate(o.mt_getstate())
+        obs0 = t.reset(bw, lat, q, loss, rate)
+        assert np.array_equal(obs0, g["ep_obs0"][ep]) and t.cur_time == g["ep_cur_time0"][ep]
+        for _ in range(g["steps_per_episode"]):
+            obs, r, d, c, info = t.step(g["action"][k])
+            assert_step_equal(g, k, obs, r, d, c, t.cur_time, t.run_dur, t.rate, info, name)
+            k += 1
+        o.mt_setstate(t.mt_getstate())
+    assert not t.overflow
+
+
+@pytest.mark.parametrize("name", golden_names("philox_"))
+def test_twin_matches_reference_on_philox_stream(name):
+    g = load_golden(name)
+    t = TwinEnv(g["history_len"], g["features"])
+    t.seed_philox(g["seed"])
+    k = 0
+    for ep in range(len(g["ep_params"])):
+        bw, lat, q, loss, rate = g["ep_params"][ep]
+        obs0 = t.reset(bw, lat, int(q), loss, rate)
+        assert np.array_equal(obs0, g["ep_obs0"][ep]) and t.cur_time == g["ep_cur_time0"][ep]
+        for _ in range(g["steps_per_episode"]):
+            obs, r, d, c, info = t.step(g["action"][k])
+            assert_step_equal(g, k, obs, r, d, c, t.cur_time, t.run_dur, t.rate, info, name)
+            k += 1
+    assert not t.overflow
+
+
+def _lockstep(seed, n_eps, n_steps, sampler, act_sigma, ring_capacity=1 << 16, ring_base=0,
+              features=oracle.DEFAULT_FEATURES):
+    g = np.random.default_rng(seed)
+    o = oracle.OracleEnv(10, features)
+    t = TwinEnv(10, features, ring_capacity)
+    o.seed_philox(seed)
+    t.seed_philox(seed)
+    t.set_ring_cursor(ring_base)
+    steps = 0
+    for ep in range(n_eps):
+        p = sampler(g)
+        a0 = o.reset(*p)
+        b0 = t.reset(*p)
+        assert np.array_equal(a0, b0) and o.cur_time == t.cur_time, (seed, ep)
+        for k in range(n_steps):
+            a = float(g.normal(0, act_sigma)) if act_sigma > 0 else 0.0
+            x = o.step(a)
+            y = t.step(a)
+            ctx = (seed, ep, k, p)
+            assert tuple(x[3]) == tuple(y[3]), ctx
+            assert np.array_equal(x[0], y[0]), ctx
+            assert x[1] == y[1] and x[2] == y[2], ctx
+            assert np.array_equal(x[4], y[4]), ctx
+            assert o.cur_time == t.cur_time and o.run_dur == t.run_dur and o.rate == t.rate, ctx
+            steps += 1
+    assert not t.overflow
+    return steps
+
+
+def default_ranges(g):
+    """create_new_links_and_senders, network_sim.py:455-466 (ICML'19 default ranges)."""
+    bw = g.uniform(100, 500)
+    return (bw, g.uniform(0.05, 0.5), 1 + int(np.exp(g.uniform(0, 8))), g.uniform(0, 0.05),
+            g.uniform(0.3, 1.5) * bw)
+
+
+def nasty_ranges(g):
+    """Heavier loss, overdriven tiny queues, wide bandwidths: maximises ties and clusters."""
+    bw = float(np.exp(g.uniform(np.log(40), np.log(5000))))
+    return (bw, float(np.exp(g.uniform(np.log(0.001), np.log(0.5)))), 1 + int(np.exp(g.uniform(0, 5))),
+            float(g.choice([0.0, 0.01, 0.3, 0.9, 1.0])), float(g.uniform(40, 1000)))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_twin_equals_oracle_default_ranges(seed):
+    _lockstep(1000 + seed, n_eps=3, n_steps=400, sampler=default_ranges, act_sigma=1.0)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_twin_equals_oracle_nasty_ranges(seed):
+    _lockstep(2000 + seed, n_eps=4, n_steps=150, sampler=nasty_ranges, act_sigma=3.0,
+              features="send rate,recv rate,recv dur,send dur,avg latency,loss ratio,"
+                       "ack latency inflation,sent latency inflation,conn min latency,"
+                       "latency increase,latency ratio,send ratio")
+
+
+def test_twin_ring_wraps_u32_and_small_capacity():
+    """Ring positions are u32 counters: run across the 2^32 wrap with a ring of 4096 slots."""
+    small = lambda g: (g.uniform(100, 300), g.uniform(0.05, 0.2), 1 + int(np.exp(g.uniform(0, 4))),
+                       g.uniform(0, 0.05), g.uniform(40, 300))
+    _lockstep(7, n_eps=3, n_steps=400, sampler=small, act_sigma=1.0, ring_capacity=4096,
+              ring_base=2**32 - 20000)
+
+
+def test_twin_reports_ring_overflow():
+    t = TwinEnv(ring_capacity=64)
+    t.seed_philox(1)
+    t.reset(500.0, 0.5, 1000, 0.0, 750.0)
+    assert t.overflow

@@ -1,0 +1,95 @@
+// pcc_twin.cpp -- TEST HARNESS: the product's per-env MI code (pcc-rl_b200/csrc/pcc_core.cuh)
+// compiled for the HOST with g++, one env at a time, so the streaming three-cursor algorithm
+// can be checked against the heap-based oracle in a container without a GPU.  It is not a
+// CPU fallback: nothing in the product loads it.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../pcc-rl_b200/csrc/pcc_core.cuh"
+
+using namespace pcc;
+
+struct HostRing {
+    Rec *buf; uint32_t mask;
+    uint32_t capacity() const { return mask + 1; }
+    Rec load(uint32_t i) const { return buf[i & mask]; }
+    void store(uint32_t i, Rec r) { buf[i & mask] = r; }
+    void store_a(uint32_t i, double a) { buf[i & mask].a = a; }
+};
+
+struct Twin {
+    int H, F; int ids[PCC_MAX_FEATURES];
+    bool need_inc;
+    Consts c;
+    EnvState s;
+    std::vector<Rec> ringbuf;
+    HostRing ring;
+    int rng_kind;  // 0 mt, 1 philox
+    uint32_t mt[625];
+    PhiloxRng ph;
+    std::vector<double> hist;  // [H][F], oldest first
+    bool overflow;
+};
+
+extern "C" {
+
+Twin *twin_create(int history_len, const int *feature_ids, int n_features, int ring_capacity)
+{
+    Twin *t = new Twin();
+    t->H = history_len; t->F = n_features;
+    for (int i = 0; i < n_features; i++) t->ids[i] = feature_ids[i];
+    t->need_inc = features_need_increase(t->ids, t->F);
+    t->c.max_rate = 1000.0; t->c.min_rate = 40.0; t->c.delta_scale = 0.025; t->c.reward_scale = 0.001;
+    t->c.max_steps = 400; t->c.bytes_per_packet = 1500;
+    t->ringbuf.resize(ring_capacity);
+    t->ring.buf = t->ringbuf.data(); t->ring.mask = (uint32_t)ring_capacity - 1;
+    t->rng_kind = 1; t->ph.init(0, 0);
+    t->hist.assign((size_t)history_len * n_features, 0.0);
+    t->overflow = false;
+    memset(&t->s, 0, sizeof(t->s));
+    return t;
+}
+void twin_destroy(Twin *t) { delete t; }
+void twin_seed_philox(Twin *t, uint64_t seed) { t->rng_kind = 1; t->ph.init(seed, 0); }
+void twin_mt_setstate(Twin *t, const uint32_t *st) { t->rng_kind = 0; memcpy(t->mt, st, sizeof(t->mt)); }
+void twin_mt_getstate(Twin *t, uint32_t *st) { memcpy(st, t->mt, sizeof(t->mt)); }
+void twin_set_max_steps(Twin *t, int n) { t->c.max_steps = n; }
+void twin_set_ring_cursor(Twin *t, uint32_t base) { t->s.tail = t->s.h1 = t->s.h2 = base; }
+
+void twin_get_obs(Twin *t, double *obs) { memcpy(obs, t->hist.data(), sizeof(double) * t->hist.size()); }
+
+void twin_reset(Twin *t, double bw, double dl, int64_t queue, double lr, double start_rate)
+{
+    bool ovf;
+    if (t->rng_kind == 0) { Mt19937Rng r; r.init(t->mt); ovf = reset_env(t->s, t->ring, r, bw, dl, lr, queue, start_rate); }
+    else ovf = reset_env(t->s, t->ring, t->ph, bw, dl, lr, queue, start_rate);
+    t->overflow |= ovf;
+    for (int h = 0; h < t->H; h++)
+        for (int f = 0; f < t->F; f++) t->hist[(size_t)h * t->F + f] = metric_empty(t->ids[f]);
+}
+
+// counts[3], info[8] as in the oracle
+void twin_step(Twin *t, double action, double *obs, double *reward, int *done, int64_t *counts, double *info)
+{
+    StepOut o;
+    if (t->rng_kind == 0) { Mt19937Rng r; r.init(t->mt); step_env(t->s, t->ring, r, action, t->c, true, o); }
+    else step_env(t->s, t->ring, t->ph, action, t->c, true, o);
+    t->overflow |= o.mi.overflow;
+    memmove(t->hist.data(), t->hist.data() + t->F, sizeof(double) * (size_t)(t->H - 1) * t->F);
+    for (int f = 0; f < t->F; f++) t->hist[(size_t)(t->H - 1) * t->F + f] = metric_value(o.st, t->ids[f]);
+    if (obs) twin_get_obs(t, obs);
+    *reward = o.st.reward;
+    *done = o.done;
+    if (counts) { counts[0] = o.mi.sent; counts[1] = o.mi.acked; counts[2] = o.mi.lost; }
+    if (info) {
+        info[0] = o.st.send_rate; info[1] = o.st.recv_rate; info[2] = o.st.avg_lat; info[3] = o.st.loss_ratio;
+        info[4] = o.st.lat_infl; info[5] = o.st.lat_ratio; info[6] = o.st.send_ratio; info[7] = o.st.dur;
+    }
+}
+double twin_cur_time(Twin *t) { return t->s.cur_time; }
+double twin_run_dur(Twin *t) { return t->s.run_dur; }
+double twin_rate(Twin *t) { return t->s.rate; }
+int twin_overflow(Twin *t) { return t->overflow; }
+uint32_t twin_inflight(Twin *t) { return t->s.tail - t->s.h2; }
+}
