@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--ring-capacity", type=int, default=None, help="experiment: override the safe ring capacity")
+    ap.add_argument("--only-device-pass", action="store_true", help="experiment: skip the b2b / e2e / cpu passes")
     return ap.parse_args()
 
 
@@ -178,7 +180,7 @@ def main():
 
     def make_env():
         return pcc_rl_b200.PccBatchEnv(n_envs=n, device=dev, seed=args.seed, global_offset=rank * n,
-                                       n_global=n_global, auto_reset=True)
+                                       n_global=n_global, auto_reset=True, ring_capacity=args.ring_capacity)
 
     def barrier():
         if world > 1:
@@ -226,6 +228,11 @@ def main():
     rets = torch.cat(finished) if finished else torch.zeros(0, dtype=torch.float64, device=dev)
     ret_stats = D.gather_episode_returns(rets)   # the path's only collective (NCCL all-gather, a few bytes)
     value = n_global * K / (dev_ms * 1e-3)
+    if args.only_device_pass:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": dev_ms / K, "sent_per_step": g_sent / (n_global * K),
+                              "clocks": clocks}))
+        return
 
     # ---------------- pass 2: back to back, no flush, one bracket around all K steps ----------------
     del env

@@ -18,7 +18,8 @@ def load_library():
 
 
 def __getattr__(name):  # lazy: importing network_sim touches gym registration
-    if name in ("SimulatedNetworkEnv", "network_sim"):
-        from . import network_sim as ns
-        return ns if name == "network_sim" else ns.SimulatedNetworkEnv
+    if name in ("SimulatedNetworkEnv", "network_sim", "distributed"):
+        import importlib
+        mod = importlib.import_module("." + ("distributed" if name == "distributed" else "network_sim"), __name__)
+        return mod.SimulatedNetworkEnv if name == "SimulatedNetworkEnv" else mod
     raise AttributeError(name)

@@ -9,7 +9,7 @@
 // Data layout in HBM (all owned by the caller, see pcc_workspace_bytes):
 //   state block : structure-of-arrays, one column of n_envs elements per scalar of
 //                 pcc::EnvState (coalesced: lane == env), then the MI-feature history
-//                 hist[slot][feature][env] (a ring over `slot` with a handle-global head, so
+//                 hist[env][slot][feature] (a ring over `slot` with a handle-global head, so
 //                 a step writes one new row instead of shifting H rows), then (MT19937 mode
 //                 only) uint32[n_envs][625] generator states, then a small meta block.
 //   ring block  : Rec[n_envs][ring_capacity], 16 B per in-flight packet (arrival time at
@@ -22,6 +22,7 @@
 
 #include "pcc_b200.h"
 #include "pcc_core.cuh"
+#include "pcc_coop.cuh"
 
 using namespace pcc;
 
@@ -49,7 +50,7 @@ struct DevState {
     unsigned long long *seed, *draws;
     uint32_t *tail, *h1, *h2;
     int32_t *steps;
-    double *hist;              // [H][F][n]
+    double *hist;              // [n][H][F]: per env a ring over H slots (handle-global head)
     uint32_t *mt;              // [n][625] or null
     unsigned long long *meta;  // [0] steps issued (history head), [1] overflow count, [2] first overflowed env + 1
     Rec *rings;                // [n][cap]
@@ -140,13 +141,13 @@ __global__ void pcc_step_kernel(DevState p, unsigned long long head_step,
     for (int h = 0; h < H - 1; h++) {
         int slot = slot_new + 1 + h;
         if (slot >= H) slot -= H;
-        for (int f = 0; f < F; f++) ob[h * F + f] = p.hist[((size_t)slot * F + f) * p.n + e];
+        for (int f = 0; f < F; f++) ob[h * F + f] = p.hist[(size_t)e * (H * F) + slot * F + f];
     }
 #pragma unroll
     for (int f = 0; f < PCC_MAX_FEATURES; f++)
         if (f < F) {
             ob[(H - 1) * F + f] = row[f];
-            p.hist[((size_t)slot_new * F + f) * p.n + e] = row[f];
+            p.hist[(size_t)e * (H * F) + slot_new * F + f] = row[f];
         }
     reward[e] = o.st.reward;
     done[e] = o.done ? 1 : 0;
@@ -163,6 +164,125 @@ __global__ void pcc_step_kernel(DevState p, unsigned long long head_step,
         q[0] = o.st.send_rate; q[1] = o.st.recv_rate; q[2] = o.st.avg_lat; q[3] = o.st.loss_ratio;
         q[4] = o.st.lat_infl; q[5] = o.st.lat_ratio; q[6] = o.st.send_ratio; q[7] = o.st.dur;
         q[8] = s.cur_time; q[9] = s.rate; q[10] = s.run_dur; q[11] = s.conn_min;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels (v2: G lanes per env, see pcc_coop.cuh) -- Philox streams only
+// ---------------------------------------------------------------------------------------
+#define PCC_COOP_THREADS 128
+
+template <int G>
+__device__ __forceinline__ void coop_emit(const Grp<G> &g, const DevState &p, int64_t e, unsigned long long head_step,
+                                          const MiStats &st, double *__restrict__ obs)
+{
+    // history ring: the new row replaces the oldest slot; obs = oldest -> newest, written by
+    // the group as one contiguous H*F*8-byte row
+    const int H = p.H, F = p.F, HF = H * F;
+    const int slot_new = (int)(head_step % (unsigned long long)H);
+    double *hrow = p.hist + (size_t)e * HF;
+    double *ob = obs + (size_t)e * HF;
+    for (int k = (int)g.gl; k < HF; k += G) {
+        const int h = k / F, f = k - h * F;
+        double v;
+        if (h == H - 1) v = metric_value(st, p.ids[f]);
+        else {
+            int slot = slot_new + 1 + h;
+            if (slot >= H) slot -= H;
+            v = hrow[slot * F + f];
+        }
+        ob[k] = v;
+    }
+    g.sync();
+    if ((int)g.gl < F) hrow[slot_new * F + (int)g.gl] = metric_value(st, p.ids[g.gl]);
+    if (G < PCC_MAX_FEATURES)
+        for (int f = G + (int)g.gl; f < F; f += G) hrow[slot_new * F + f] = metric_value(st, p.ids[f]);
+}
+
+template <int G>
+__global__ void __launch_bounds__(PCC_COOP_THREADS)
+pcc_step_coop_kernel(DevState p, unsigned long long head_step, const double *__restrict__ actions,
+                     double *__restrict__ obs, double *__restrict__ reward, uint8_t *__restrict__ done,
+                     int32_t *__restrict__ counts, double *__restrict__ info)
+{
+    __shared__ double sbuf[(PCC_COOP_THREADS / G) * (PCC_LEAF + G)];
+    const Grp<G> g;
+    const int64_t e = ((int64_t)blockIdx.x * PCC_COOP_THREADS + threadIdx.x) / G;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
+    if (e >= p.n) return;
+    double *buf = sbuf + (threadIdx.x / G) * (PCC_LEAF + G);
+    EnvState s;
+    load_env(p, e, s);
+    DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
+    const uint64_t seed = p.seed[e];
+    uint64_t draws = p.draws[e];
+    StepOut o;
+    s.rate = apply_rate_delta(s.rate, actions[e], p.c);                          // :412
+    run_mi_coop(g, s, ring, seed, draws, s.run_dur, o.mi);                      // :416
+    double avg_lat, lat_inc;
+    mi_means_coop(g, o.mi, ring, s.dl, buf, p.need_inc != 0, avg_lat, lat_inc);
+    mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
+    s.steps += 1;                                                                // :419
+    if (o.st.avg_lat > 0.0) s.run_dur = 0.5 * o.st.avg_lat;                      // :437-438
+    o.done = s.steps >= p.c.max_steps;                                           // :444
+    coop_emit(g, p, e, head_step, o.st, obs);
+    if (g.gl == 0) {
+        store_env_dynamic(p, e, s);
+        p.draws[e] = draws;
+        if (o.mi.overflow) flag_overflow(p, e);
+        reward[e] = o.st.reward;
+        done[e] = o.done ? 1 : 0;
+        const double acc = p.ret_acc[e] + o.st.reward;                           // :443
+        p.ret_acc[e] = acc;
+        if (o.done) p.ret_last[e] = acc;
+        if (counts) { counts[3 * e + 0] = o.mi.sent; counts[3 * e + 1] = o.mi.acked; counts[3 * e + 2] = o.mi.lost; }
+        if (info) {
+            double *q = info + (size_t)e * PCC_INFO_WIDTH;
+            q[0] = o.st.send_rate; q[1] = o.st.recv_rate; q[2] = o.st.avg_lat; q[3] = o.st.loss_ratio;
+            q[4] = o.st.lat_infl; q[5] = o.st.lat_ratio; q[6] = o.st.send_ratio; q[7] = o.st.dur;
+            q[8] = s.cur_time; q[9] = s.rate; q[10] = s.run_dur; q[11] = s.conn_min;
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(PCC_COOP_THREADS)
+pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double *__restrict__ bw,
+                      const double *__restrict__ delay, const long long *__restrict__ queue,
+                      const double *__restrict__ loss, const double *__restrict__ start_rate,
+                      double *__restrict__ obs)
+{
+    const Grp<G> g;
+    const int64_t e = ((int64_t)blockIdx.x * PCC_COOP_THREADS + threadIdx.x) / G;
+    if (e >= p.n) return;
+    if (mask && !mask[e]) return;
+    EnvState s;
+    const double bwv = bw[e], dlv = delay[e], sr = start_rate[e];
+    // reset_env of pcc_core.cuh (network_sim.py:454-484), cooperatively
+    s.d_bw = 1.0 / bwv; s.dl = dlv; s.lr = loss[e]; s.max_qd = (double)queue[e] / bwv;
+    s.qd = 0.0; s.t_upd = 0.0; s.rate = sr; s.cur_time = 0.0; s.next_send = 1.0 / sr;
+    s.run_dur = 3 * dlv; s.conn_min = 0.0;
+    s.tail = p.tail[e]; s.h1 = s.tail; s.h2 = s.tail; s.steps = 0;
+    DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
+    const uint64_t seed = p.seed[e];
+    uint64_t draws = p.draws[e];
+    MiOut o;
+    run_mi_coop(g, s, ring, seed, draws, s.run_dur, o);                          // :478
+    bool ovf = o.overflow;
+    run_mi_coop(g, s, ring, seed, draws, s.run_dur, o);                          // :479
+    ovf = ovf || o.overflow;
+    const int HF = p.H * p.F;
+    for (int k = (int)g.gl; k < HF; k += G) {
+        const double v = metric_empty(p.ids[k % p.F]);
+        p.hist[(size_t)e * HF + k] = v;
+        if (obs) obs[(size_t)e * HF + k] = v;
+    }
+    if (g.gl == 0) {
+        p.d_bw[e] = s.d_bw; p.bw[e] = bwv; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd;
+        store_env_dynamic(p, e, s);
+        p.draws[e] = draws;
+        p.ret_acc[e] = 0.0;
+        if (ovf) flag_overflow(p, e);
     }
 }
 
@@ -197,7 +317,7 @@ __global__ void pcc_reset_kernel(DevState p, const uint8_t *__restrict__ mask,
     for (int h = 0; h < H; h++)
         for (int f = 0; f < F; f++) {
             double v = metric_empty(p.ids[f]);
-            p.hist[((size_t)h * F + f) * p.n + e] = v;
+            p.hist[(size_t)e * (H * F) + h * F + f] = v;
             if (obs) obs[(size_t)e * (size_t)(H * F) + h * F + f] = v;
         }
 }
@@ -250,6 +370,7 @@ struct pcc_handle_s {
     unsigned long long head;  // steps issued so far (history ring head)
     int64_t launches;
     int block;
+    int group;   // lanes per env of the cooperative kernels (0 = v1 thread-per-env)
     // staging for pcc_step_host
     double *st_actions, *st_obs, *st_reward;
     uint8_t *st_done;
@@ -382,6 +503,10 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     const char *blk = getenv("PCC_B200_BLOCK");
     h->block = blk ? atoi(blk) : 32;
     if (h->block < 32 || h->block > 1024 || (h->block & 31)) h->block = 32;
+    const char *grp = getenv("PCC_B200_GROUP");
+    h->group = grp ? atoi(grp) : 8;
+    if (h->group != 0 && h->group != 8 && h->group != 16 && h->group != 32) h->group = 8;
+    if (cfg->rng_kind != PCC_RNG_PHILOX) h->group = 0;   // MT19937 (fidelity mode) runs the scalar kernels
     if (init) {
         cudaError_t e = cudaMemset(state_dev, 0, L.total);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -462,7 +587,13 @@ int pcc_reset(pcc_handle h, const uint8_t *mask_dev, const double *bw_dev, const
         return fail(PCC_EINVAL, "null pointer");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->cfg.rng_kind == PCC_RNG_PHILOX)
+    const unsigned cgrid = h->group ? (unsigned)((h->cfg.n_envs * h->group + PCC_COOP_THREADS - 1) / PCC_COOP_THREADS) : 0u;
+#define PCC_RESET_COOP(G_) pcc_reset_coop_kernel<G_><<<cgrid, PCC_COOP_THREADS, 0, st>>>( \
+        h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rate_dev, obs_dev)
+    if (h->group == 8) PCC_RESET_COOP(8);
+    else if (h->group == 16) PCC_RESET_COOP(16);
+    else if (h->group == 32) PCC_RESET_COOP(32);
+    else if (h->cfg.rng_kind == PCC_RNG_PHILOX)
         pcc_reset_kernel<PCC_RNG_PHILOX><<<grid_for(h), h->block, 0, st>>>(
             h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rate_dev, obs_dev);
     else
@@ -479,7 +610,13 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
     if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(PCC_EINVAL, "null pointer");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->cfg.rng_kind == PCC_RNG_PHILOX)
+    const unsigned cgrid = h->group ? (unsigned)((h->cfg.n_envs * h->group + PCC_COOP_THREADS - 1) / PCC_COOP_THREADS) : 0u;
+#define PCC_STEP_COOP(G_) pcc_step_coop_kernel<G_><<<cgrid, PCC_COOP_THREADS, 0, st>>>( \
+        h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev)
+    if (h->group == 8) PCC_STEP_COOP(8);
+    else if (h->group == 16) PCC_STEP_COOP(16);
+    else if (h->group == 32) PCC_STEP_COOP(32);
+    else if (h->cfg.rng_kind == PCC_RNG_PHILOX)
         pcc_step_kernel<PCC_RNG_PHILOX><<<grid_for(h), h->block, 0, st>>>(
             h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
     else

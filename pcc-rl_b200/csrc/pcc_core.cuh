@@ -471,33 +471,22 @@ struct MiStats {
     double conn_min, lat_ratio, send_ratio, reward;
 };
 
-template <class Ring>
-PCC_HD void mi_stats(const MiOut &o, Ring &ring, double dl, const Consts &c, bool need_increase,
-                     double &conn_min_state, bool update_conn_min, MiStats &st)
+// Everything of mi_stats that is scalar: takes the two np.mean-derived quantities as inputs.
+PCC_HD void mi_stats_finish(const MiOut &o, const Consts &c, double avg_lat, double lat_increase,
+                            double &conn_min_state, bool update_conn_min, MiStats &st)
 {
-    const int n = o.acked;
     const double bytes_sent = (double)((int64_t)o.sent * c.bytes_per_packet);
     const double bytes_acked_m1 = (double)((int64_t)o.acked * c.bytes_per_packet - c.bytes_per_packet);
     st.dur = o.end - o.start;                                                     // :116-117
     st.send_rate = (st.dur > 0.0) ? 8.0 * bytes_sent / st.dur : 0.0;              // :124-128
     st.recv_rate = (st.dur > 0.0) ? 8.0 * bytes_acked_m1 / st.dur : 0.0;          // :110-114
-    if (n > 0) { SampleReader<Ring> rd(ring, o, dl); st.avg_lat = np_mean_stream(rd, n); }
-    else st.avg_lat = 0.0;                                                        // :119-122
+    st.avg_lat = avg_lat;                                                         // :119-122
     // bytes_lost / (bytes_lost + bytes_acked): both are exact ints * 1500; int/int true
     // division in Python is correctly rounded, as is this double division of exact values.
     st.loss_ratio = (o.lost + o.acked > 0)
         ? (double)((int64_t)o.lost * c.bytes_per_packet) /
           (double)(((int64_t)o.lost + o.acked) * c.bytes_per_packet) : 0.0;       // :133-136
-    st.lat_increase = 0.0;
-    if (need_increase) {
-        int half = n / 2;                                                         // :138-142
-        if (half >= 1) {
-            SampleReader<Ring> rd(ring, o, dl);
-            double first = np_mean_stream(rd, half);
-            double second = np_mean_stream(rd, n - half);
-            st.lat_increase = second - first;
-        }
-    }
+    st.lat_increase = lat_increase;                                               // :138-142
     st.lat_infl = (st.dur > 0.0) ? st.lat_increase / st.dur : 0.0;                // :144-156
     // conn min latency (:158-176); the dict entry exists iff conn_min_state > 0
     double cm;
@@ -516,6 +505,25 @@ PCC_HD void mi_stats(const MiOut &o, Ring &ring, double dl, const Consts &c, boo
     // reward :194,205 -- ((10*thr)/12000 - 1e3*lat) - 2e3*loss, then * REWARD_SCALE
     double rw = 10.0 * st.recv_rate / (double)(8 * c.bytes_per_packet) - 1e3 * st.avg_lat - 2e3 * st.loss_ratio;
     st.reward = rw * c.reward_scale;
+}
+
+template <class Ring>
+PCC_HD void mi_stats(const MiOut &o, Ring &ring, double dl, const Consts &c, bool need_increase,
+                     double &conn_min_state, bool update_conn_min, MiStats &st)
+{
+    const int n = o.acked;
+    double avg_lat = 0.0, lat_increase = 0.0;
+    if (n > 0) { SampleReader<Ring> rd(ring, o, dl); avg_lat = np_mean_stream(rd, n); }
+    if (need_increase) {
+        int half = n / 2;                                                         // :138-142
+        if (half >= 1) {
+            SampleReader<Ring> rd(ring, o, dl);
+            double first = np_mean_stream(rd, half);
+            double second = np_mean_stream(rd, n - half);
+            lat_increase = second - first;
+        }
+    }
+    mi_stats_finish(o, c, avg_lat, lat_increase, conn_min_state, update_conn_min, st);
 }
 
 PCC_HD double metric_value(const MiStats &st, int id)

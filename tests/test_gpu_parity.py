@@ -167,8 +167,11 @@ def test_cuda_config3_spot_check_and_invariants():
             if o_d:
                 o_obs = o.reset(*[env.params[k][i] for k in ("bw", "lat", "queue", "loss", "start_rate")])
             assert tuple(o_c) == tuple(c_h[j]) and o_r == r_h[j] and np.array_equal(o_obs, o_h[j]), (t, int(i))
-        if t == 48:  # just before the synchronized reset: packets are conserved
-            assert bool((tot[:, 0] >= tot[:, 1] + tot[:, 2]).all())
+        if t == 48:  # just before the synchronized reset: packets are conserved (every acked/lost
+            # packet was sent in this episode, possibly during its two warm-up MIs of 3*lat each)
+            warm = torch.as_tensor(2 * 3 * params0["lat"] * params0["start_rate"] + 4, device=env.device)
+            assert bool((tot[:, 0] + warm >= tot[:, 1] + tot[:, 2]).all())
+            assert bool((tot[:, 0] > 0).all())
     env.check()
 
 
