@@ -79,6 +79,7 @@ struct DevRing {
         *reinterpret_cast<double2 *>(base + (i & mask)) = make_double2(r.a, r.l);
     }
     __device__ __forceinline__ void store_a(uint32_t i, double a) { base[i & mask].a = a; }
+    __device__ __forceinline__ const Rec *addr(uint32_t i) const { return base + (i & mask); }
 };
 
 __device__ __forceinline__ void load_env(const DevState &p, int64_t e, EnvState &s)
@@ -193,7 +194,7 @@ __device__ __forceinline__ void coop_emit(const Grp<G> &g, const DevState &p, in
         }
         ob[k] = v;
     }
-    g.sync();
+    g.gsync();
     if ((int)g.gl < F) hrow[slot_new * F + (int)g.gl] = metric_value(st, p.ids[g.gl]);
     if (G < PCC_MAX_FEATURES)
         for (int f = G + (int)g.gl; f < F; f += G) hrow[slot_new * F + f] = metric_value(st, p.ids[f]);
@@ -205,12 +206,13 @@ pcc_step_coop_kernel(DevState p, unsigned long long head_step, const double *__r
                      double *__restrict__ obs, double *__restrict__ reward, uint8_t *__restrict__ done,
                      int32_t *__restrict__ counts, double *__restrict__ info)
 {
-    __shared__ double sbuf[(PCC_COOP_THREADS / G) * (PCC_LEAF + G)];
+    __shared__ GroupSmem<G> smem[PCC_COOP_THREADS / G];
     const Grp<G> g;
-    const int64_t e = ((int64_t)blockIdx.x * PCC_COOP_THREADS + threadIdx.x) / G;
+    int64_t e = ((int64_t)blockIdx.x * PCC_COOP_THREADS + threadIdx.x) / G;
     if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
-    if (e >= p.n) return;
-    double *buf = sbuf + (threadIdx.x / G) * (PCC_LEAF + G);
+    const bool alive = e < p.n;      // whole groups; dead groups follow the warp's control flow
+    if (!alive) e = p.n - 1;
+    GroupSmem<G> &sm = smem[threadIdx.x / G];
     EnvState s;
     load_env(p, e, s);
     DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
@@ -218,13 +220,14 @@ pcc_step_coop_kernel(DevState p, unsigned long long head_step, const double *__r
     uint64_t draws = p.draws[e];
     StepOut o;
     s.rate = apply_rate_delta(s.rate, actions[e], p.c);                          // :412
-    run_mi_coop(g, s, ring, seed, draws, s.run_dur, o.mi);                      // :416
+    run_mi_coop(g, alive, s, ring, seed, draws, s.run_dur, sm, o.mi);           // :416
     double avg_lat, lat_inc;
-    mi_means_coop(g, o.mi, ring, s.dl, buf, p.need_inc != 0, avg_lat, lat_inc);
+    mi_means_coop(g, alive, o.mi, ring, s.dl, sm, p.need_inc != 0, avg_lat, lat_inc);
     mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
     s.steps += 1;                                                                // :419
     if (o.st.avg_lat > 0.0) s.run_dur = 0.5 * o.st.avg_lat;                      // :437-438
     o.done = s.steps >= p.c.max_steps;                                           // :444
+    if (!alive) return;
     coop_emit(g, p, e, head_step, o.st, obs);
     if (g.gl == 0) {
         store_env_dynamic(p, e, s);
@@ -252,10 +255,13 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
                       const double *__restrict__ loss, const double *__restrict__ start_rate,
                       double *__restrict__ obs)
 {
+    __shared__ GroupSmem<G> smem[PCC_COOP_THREADS / G];
     const Grp<G> g;
-    const int64_t e = ((int64_t)blockIdx.x * PCC_COOP_THREADS + threadIdx.x) / G;
-    if (e >= p.n) return;
-    if (mask && !mask[e]) return;
+    int64_t e = ((int64_t)blockIdx.x * PCC_COOP_THREADS + threadIdx.x) / G;
+    bool alive = e < p.n;
+    if (!alive) e = p.n - 1;
+    if (mask && !mask[e]) alive = false;
+    GroupSmem<G> &sm = smem[threadIdx.x / G];
     EnvState s;
     const double bwv = bw[e], dlv = delay[e], sr = start_rate[e];
     // reset_env of pcc_core.cuh (network_sim.py:454-484), cooperatively
@@ -267,10 +273,11 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     const uint64_t seed = p.seed[e];
     uint64_t draws = p.draws[e];
     MiOut o;
-    run_mi_coop(g, s, ring, seed, draws, s.run_dur, o);                          // :478
+    run_mi_coop(g, alive, s, ring, seed, draws, s.run_dur, sm, o);               // :478
     bool ovf = o.overflow;
-    run_mi_coop(g, s, ring, seed, draws, s.run_dur, o);                          // :479
+    run_mi_coop(g, alive, s, ring, seed, draws, s.run_dur, sm, o);               // :479
     ovf = ovf || o.overflow;
+    if (!alive) return;
     const int HF = p.H * p.F;
     for (int k = (int)g.gl; k < HF; k += G) {
         const double v = metric_empty(p.ids[k % p.F]);

@@ -1,23 +1,34 @@
-// pcc_coop.cuh -- group-cooperative monitor interval: G lanes of a warp work on ONE env.
+// pcc_coop.cuh -- group-cooperative monitor interval: G lanes of a warp work on ONE env, the
+// 32/G groups of a warp move through the phases of the MI in lock step.
 //
 // Same algorithm and the same arithmetic as pcc_core.cuh::run_mi / mi_stats (which the host
 // twin proves against the oracle); what changes is who does the work:
-//   * queue recurrence (network_sim.py:72-84, inherently serial in binary64): lane 0 of the
-//     group, with the per-packet loss draws precomputed by all G lanes (one Philox4x32-10
-//     block per lane = 2G draws per chunk) and handed over as two ballot masks;
-//   * ring scans (hop-1 / hop-2 cursors): G consecutive 16-byte records per load = full
-//     128-byte lines for G = 8, predicate + ballot + ffs instead of a dependent-load loop;
-//   * MI-boundary cluster analysis (stragglers, tuple-order minimum): ballots and
-//     shuffle min-reductions over the window;
-//   * np.mean: samples are compacted (ballot + popc prefix) into a shared-memory staging
-//     buffer, numpy's 8 accumulators live in 8 lanes, combined with a 3-level xor-shuffle
-//     tree -- bit-identical to DOUBLE_pairwise_sum.
+//   * queue recurrence (network_sim.py:72-84, inherently serial in binary64): lane 0 of each
+//     group runs a branch-free loop over a chunk of 2G packets; the per-packet loss draws
+//     are precomputed by all G lanes (one Philox4x32-10 block per lane) and handed over as
+//     one bit mask; records are staged in shared memory and copied to the in-flight ring by
+//     the whole group (coalesced 16-byte stores);
+//   * ring scans (hop-1 / hop-2 cursors): W windows of G consecutive 16-byte records per
+//     round, loads issued together (memory-level parallelism), predicate + ballot + ffs
+//     instead of a dependent-load loop; the lines are prefetched before the send phase;
+//   * MI-boundary cluster analysis (stragglers, tuple-order minimum): ballots and shuffle
+//     min-reductions over the window;
+//   * np.mean: acked latencies are compacted (ballot + popc prefix) into a shared-memory
+//     staging buffer during the hop-2 scan; numpy's 8 accumulators live in 8 lanes and are
+//     combined with a 3-level xor-shuffle tree -- bit-identical to DOUBLE_pairwise_sum
+//     (SURVEY.md F2).
+// Control flow is warp-uniform (loops run while ANY group needs them, finished groups are
+// predicated off), so every *_sync primitive uses the full mask -- except the rare
+// "more than 128 samples" path, which runs per group with group masks.
 #pragma once
 #include "pcc_core.cuh"
 
 namespace pcc {
 
 #define PCC_INF_BITS 0x7FF0000000000000ull
+#define PCC_FULL 0xffffffffu
+#define PCC_LEAF 128          // numpy's PW_BLOCKSIZE
+#define PCC_SCAN_W 4          // windows per scan round
 
 template <int G>
 struct Grp {
@@ -30,18 +41,23 @@ struct Grp {
         gbase = lane - gl;
         gmask = LOW << gbase;
     }
-    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(gmask, p) >> gbase) & LOW; }
-    __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(gmask, v, (int)gbase + src); }
-    __device__ __forceinline__ int bcast(int v, int src) const { return __shfl_sync(gmask, v, (int)gbase + src); }
-    __device__ __forceinline__ unsigned bcast(unsigned v, int src) const { return __shfl_sync(gmask, v, (int)gbase + src); }
+    // warp-wide vote, returns this group's G bits
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(PCC_FULL, p) >> gbase) & LOW; }
+    __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(PCC_FULL, v, (int)gbase + src); }
+    __device__ __forceinline__ int bcast(int v, int src) const { return __shfl_sync(PCC_FULL, v, (int)gbase + src); }
+    __device__ __forceinline__ unsigned bcast(unsigned v, int src) const { return __shfl_sync(PCC_FULL, v, (int)gbase + src); }
     __device__ __forceinline__ double min(double v) const
     {
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(gmask, v, o));
+        for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(PCC_FULL, v, o));
         return v;
     }
-    __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+    // group-mask variants for the divergent (per-group) slow path
+    __device__ __forceinline__ unsigned gballot(bool p) const { return (__ballot_sync(gmask, p) >> gbase) & LOW; }
+    __device__ __forceinline__ double gbcast(double v, int src) const { return __shfl_sync(gmask, v, (int)gbase + src); }
+    __device__ __forceinline__ void gsync() const { __syncwarp(gmask); }
     static __device__ __forceinline__ int lead_ones(unsigned bm) { return (bm == LOW) ? G : (__ffs(~bm) - 1); }
+    static __device__ __forceinline__ unsigned lowmask(int n) { return (n >= 32) ? 0xffffffffu : ((1u << n) - 1u); }
 };
 
 __device__ __forceinline__ void philox_block(uint64_t seed, uint64_t blk, uint32_t &c0, uint32_t &c1,
@@ -51,13 +67,27 @@ __device__ __forceinline__ void philox_block(uint64_t seed, uint64_t blk, uint32
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
-// window load: lane gl gets record i + gl if it lies before `lim`, else a neutral dummy
-// (a = +inf: never consumable, not flagged; l = +1: not dropped)
+// bit k of the result = bit k/2 of (k even ? even_bits : odd_bits)
+__device__ __forceinline__ uint64_t interleave_bits(uint32_t even_bits, uint32_t odd_bits)
+{
+    uint64_t x = even_bits, y = odd_bits;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull; y = (y | (y << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;  y = (y | (y << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;  y = (y | (y << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;  y = (y | (y << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;  y = (y | (y << 1)) & 0x5555555555555555ull;
+    return x | (y << 1);
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// window load: lane gl gets record i + gl if `on` and it lies before `lim`, else a neutral
+// dummy (a = +inf: never consumable, not flagged; l = +1: not dropped)
 template <int G, class Ring>
-__device__ __forceinline__ Rec load_window(const Grp<G> &g, Ring &ring, uint32_t i, uint32_t lim, bool &valid)
+__device__ __forceinline__ Rec load_window(const Grp<G> &g, Ring &ring, uint32_t i, uint32_t lim, bool on, bool &valid)
 {
     const uint32_t idx = i + g.gl;
-    valid = (int32_t)(idx - lim) < 0;
+    valid = on && ((int32_t)(idx - lim) < 0);
     Rec r;
     if (valid) r = ring.load(idx);
     else { r.a = u2d(PCC_INF_BITS); r.l = 1.0; }
@@ -65,7 +95,7 @@ __device__ __forceinline__ Rec load_window(const Grp<G> &g, Ring &ring, uint32_t
 }
 
 // argmin of (key1, key2, dropped False<True) over candidate lanes, merged into the running
-// minimum (has, m_idx, m_k1, m_k2, m_d).  All outputs are group-uniform.
+// minimum (has, m_idx, m_k1, m_k2, m_d).  Results are group-uniform; warp-uniform call.
 template <int G>
 __device__ __forceinline__ void window_argmin(const Grp<G> &g, bool cand, double k1, double k2, bool dr,
                                               uint32_t base_idx, bool &has, uint32_t &m_idx, double &m_k1,
@@ -86,18 +116,25 @@ __device__ __forceinline__ void window_argmin(const Grp<G> &g, bool cand, double
     }
 }
 
-// One monitor interval, cooperatively.  Every lane of the group holds the same EnvState copy
-// on entry and on exit.  `draws` is the env's Philox draw counter.
+// Per-group shared-memory scratch
+template <int G>
+struct GroupSmem {
+    double2 stage[2 * G];        // records of one send chunk
+    double buf[PCC_LEAF + G];    // acked-latency staging for np.mean
+};
+
+// One monitor interval.  Every lane of a group holds the same EnvState copy on entry and on
+// exit.  `alive` = this group has an env (warp-uniform control flow needs all lanes present).
+// On exit, if out.acked <= PCC_LEAF, sm.buf[0..out.acked) holds the MI's samples in order.
 template <int G, class Ring>
-__device__ __forceinline__ void run_mi_coop(const Grp<G> &g, EnvState &s, Ring &ring, uint64_t seed,
-                                            uint64_t &draws, double dur, MiOut &out)
+__device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvState &s, Ring &ring, uint64_t seed,
+                                            uint64_t &draws, double dur, GroupSmem<G> &sm, MiOut &out)
 {
     const double end = s.cur_time + dur;            // network_sim.py:124
     const double inv_rate = 1.0 / s.rate;           // :161
     const uint32_t cap = ring.capacity();
     int32_t sent = 0, acked = 0, lost = 0;
     out.start = s.cur_time;
-    out.overflow = false;
     out.has_extra = false;
     out.extra = 0.0;
     out.s_begin = s.h2;
@@ -105,67 +142,100 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, EnvState &s, Ring &
     uint32_t tail = s.tail, h1 = s.h1, h2 = s.h2;
     bool ovf = false;
 
+    // pull the lines the two cursors will walk into L1 while the send phase runs
+    if (alive) {
+        const uint32_t pend1 = tail - h1, pend2 = tail - h2;   // records pending per stream
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            const uint32_t o = (uint32_t)((w * G + (int)g.gl) * 8);
+            if (o < pend1) prefetch_l1(ring.addr(h1 + o));
+            if (o < pend2) prefetch_l1(ring.addr(h2 + o));
+        }
+    }
+
     // ---- (1) sends with t < end: chain on lane 0, loss draws from all lanes ---------------
-    bool more = t < end;
-    while (more) {
+    bool more = alive && (t < end);
+    while (__any_sync(PCC_FULL, more)) {
         const unsigned off = (unsigned)(draws & 1ull);
         uint32_t c0, c1, c2, c3;
         philox_block(seed, (draws >> 1) + g.gl, c0, c1, c2, c3);
-        const unsigned m_even = g.ballot(res53(c0, c1) < s.lr);   // draw 2*blk   of lane's block
-        const unsigned m_odd = g.ballot(res53(c2, c3) < s.lr);    // draw 2*blk+1
+        const unsigned be = g.ballot(res53(c0, c1) < s.lr);   // draw 2*blk   of lane's block  (:73)
+        const unsigned bo = g.ballot(res53(c2, c3) < s.lr);   // draw 2*blk+1
+        uint64_t dm = interleave_bits(be, bo) >> off;         // bit k = random drop of the chunk's k-th packet
         const int navail = 2 * G - (int)off;
         int k = 0;
-        if (g.gl == 0) {
-            for (; k < navail && t < end; ++k) {
-                const unsigned d = off + (unsigned)k;
-                const bool rdrop = ((((d & 1u) ? m_odd : m_even) >> (d >> 1)) & 1u) != 0u;   // :73
-                const double w = py_max0(qd - (t - t_upd));          // :170 -> :66-70
-                const double ll = s.dl + w;
-                bool dropped = rdrop;
-                if (!rdrop) {
-                    qd = w; t_upd = t;                               // :75-76
-                    if (s.d_bw + qd > s.max_qd) dropped = true;      // :79
-                    else qd += s.d_bw;                               // :82
+        if (g.gl == 0 && more) {
+            if ((uint32_t)(tail - h2) + (uint32_t)navail > cap) { ovf = true; }   // fatal, reported by the host
+            else {
+                double tt = t, q = qd, tu = t_upd;
+#pragma unroll 2
+                for (; k < navail; ++k) {
+                    if (!(tt < end)) break;
+                    const bool rdrop = (dm & 1ull) != 0ull;
+                    dm >>= 1;
+                    const long long yb = __double_as_longlong(q - (tt - tu));   // :66-67
+                    const double w = __longlong_as_double(yb & ~(yb >> 63));    // max(0.0, y)
+                    const double c = s.d_bw + w;                                // :77-79
+                    const bool full = c > s.max_qd;
+                    const double ll = s.dl + w;                                 // :69-70
+                    q = rdrop ? q : (full ? w : c);                             // :74-82
+                    tu = rdrop ? tu : tt;
+                    const bool dropped = rdrop || full;
+                    const double lsigned = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
+                    sm.stage[k] = make_double2(tt + ll, lsigned);              // :173-175
+                    tt = tt + inv_rate;                                         // :161
                 }
-                Rec r; r.a = t + ll; r.l = dropped ? negd(ll) : ll;
-                if ((uint32_t)(tail - h2) >= cap) ovf = true;
-                else { ring.store(tail, r); tail++; }
-                t = t + inv_rate;                                    // :161
+                t = tt; qd = q; t_upd = tu;
             }
         }
-        const int packed = g.bcast((int)(k | ((k == navail && t < end) ? 0x100 : 0)), 0);
+        const int packed = g.bcast((int)(k | ((k == navail && t < end && !ovf) ? 0x100 : 0)), 0);
         k = packed & 0xff;
-        more = (packed & 0x100) != 0;
-        draws += (uint64_t)k;
-        sent += k;
+        __syncwarp();
+        for (int j = (int)g.gl; j < k; j += G) {
+            const double2 v = sm.stage[j];
+            Rec r; r.a = v.x; r.l = v.y;
+            ring.store(tail + (uint32_t)j, r);
+        }
+        __syncwarp();
+        if (more) { tail += (uint32_t)k; draws += (uint64_t)k; sent += k; }
+        more = more && ((packed & 0x100) != 0);
     }
     // make the chain lane's state the group's state
     t = g.bcast(t, 0); qd = g.bcast(qd, 0); t_upd = g.bcast(t_upd, 0);
-    tail = g.bcast(tail, 0);
     ovf = g.bcast((int)ovf, 0) != 0;
-    g.sync();   // the chain lane's record stores are read by every lane below
+    __syncwarp();   // record stores above are read by other lanes below
 
     // ---- (2) hop-1 events with a < end ------------------------------------------------------
     {
-        uint32_t i = h1;
-        for (;;) {
-            bool valid;
-            const Rec r = load_window(g, ring, i, tail, valid);
-            const bool cons = valid && (sgn(r.a) || r.a < end);
-            const int nlead = Grp<G>::lead_ones(g.ballot(cons));
-            i += (uint32_t)nlead;
-            if (nlead < G) break;
+        bool scanning = alive;
+        while (__any_sync(PCC_FULL, scanning)) {
+            unsigned bm[PCC_SCAN_W];
+#pragma unroll
+            for (int w = 0; w < PCC_SCAN_W; w++) {
+                bool valid;
+                const Rec r = load_window(g, ring, h1 + (uint32_t)(w * G), tail, scanning, valid);
+                bm[w] = g.ballot(valid && (sgn(r.a) || r.a < end));
+            }
+            int adv = 0;
+            bool stop = false;
+#pragma unroll
+            for (int w = 0; w < PCC_SCAN_W; w++) {
+                const int nl = Grp<G>::lead_ones(bm[w]);
+                if (!stop) adv += nl;
+                stop = stop || (nl < G);
+            }
+            if (scanning) h1 += (uint32_t)adv;
+            scanning = scanning && !stop;
         }
-        h1 = i;
     }
     bool has1 = false;
     uint32_t m1 = 0; double m1a = 0.0, m1l = 0.0; bool m1d = false;
     {
         uint32_t kk = h1;
-        bool open = (kk != tail);
-        while (open) {
+        bool open = alive && (kk != tail);
+        while (__any_sync(PCC_FULL, open)) {
             bool valid;
-            const Rec r = load_window(g, ring, kk, tail, valid);
+            const Rec r = load_window(g, ring, kk, tail, open, valid);
             const bool dr = sgn(r.l);
             const unsigned validm = g.ballot(valid);
             const unsigned ndm = g.ballot(valid && !dr);
@@ -174,45 +244,67 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, EnvState &s, Ring &
             const bool strag = pending && (r.a < end);
             if (strag) ring.store_a(kk + g.gl, negd(r.a));
             window_argmin(g, pending && !strag, r.a, absd(r.l), dr, kk, has1, m1, m1a, m1l, m1d);
-            open = (pend == G) && (validm == Grp<G>::LOW) && ((uint32_t)(kk + G) != tail);
+            open = open && (pend == G) && (validm == Grp<G>::LOW) && ((uint32_t)(kk + G) != tail);
             kk += G;
         }
-        g.sync();   // straggler flags are read by the hop-2 scan
+        __syncwarp();   // straggler flags are read by the hop-2 scan
     }
 
-    // ---- (3) hop-2 events with b < end ------------------------------------------------------
+    // ---- (3) hop-2 events with b < end; acked latencies staged for np.mean --------------------
     bool at_live = false;
     {
-        uint32_t i = h2;
-        for (;;) {
-            bool valid;
-            const Rec r = load_window(g, ring, i, tail, valid);
-            const bool dead = is_dead(r.a);
-            const bool c1 = ((int32_t)(i + g.gl - h1) < 0) || sgn(r.a);
-            const double b = absd(r.a) + s.dl;               // :149-154, link 1 latency == dl
-            const bool cons = valid && (dead || (c1 && b < end));
-            const int nlead = Grp<G>::lead_ones(g.ballot(cons));
-            const unsigned leadmask = (nlead >= 32) ? 0xffffffffu : ((1u << nlead) - 1u);
-            acked += __popc(g.ballot(cons && !dead && !sgn(r.l)) & leadmask);   // :144-145
-            lost += __popc(g.ballot(cons && !dead && sgn(r.l)) & leadmask);     // :141-142
-            i += (uint32_t)nlead;
-            if (nlead < G) {
-                const unsigned lv = g.ballot(valid && !dead && c1 && !(b < end));
-                at_live = ((lv >> nlead) & 1u) != 0u;
-                break;
+        bool scanning = alive;
+        while (__any_sync(PCC_FULL, scanning)) {
+            unsigned bm[PCC_SCAN_W], am[PCC_SCAN_W], lm[PCC_SCAN_W], lv[PCC_SCAN_W];
+            double l2[PCC_SCAN_W];
+#pragma unroll
+            for (int w = 0; w < PCC_SCAN_W; w++) {
+                bool valid;
+                const uint32_t i = h2 + (uint32_t)(w * G);
+                const Rec r = load_window(g, ring, i, tail, scanning, valid);
+                const bool dead = is_dead(r.a);
+                const bool c1 = ((int32_t)(i + g.gl - h1) < 0) || sgn(r.a);
+                const bool early = (absd(r.a) + s.dl) < end;         // :149-154, link 1 latency == dl
+                const bool cons = valid && (dead || (c1 && early));
+                bm[w] = g.ballot(cons);
+                am[w] = g.ballot(cons && !dead && !sgn(r.l));        // :144-145
+                lm[w] = g.ballot(cons && !dead && sgn(r.l));         // :141-142
+                lv[w] = g.ballot(valid && !dead && c1 && !early);
+                l2[w] = r.l + s.dl;                                  // rtt = fl(ll + dl)
             }
+            int adv = 0;
+            bool stop = false;
+#pragma unroll
+            for (int w = 0; w < PCC_SCAN_W; w++) {
+                const int nl = Grp<G>::lead_ones(bm[w]);
+                const unsigned lead = Grp<G>::lowmask(nl);
+                const bool on = scanning && !stop;
+                const unsigned a_w = on ? (am[w] & lead) : 0u;
+                if ((a_w >> g.gl) & 1u) {
+                    const int pos = acked + __popc(a_w & Grp<G>::lowmask((int)g.gl));
+                    if (pos < PCC_LEAF) sm.buf[pos] = l2[w];
+                }
+                if (on) {
+                    acked += __popc(a_w);
+                    lost += __popc(lm[w] & lead);
+                    adv += nl;
+                    if (nl < G) at_live = ((lv[w] >> nl) & 1u) != 0u;
+                }
+                stop = stop || (nl < G);
+            }
+            if (scanning) h2 += (uint32_t)adv;
+            scanning = scanning && !stop;
         }
-        h2 = i;
     }
     out.s_end = h2;
     bool has2 = false;
     uint32_t m2 = 0; double m2b = 0.0, m2l = 0.0; bool m2d = false;
-    if (at_live) {
+    {
         uint32_t kk = h2;
-        bool open = true;
-        while (open) {
+        bool open = alive && at_live;
+        while (__any_sync(PCC_FULL, open)) {
             bool valid;
-            const Rec r = load_window(g, ring, kk, tail, valid);
+            const Rec r = load_window(g, ring, kk, tail, open, valid);
             const bool dr = sgn(r.l);
             const bool dead = is_dead(r.a);
             const bool c1 = ((int32_t)(kk + g.gl - h1) < 0) || sgn(r.a);
@@ -220,22 +312,23 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, EnvState &s, Ring &
             const unsigned x2 = g.ballot(valid && !dr);               // stop AFTER this record
             const int p1 = x1 ? (__ffs(x1) - 1) : G;
             const int p2 = x2 ? (__ffs(x2) - 1) : G;
-            const bool act = (int)g.gl < p1 && (int)g.gl <= p2 && !dead;
+            const bool act = open && (int)g.gl < p1 && (int)g.gl <= p2 && !dead;
             const double b = absd(r.a) + s.dl;
             const double l2 = absd(r.l) + s.dl;
             const bool strag = act && (b < end);
             const unsigned sa = g.ballot(strag && !dr), sl = g.ballot(strag && dr);
+            const double ex = g.bcast(l2, sa ? (__ffs(sa) - 1) : 0);
+            if (sa) { out.extra = ex; out.has_extra = true; }   // at most one acked per cluster
             acked += __popc(sa);
             lost += __popc(sl);
-            if (sa) { out.extra = g.bcast(l2, __ffs(sa) - 1); out.has_extra = true; }
             if (strag) ring.store_a(kk + g.gl, u2d(PCC_NEG_INF));
             window_argmin(g, act && !strag, b, l2, dr, kk, has2, m2, m2b, m2l, m2d);
-            open = (p1 == G) && (p2 == G);
+            open = open && (p1 == G) && (p2 == G);
             kk += G;
         }
     }
 
-    // ---- (4) the event that crosses `end` (group-uniform) -----------------------------------
+    // ---- (4) the event that crosses `end` (group-uniform values, no votes) --------------------
     int which;
     if (has1 && (!has2 || m1a <= m2b)) which = (m1a <= t) ? 1 : 0;
     else if (has2) which = (m2b <= t) ? 2 : 0;
@@ -258,19 +351,21 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, EnvState &s, Ring &
         }
         Rec r; r.a = t + ll; r.l = dropped ? negd(ll) : ll;
         if ((uint32_t)(tail - h2) >= cap) ovf = true;
-        else { if (g.gl == 0) ring.store(tail, r); tail++; }
+        else { if (alive && g.gl == 0) ring.store(tail, r); tail++; }
         t = t + inv_rate;
     } else if (which == 1) {
         s.cur_time = m1a;
         if (m1 == h1) h1++;
-        else if (g.gl == 0) ring.store_a(m1, negd(m1a));
+        else if (alive && g.gl == 0) ring.store_a(m1, negd(m1a));
     } else {
         s.cur_time = m2b;
         if (m2d) lost++; else { acked++; out.extra = m2l; out.has_extra = true; }
         if (m2 == h2) h2++;
-        else if (g.gl == 0) ring.store_a(m2, u2d(PCC_NEG_INF));
+        else if (alive && g.gl == 0) ring.store_a(m2, u2d(PCC_NEG_INF));
     }
-    g.sync();   // order this MI's flag stores before any later window load by other lanes
+    // the one possible out-of-order sample is the MI's last sample
+    if (out.has_extra && acked <= PCC_LEAF && g.gl == 0) sm.buf[acked - 1] = out.extra;
+    __syncwarp();   // orders this MI's flag stores / staging writes before later reads
     s.next_send = t;
     s.qd = qd; s.t_upd = t_upd;
     s.tail = tail; s.h1 = h1; s.h2 = h2;
@@ -280,59 +375,10 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, EnvState &s, Ring &
 }
 
 // ---------------------------------------------------------------------------------------------
-// np.mean over the MI's samples, cooperatively.  Samples = acked, not-dead records of
-// [s_begin, s_end) in ring order, then the one possible out-of-order sample `extra`.
+// np.mean over the MI's samples.
 // ---------------------------------------------------------------------------------------------
-#define PCC_LEAF 128
-
-template <int G, class Ring>
-struct CoopSamples {
-    const Grp<G> &g;
-    Ring &ring;
-    double *buf;          // shared memory, PCC_LEAF + G doubles, private to the group
-    uint32_t i, end;
-    double dl, extra;
-    bool extra_pending;
-    int fill;
-    __device__ __forceinline__ CoopSamples(const Grp<G> &g_, Ring &r, double *b, const MiOut &o, double dl_)
-        : g(g_), ring(r), buf(b), i(o.s_begin), end(o.s_end), dl(dl_), extra(o.extra),
-          extra_pending(o.has_extra), fill(0) {}
-
-    // make at least `need` (<= PCC_LEAF) samples available in buf[0..fill)
-    __device__ __forceinline__ void fill_until(int need)
-    {
-        while (fill < need && (i != end || extra_pending)) {
-            if (i != end) {
-                bool valid;
-                const Rec r = load_window(g, ring, i, end, valid);
-                const bool keep = valid && !is_dead(r.a) && !sgn(r.l);
-                const unsigned km = g.ballot(keep);
-                if (keep) buf[fill + __popc(km & ((1u << g.gl) - 1u))] = r.l + dl;   // rtt = fl(ll + dl)
-                fill += __popc(km);
-                i = ((uint32_t)(end - i) < (uint32_t)G) ? end : i + (uint32_t)G;
-            } else {
-                if (g.gl == 0) buf[fill] = extra;
-                fill++;
-                extra_pending = false;
-            }
-        }
-        g.sync();
-    }
-    // drop the first cnt samples
-    __device__ __forceinline__ void consume(int cnt)
-    {
-        const int rem = fill - cnt;   // < G by construction of fill_until
-        double v = 0.0;
-        if ((int)g.gl < rem) v = buf[cnt + (int)g.gl];
-        g.sync();
-        if ((int)g.gl < rem) buf[(int)g.gl] = v;
-        fill = rem;
-        g.sync();
-    }
-};
-
 // numpy's DOUBLE_pairwise_sum leaf (n <= 128) over a[0..n) in shared memory; 8 lanes hold the
-// 8 accumulators; result is group-uniform.
+// 8 accumulators; result is group-uniform.  Uses the group mask: callable from divergent code.
 template <int G>
 __device__ __forceinline__ double coop_leaf(const Grp<G> &g, const double *a, int n)
 {
@@ -349,14 +395,62 @@ __device__ __forceinline__ double coop_leaf(const Grp<G> &g, const double *a, in
     r += __shfl_xor_sync(g.gmask, r, 1);    // (r0+r1) (r2+r3) (r4+r5) (r6+r7)
     r += __shfl_xor_sync(g.gmask, r, 2);    // ((r0+r1)+(r2+r3)) ((r4+r5)+(r6+r7))
     r += __shfl_xor_sync(g.gmask, r, 4);
-    double res = (G == 8) ? r : g.bcast(r, 0);
+    double res = (G == 8) ? r : g.gbcast(r, 0);
     for (int k = nb; k < n; k++) res += a[k];
     return res;
 }
 
+// Streaming re-read of the MI's samples for n > PCC_LEAF: acked, not-dead records of
+// [s_begin, s_end) in ring order, then the one possible out-of-order sample `extra`.
+template <int G, class Ring>
+struct CoopSamples {
+    const Grp<G> &g;
+    Ring &ring;
+    double *buf;          // shared memory, PCC_LEAF + G doubles, private to the group
+    uint32_t i, end;
+    double dl, extra;
+    bool extra_pending;
+    int fill;
+    __device__ __forceinline__ CoopSamples(const Grp<G> &g_, Ring &r, double *b, const MiOut &o, double dl_)
+        : g(g_), ring(r), buf(b), i(o.s_begin), end(o.s_end), dl(dl_), extra(o.extra),
+          extra_pending(o.has_extra), fill(0) {}
+
+    __device__ __forceinline__ void fill_until(int need)   // need <= PCC_LEAF
+    {
+        while (fill < need && (i != end || extra_pending)) {
+            if (i != end) {
+                const uint32_t idx = i + g.gl;
+                const bool valid = (int32_t)(idx - end) < 0;
+                Rec r; r.a = 0.0; r.l = -1.0;
+                if (valid) r = ring.load(idx);
+                const bool keep = valid && !is_dead(r.a) && !sgn(r.l);
+                const unsigned km = g.gballot(keep);
+                if (keep) buf[fill + __popc(km & Grp<G>::lowmask((int)g.gl))] = r.l + dl;   // rtt = fl(ll + dl)
+                fill += __popc(km);
+                i = ((uint32_t)(end - i) < (uint32_t)G) ? end : i + (uint32_t)G;
+            } else {
+                if (g.gl == 0) buf[fill] = extra;
+                fill++;
+                extra_pending = false;
+            }
+        }
+        g.gsync();
+    }
+    __device__ __forceinline__ void consume(int cnt)
+    {
+        const int rem = fill - cnt;   // < G by construction of fill_until
+        double v = 0.0;
+        if ((int)g.gl < rem) v = buf[cnt + (int)g.gl];
+        g.gsync();
+        if ((int)g.gl < rem) buf[(int)g.gl] = v;
+        fill = rem;
+        g.gsync();
+    }
+};
+
 // pairwise sum of the next n samples of the stream (numpy's recursion, iterative post-order)
 template <int G, class Ring>
-__device__ __forceinline__ double coop_pw_sum(const Grp<G> &g, CoopSamples<G, Ring> &st, int n)
+__device__ __noinline__ double coop_pw_sum(const Grp<G> &g, CoopSamples<G, Ring> &st, int n)
 {
     int right_n[PCC_PW_STACK];
     double left_sum[PCC_PW_STACK];
@@ -386,45 +480,43 @@ __device__ __forceinline__ double coop_pw_sum(const Grp<G> &g, CoopSamples<G, Ri
     }
 }
 
+// avg latency (sender_obs.py:119-122) and latency increase (:138-142) of the MI
 template <int G, class Ring>
-__device__ __forceinline__ void mi_means_coop(const Grp<G> &g, const MiOut &o, Ring &ring, double dl,
-                                              double *buf, bool need_increase, double &avg_lat,
+__device__ __forceinline__ void mi_means_coop(const Grp<G> &g, bool alive, const MiOut &o, Ring &ring, double dl,
+                                              GroupSmem<G> &sm, bool need_increase, double &avg_lat,
                                               double &lat_increase)
 {
-    const int n = o.acked;
+    const int n = alive ? o.acked : 0;
     avg_lat = 0.0;
     lat_increase = 0.0;
-    if (n <= 0) return;
     const int half = n / 2;
-    if (n <= PCC_LEAF) {
-        // everything fits the staging buffer: one pass over the ring, three leaves
-        CoopSamples<G, Ring> st(g, ring, buf, o, dl);
-        st.fill_until(n);
+    if (n > 0 && n <= PCC_LEAF) {
+        // common case: run_mi_coop left all n samples in sm.buf
         double sum = 0.0;
-        sum += coop_leaf(g, buf, n);
-        avg_lat = sum / (double)n;                                          // sender_obs.py:119-122
-        if (need_increase && half >= 1) {                                   // :138-142
+        sum += coop_leaf(g, sm.buf, n);
+        avg_lat = sum / (double)n;
+        if (need_increase && half >= 1) {
             double s1 = 0.0, s2 = 0.0;
-            s1 += coop_leaf(g, buf, half);
-            s2 += coop_leaf(g, buf + half, n - half);
+            s1 += coop_leaf(g, sm.buf, half);
+            s2 += coop_leaf(g, sm.buf + half, n - half);
             lat_increase = s2 / (double)(n - half) - s1 / (double)half;
         }
-        g.sync();
-        return;
+    } else if (n > PCC_LEAF) {
+        {
+            CoopSamples<G, Ring> st(g, ring, sm.buf, o, dl);
+            double sum = 0.0;
+            sum += coop_pw_sum(g, st, n);
+            avg_lat = sum / (double)n;
+        }
+        if (need_increase) {
+            CoopSamples<G, Ring> st(g, ring, sm.buf, o, dl);
+            double s1 = 0.0, s2 = 0.0;
+            s1 += coop_pw_sum(g, st, half);
+            s2 += coop_pw_sum(g, st, n - half);
+            lat_increase = s2 / (double)(n - half) - s1 / (double)half;
+        }
     }
-    {
-        CoopSamples<G, Ring> st(g, ring, buf, o, dl);
-        double sum = 0.0;
-        sum += coop_pw_sum(g, st, n);
-        avg_lat = sum / (double)n;
-    }
-    if (need_increase) {
-        CoopSamples<G, Ring> st(g, ring, buf, o, dl);
-        double s1 = 0.0, s2 = 0.0;
-        s1 += coop_pw_sum(g, st, half);
-        s2 += coop_pw_sum(g, st, n - half);
-        lat_increase = s2 / (double)(n - half) - s1 / (double)half;
-    }
+    __syncwarp();
 }
 
 }  // namespace pcc
