@@ -23,6 +23,9 @@
 #include "pcc_b200.h"
 #include "pcc_core.cuh"
 #include "pcc_coop.cuh"
+#include "pcc_warp.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 using namespace pcc;
 
@@ -62,7 +65,7 @@ struct DevState {
     Consts c;
 };
 
-enum { META_HEAD = 0, META_OVF_COUNT = 1, META_OVF_ENV = 2, META_WORDS = 8 };
+enum { META_HEAD = 0, META_OVF_COUNT = 1, META_OVF_ENV = 2, META_PART_ERR = 3, META_WORDS = 8 };
 
 struct DevRing {
     Rec *base;
@@ -293,6 +296,268 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// kernels (v4: a warp owns E envs, see pcc_warp.cuh) -- Philox streams only
+// ---------------------------------------------------------------------------------------
+#define PCC_WARP_THREADS 128
+
+// One MI for the E envs of this warp.  `owner` lanes hold their env's state in `s`.
+template <bool WANT_MEANS>
+__device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, bool owner, int cnt, int64_t e, EnvState &s,
+                                        PhiloxRng &rng, double dur, double *buf, MiOut &mo, double &avg_lat,
+                                        double &lat_inc)
+{
+    const unsigned lane = g.gl;
+    const double end = s.cur_time + dur;            // network_sim.py:124
+    const double inv_rate = 1.0 / s.rate;           // :161
+    DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
+    LaneChain c;
+    c.t = s.next_send; c.q = s.qd; c.tu = s.t_upd; c.tail = s.tail; c.sent = 0; c.ovf = false;
+    mo.start = s.cur_time;                          // reset_obs :319-324
+    // phase A: E serial chains side by side
+    if (owner) lane_send_phase(c, s, ring, rng, s.h2, p.cap, end, inv_rate);
+    __syncwarp();
+    // phase B: the warp consumes each env's hop-1 / hop-2 events
+    int which = 0, acked = 0, lost = 0;
+    double ct = 0.0;
+    avg_lat = 0.0; lat_inc = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+        if (!__shfl_sync(PCC_FULL, (int)owner, j)) continue;
+        if (j + 1 < cnt && __shfl_sync(PCC_FULL, (int)owner, j + 1)) {
+            // pull the next env's cursor neighbourhoods into L1 while this one is processed
+            const long long en = __shfl_sync(PCC_FULL, (long long)e, j + 1);
+            const uint32_t h1n = __shfl_sync(PCC_FULL, s.h1, j + 1), h2n = __shfl_sync(PCC_FULL, s.h2, j + 1);
+            const uint32_t tn = __shfl_sync(PCC_FULL, c.tail, j + 1);
+            const Rec *bn = p.rings + (size_t)en * p.cap;
+            const uint32_t o = lane * 8u;
+            if (o < (uint32_t)(tn - h1n)) prefetch_l1(bn + ((h1n + o) & (p.cap - 1u)));
+            if (o < (uint32_t)(tn - h2n)) prefetch_l1(bn + ((h2n + o) & (p.cap - 1u)));
+        }
+        ConsumeIn in;
+        in.end = __shfl_sync(PCC_FULL, end, j);
+        in.dl = __shfl_sync(PCC_FULL, s.dl, j);
+        in.tnext = __shfl_sync(PCC_FULL, c.t, j);
+        in.tail = __shfl_sync(PCC_FULL, c.tail, j);
+        in.h1 = __shfl_sync(PCC_FULL, s.h1, j);
+        in.h2 = __shfl_sync(PCC_FULL, s.h2, j);
+        const long long ej = __shfl_sync(PCC_FULL, (long long)e, j);
+        DevRing rj{p.rings + (size_t)ej * p.cap, p.cap - 1u};
+        ConsumeOut co;
+        consume_mi_warp(g, in, rj, buf, co);
+        double a = 0.0, li = 0.0;
+        if (WANT_MEANS) mi_means_warp(g, co, rj, in.dl, buf, p.need_inc != 0, a, li);
+        if ((int)lane == j) {
+            s.h1 = co.h1; s.h2 = co.h2;
+            acked = co.acked; lost = co.lost; which = co.which; ct = co.cur_time;
+            avg_lat = a; lat_inc = li;
+        }
+    }
+    // phase C (per lane): the crossing event if it is the pacing timer (:156-178)
+    if (owner) {
+        if (which == 0) {
+            s.cur_time = c.t;
+            lane_send_one(c, s, ring, s.h2, p.cap, inv_rate, rng.next());
+        } else {
+            s.cur_time = ct;
+        }
+    }
+    s.next_send = c.t; s.qd = c.q; s.t_upd = c.tu; s.tail = c.tail;
+    mo.sent = c.sent; mo.acked = acked; mo.lost = lost;
+    mo.end = s.cur_time;
+    mo.overflow = c.ovf;
+}
+
+// Work partition of a step: warp w owns the envs perm[starts[w] .. starts[w+1]) of the cost-sorted
+// list (at most 32), or -- without a partition -- the static_e consecutive envs w*static_e ...
+struct WarpPartition {
+    const int32_t *perm;      // cost-sorted env ids, or null
+    const int32_t *starts;    // [n_warps + 1] offsets into perm, or null
+    const int32_t *n_warps;   // device scalar
+    int32_t static_e;
+};
+
+__global__ void __launch_bounds__(PCC_WARP_THREADS)
+pcc_step_warp_kernel(DevState p, WarpPartition part, unsigned long long head_step,
+                     const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
+                     uint8_t *__restrict__ done, int32_t *__restrict__ counts, double *__restrict__ info)
+{
+    __shared__ double sbuf[PCC_WARP_THREADS / 32][PCC_WBUF + 32];
+    const Grp<32> g;
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t w = (int64_t)blockIdx.x * (PCC_WARP_THREADS / 32) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
+    int64_t first;
+    int cnt;
+    if (part.starts) {
+        const int nw = *part.n_warps;
+        if (w >= nw) return;                       // whole warp
+        first = part.starts[w];
+        cnt = (int)(part.starts[w + 1] - first);
+    } else {
+        first = w * part.static_e;
+        if (first >= p.n) return;
+        cnt = (int)((p.n - first < part.static_e) ? (p.n - first) : part.static_e);
+    }
+    const bool owner = (int)lane < cnt;
+    const int64_t e = owner ? (part.perm ? (int64_t)part.perm[first + lane] : first + lane) : 0;
+    EnvState s;
+    load_env(p, e, s);
+    PhiloxRng rng;
+    rng.init(p.seed[e], p.draws[e]);
+    s.rate = apply_rate_delta(s.rate, actions[e], p.c);                          // :412
+    StepOut o;
+    double avg_lat, lat_inc;
+    warp_mi<true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], o.mi, avg_lat, lat_inc);   // :416
+    if (!owner) return;
+    mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
+    s.steps += 1;                                                                // :419
+    if (o.st.avg_lat > 0.0) s.run_dur = 0.5 * o.st.avg_lat;                      // :437-438
+    o.done = s.steps >= p.c.max_steps;                                           // :444
+    store_env_dynamic(p, e, s);
+    p.draws[e] = rng.draws;
+    if (o.mi.overflow) flag_overflow(p, e);
+    // history ring + obs row (oldest -> newest), each lane writes its env's contiguous row
+    {
+        const int H = p.H, F = p.F, HF = H * F;
+        const int slot_new = (int)(head_step % (unsigned long long)H);
+        double *hrow = p.hist + (size_t)e * HF;
+        double *ob = obs + (size_t)e * HF;
+        for (int h = 0; h < H - 1; h++) {
+            int sl = slot_new + 1 + h;
+            if (sl >= H) sl -= H;
+            for (int f = 0; f < F; f++) ob[h * F + f] = hrow[sl * F + f];
+        }
+        for (int f = 0; f < F; f++) {
+            const double v = metric_value(o.st, p.ids[f]);
+            ob[(H - 1) * F + f] = v;
+            hrow[slot_new * F + f] = v;
+        }
+    }
+    reward[e] = o.st.reward;
+    done[e] = o.done ? 1 : 0;
+    const double acc = p.ret_acc[e] + o.st.reward;                               // :443
+    p.ret_acc[e] = acc;
+    if (o.done) p.ret_last[e] = acc;
+    if (counts) { counts[3 * e + 0] = o.mi.sent; counts[3 * e + 1] = o.mi.acked; counts[3 * e + 2] = o.mi.lost; }
+    if (info) {
+        double *q = info + (size_t)e * PCC_INFO_WIDTH;
+        q[0] = o.st.send_rate; q[1] = o.st.recv_rate; q[2] = o.st.avg_lat; q[3] = o.st.loss_ratio;
+        q[4] = o.st.lat_infl; q[5] = o.st.lat_ratio; q[6] = o.st.send_ratio; q[7] = o.st.dur;
+        q[8] = s.cur_time; q[9] = s.rate; q[10] = s.run_dur; q[11] = s.conn_min;
+    }
+}
+
+template <int E>
+__global__ void __launch_bounds__(PCC_WARP_THREADS)
+pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double *__restrict__ bw,
+                      const double *__restrict__ delay, const long long *__restrict__ queue,
+                      const double *__restrict__ loss, const double *__restrict__ start_rate,
+                      double *__restrict__ obs)
+{
+    __shared__ double sbuf[PCC_WARP_THREADS / 32][PCC_WBUF + 32];
+    const Grp<32> g;
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t warp_global = (int64_t)blockIdx.x * (PCC_WARP_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t slot = warp_global * E + lane;
+    if (warp_global * E >= p.n) return;   // whole warp
+    bool owner = lane < (unsigned)E && slot < p.n;
+    const int64_t e = owner ? slot : 0;
+    if (mask && !mask[e]) owner = false;
+    EnvState s;
+    const double bwv = bw[e], dlv = delay[e], sr = start_rate[e];
+    // reset_env of pcc_core.cuh (network_sim.py:454-484)
+    s.d_bw = 1.0 / bwv; s.dl = dlv; s.lr = loss[e]; s.max_qd = (double)queue[e] / bwv;
+    s.qd = 0.0; s.t_upd = 0.0; s.rate = sr; s.cur_time = 0.0; s.next_send = 1.0 / sr;
+    s.run_dur = 3 * dlv; s.conn_min = 0.0;
+    s.tail = p.tail[e]; s.h1 = s.tail; s.h2 = s.tail; s.steps = 0;
+    PhiloxRng rng;
+    rng.init(p.seed[e], p.draws[e]);
+    MiOut mo;
+    double a, li;
+    const int cnt = (int)((p.n - warp_global * E < E) ? (p.n - warp_global * E) : E);
+    warp_mi<false>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], mo, a, li);   // :478
+    bool ovf = mo.overflow;
+    warp_mi<false>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], mo, a, li);   // :479
+    ovf = ovf || mo.overflow;
+    if (!owner) return;
+    const int HF = p.H * p.F;
+    for (int k = 0; k < HF; k++) {
+        const double v = metric_empty(p.ids[k % p.F]);
+        p.hist[(size_t)e * HF + k] = v;
+        if (obs) obs[(size_t)e * HF + k] = v;
+    }
+    p.d_bw[e] = s.d_bw; p.bw[e] = bwv; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd;
+    store_env_dynamic(p, e, s);
+    p.draws[e] = rng.draws;
+    p.ret_acc[e] = 0.0;
+    if (ovf) flag_overflow(p, e);
+}
+
+// ---- work-balanced partition (rebalance) -----------------------------------------------------
+// cost model of one env-MI in SM cycles: fixed cooperative overhead + per-packet work
+struct CostModel { float c0, c1; int32_t target_warps; };
+
+__global__ void pcc_cost_kernel(DevState p, CostModel cm, uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    const double pk = p.rate[e] * p.run_dur[e];            // packets the next MI will send, roughly
+    const double c = (double)cm.c0 + (double)cm.c1 * (pk > 0.0 ? pk : 0.0);
+    keys[e] = (uint32_t)fmin(c, 4.0e9);
+    vals[e] = (int32_t)e;
+}
+
+// one block: T = max(heaviest env, total / target_warps); per-env cost floor T/32 caps a warp at 32 envs
+__global__ void pcc_target_kernel(const uint32_t *__restrict__ sorted_cost, int64_t n, CostModel cm,
+                                  unsigned long long *__restrict__ target)
+{
+    __shared__ unsigned long long part[32];
+    unsigned long long acc = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += sorted_cost[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) tot += part[k];
+        unsigned long long t = tot / (unsigned long long)(cm.target_warps > 0 ? cm.target_warps : 1);
+        const unsigned long long mx = sorted_cost[0];
+        if (t < mx) t = mx;
+        if (t < 32) t = 32;
+        target[0] = t;
+    }
+}
+
+__global__ void pcc_costfloor_kernel(const uint32_t *__restrict__ sorted_cost, int64_t n,
+                                     const unsigned long long *__restrict__ target,
+                                     unsigned long long *__restrict__ cost64)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long fl = target[0] / 32ull + 1ull;
+    const unsigned long long c = sorted_cost[i];
+    cost64[i] = c > fl ? c : fl;
+}
+
+// warp id of sorted position i = floor(exclusive prefix cost / T); ids are gap-free (cost' <= T)
+__global__ void pcc_heads_kernel(const unsigned long long *__restrict__ cum_excl, int64_t n,
+                                 const unsigned long long *__restrict__ target, int32_t *__restrict__ starts,
+                                 int32_t *__restrict__ n_warps, long long max_warps, unsigned long long *meta)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long t = target[0];
+    const long long wid = (long long)(cum_excl[i] / t);
+    const long long prev = (i == 0) ? -1 : (long long)(cum_excl[i - 1] / t);
+    if (wid != prev) starts[wid] = (int32_t)i;
+    if (i == n - 1) {
+        starts[wid + 1] = (int32_t)n;
+        n_warps[0] = (int32_t)(wid + 1);
+        if (wid + 1 > max_warps) meta[META_PART_ERR] = (unsigned long long)(wid + 1);   // launch grid too small
+    }
+}
+
 template <int RNG>
 __global__ void pcc_reset_kernel(DevState p, const uint8_t *__restrict__ mask,
                                  const double *__restrict__ bw, const double *__restrict__ delay,
@@ -377,7 +642,19 @@ struct pcc_handle_s {
     unsigned long long head;  // steps issued so far (history ring head)
     int64_t launches;
     int block;
-    int group;   // lanes per env of the cooperative kernels (0 = v1 thread-per-env)
+    int group;   // lanes per env of the group-cooperative kernels (0 = off)
+    int epw;     // envs per warp of the warp-owned kernels (0 = off); the default path
+    int rebalance_every;       // re-sort envs by work every this many steps (0 = never)
+    bool rebalance_now;
+    int64_t steps_since_rebalance;
+    uint32_t *sort_keys_in, *sort_keys_out;
+    int32_t *sort_vals_in, *perm;
+    void *sort_tmp;
+    size_t sort_tmp_bytes;
+    unsigned long long *cost64, *cum_excl, *target;
+    int32_t *starts, *n_warps;
+    int64_t max_warps;
+    CostModel cm;
     // staging for pcc_step_host
     double *st_actions, *st_obs, *st_reward;
     uint8_t *st_done;
@@ -513,7 +790,54 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     const char *grp = getenv("PCC_B200_GROUP");
     h->group = grp ? atoi(grp) : 8;
     if (h->group != 0 && h->group != 8 && h->group != 16 && h->group != 32) h->group = 8;
-    if (cfg->rng_kind != PCC_RNG_PHILOX) h->group = 0;   // MT19937 (fidelity mode) runs the scalar kernels
+    // execution mode: "warp" (default: a warp owns E envs), "group" (G lanes per env), "scalar" (1 thread per env)
+    const char *mode = getenv("PCC_B200_MODE");
+    const char *epw = getenv("PCC_B200_EPW");
+    h->epw = 0;
+    if (!mode || !strcmp(mode, "warp")) {
+        if (epw) h->epw = atoi(epw);
+        else {   // aim at >= ~12 warps per SM (148 SMs), at most 32 envs per warp
+            const int64_t per = cfg->n_envs / (148 * 12);
+            h->epw = per >= 32 ? 32 : per >= 16 ? 16 : per >= 8 ? 8 : 4;
+        }
+        if (h->epw != 4 && h->epw != 8 && h->epw != 16 && h->epw != 32) h->epw = 8;
+        h->group = 0;
+    } else if (!strcmp(mode, "scalar")) {
+        h->group = 0;
+    }
+    if (cfg->rng_kind != PCC_RNG_PHILOX) { h->group = 0; h->epw = 0; }   // MT19937 (fidelity mode): scalar kernels
+    const char *reb = getenv("PCC_B200_REBALANCE");
+    h->rebalance_every = reb ? atoi(reb) : 16;
+    h->rebalance_now = true;
+    h->steps_since_rebalance = 0;
+    if (h->epw && h->rebalance_every > 0) {
+        const size_t n = (size_t)cfg->n_envs;
+        cudaError_t ce = cudaMalloc(&h->sort_keys_in, 4 * n);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->sort_keys_out, 4 * n);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->sort_vals_in, 4 * n);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->perm, 4 * n);
+        h->sort_tmp_bytes = 0;
+        if (ce == cudaSuccess)
+            ce = cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->sort_keys_in, h->sort_keys_out,
+                                                           h->sort_vals_in, h->perm, (int)n);
+        size_t scan_bytes = 0;
+        if (ce == cudaSuccess)
+            ce = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->cost64, h->cum_excl, (int)n);
+        if (scan_bytes > h->sort_tmp_bytes) h->sort_tmp_bytes = scan_bytes;
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->sort_tmp, h->sort_tmp_bytes);
+        const char *c0 = getenv("PCC_B200_COST0"), *c1 = getenv("PCC_B200_COST1"), *tw = getenv("PCC_B200_TARGET_WARPS");
+        h->cm.c0 = c0 ? (float)atof(c0) : 4000.0f;
+        h->cm.c1 = c1 ? (float)atof(c1) : 60.0f;
+        h->cm.target_warps = tw ? atoi(tw) : 148 * 16;
+        h->max_warps = (int64_t)h->cm.target_warps + (int64_t)n / 16 + 8;
+        if (h->max_warps > (int64_t)n) h->max_warps = (int64_t)n;
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->cost64, 8 * n);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->cum_excl, 8 * n);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->target, 8);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->starts, 4 * (n + 2));
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->n_warps, 4);
+        if (ce != cudaSuccess) { delete h; return fail(PCC_ECUDA, "rebalance scratch: %s", cudaGetErrorString(ce)); }
+    }
     if (init) {
         cudaError_t e = cudaMemset(state_dev, 0, L.total);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -544,6 +868,8 @@ void pcc_destroy(pcc_handle h)
     cudaSetDevice(h->cfg.device);
     cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_reward);
     cudaFree(h->st_done); cudaFree(h->st_counts);
+    cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->perm); cudaFree(h->sort_tmp);
+    cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps);
     delete h;
 }
 
@@ -597,7 +923,15 @@ int pcc_reset(pcc_handle h, const uint8_t *mask_dev, const double *bw_dev, const
     const unsigned cgrid = h->group ? (unsigned)((h->cfg.n_envs * h->group + PCC_COOP_THREADS - 1) / PCC_COOP_THREADS) : 0u;
 #define PCC_RESET_COOP(G_) pcc_reset_coop_kernel<G_><<<cgrid, PCC_COOP_THREADS, 0, st>>>( \
         h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rate_dev, obs_dev)
-    if (h->group == 8) PCC_RESET_COOP(8);
+    const unsigned wgrid = h->epw ? (unsigned)((h->cfg.n_envs + (int64_t)h->epw * 4 - 1) / ((int64_t)h->epw * 4)) : 0u;
+#define PCC_RESET_WARP(E_) pcc_reset_warp_kernel<E_><<<wgrid, PCC_WARP_THREADS, 0, st>>>( \
+        h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rate_dev, obs_dev)
+    h->rebalance_now = true;
+    if (h->epw == 4) PCC_RESET_WARP(4);
+    else if (h->epw == 8) PCC_RESET_WARP(8);
+    else if (h->epw == 16) PCC_RESET_WARP(16);
+    else if (h->epw == 32) PCC_RESET_WARP(32);
+    else if (h->group == 8) PCC_RESET_COOP(8);
     else if (h->group == 16) PCC_RESET_COOP(16);
     else if (h->group == 32) PCC_RESET_COOP(32);
     else if (h->cfg.rng_kind == PCC_RNG_PHILOX)
@@ -620,7 +954,35 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
     const unsigned cgrid = h->group ? (unsigned)((h->cfg.n_envs * h->group + PCC_COOP_THREADS - 1) / PCC_COOP_THREADS) : 0u;
 #define PCC_STEP_COOP(G_) pcc_step_coop_kernel<G_><<<cgrid, PCC_COOP_THREADS, 0, st>>>( \
         h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev)
-    if (h->group == 8) PCC_STEP_COOP(8);
+    if (h->epw) {
+        WarpPartition part{nullptr, nullptr, nullptr, h->epw};
+        int64_t nwarps = (h->cfg.n_envs + h->epw - 1) / h->epw;
+        if (h->rebalance_every > 0) {
+            if (h->rebalance_now || h->steps_since_rebalance >= h->rebalance_every) {
+                // cost-sort the envs (descending) and cut the list into warps of ~equal cost
+                const int64_t n = h->cfg.n_envs;
+                const unsigned kg = (unsigned)((n + 255) / 256);
+                pcc_cost_kernel<<<kg, 256, 0, st>>>(h->d, h->cm, h->sort_keys_in, h->sort_vals_in);
+                CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp, h->sort_tmp_bytes, h->sort_keys_in,
+                                                                   h->sort_keys_out, h->sort_vals_in, h->perm, (int)n,
+                                                                   0, 32, st));
+                pcc_target_kernel<<<1, 1024, 0, st>>>(h->sort_keys_out, n, h->cm, h->target);
+                pcc_costfloor_kernel<<<kg, 256, 0, st>>>(h->sort_keys_out, n, h->target, h->cost64);
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(h->sort_tmp, h->sort_tmp_bytes, h->cost64, h->cum_excl, (int)n, st));
+                pcc_heads_kernel<<<kg, 256, 0, st>>>(h->cum_excl, n, h->target, h->starts, h->n_warps, (long long)h->max_warps, h->d.meta);
+                h->rebalance_now = false;
+                h->steps_since_rebalance = 0;
+                h->launches += 6;
+            }
+            h->steps_since_rebalance++;
+            part.perm = h->perm; part.starts = h->starts; part.n_warps = h->n_warps;
+            nwarps = h->max_warps;
+        }
+        const unsigned wgrid = (unsigned)((nwarps + 3) / 4);
+        pcc_step_warp_kernel<<<wgrid, PCC_WARP_THREADS, 0, st>>>(h->d, part, h->head, actions_dev, obs_dev, reward_dev,
+                                                                 done_dev, counts_dev, info_dev);
+    }
+    else if (h->group == 8) PCC_STEP_COOP(8);
     else if (h->group == 16) PCC_STEP_COOP(16);
     else if (h->group == 32) PCC_STEP_COOP(32);
     else if (h->cfg.rng_kind == PCC_RNG_PHILOX)
@@ -668,6 +1030,8 @@ int pcc_check(pcc_handle h, void *stream)
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     unsigned long long meta[META_WORDS];
     CUDA_TRY(cudaMemcpy(meta, h->d.meta, sizeof(meta), cudaMemcpyDeviceToHost));
+    if (meta[META_PART_ERR])
+        return fail(PCC_EINVAL, "internal: work partition produced more warps than were launched");
     if (meta[META_OVF_COUNT]) {
         snprintf(g_err, sizeof(g_err),
                  "in-flight ring overflow in %llu env-MI(s), first env %llu: ring_capacity %lld is too small "
