@@ -44,8 +44,8 @@ def load(rebuild_if_stale=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if rebuild_if_stale and not _build.up_to_date():
+    path = os.environ.get("PCC_B200_LIB") or _build.LIB   # override: experiments with alternative builds
+    if path == _build.LIB and rebuild_if_stale and not _build.up_to_date():
         try:
             _build.build()
         except Exception:

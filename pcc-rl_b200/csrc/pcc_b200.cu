@@ -300,23 +300,30 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
 // kernels (v4: a warp owns E envs, see pcc_warp.cuh) -- Philox streams only
 // ---------------------------------------------------------------------------------------
 #define PCC_WARP_THREADS 128
+#ifndef PCC_WARP_MINBLOCKS
+#define PCC_WARP_MINBLOCKS 4
+#endif
 
 // One MI for the E envs of this warp.  `owner` lanes hold their env's state in `s`.
-template <bool WANT_MEANS>
+template <bool WANT_MEANS, bool DO_SEND>
 __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, bool owner, int cnt, int64_t e, EnvState &s,
                                         PhiloxRng &rng, double dur, double *buf, MiOut &mo, double &avg_lat,
-                                        double &lat_inc)
+                                        double &lat_inc, int32_t sent_before = 0)
 {
     const unsigned lane = g.gl;
     const double end = s.cur_time + dur;            // network_sim.py:124
     const double inv_rate = 1.0 / s.rate;           // :161
     DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
     LaneChain c;
-    c.t = s.next_send; c.q = s.qd; c.tu = s.t_upd; c.tail = s.tail; c.sent = 0; c.ovf = false;
+    c.t = s.next_send; c.q = s.qd; c.tu = s.t_upd; c.tail = s.tail;
+    c.sent = sent_before & 0x7fffffff; c.ovf = sent_before < 0;
     mo.start = s.cur_time;                          // reset_obs :319-324
-    // phase A: E serial chains side by side
-    if (owner) lane_send_phase(c, s, ring, rng, s.h2, p.cap, end, inv_rate);
-    __syncwarp();
+    // phase A: E serial chains side by side (already done by pcc_send_kernel when !DO_SEND)
+    if (DO_SEND) {
+        if (cnt <= 8) coop_send_phase(c, s, ring, rng, owner, cnt, s.h2, p.cap, end, inv_rate);   // warp-uniform branch
+        else if (owner) lane_send_phase(c, s, ring, rng, s.h2, p.cap, end, inv_rate);
+        __syncwarp();
+    }
     // phase B: the warp consumes each env's hop-1 / hop-2 events
     int which = 0, acked = 0, lost = 0;
     double ct = 0.0;
@@ -377,8 +384,9 @@ struct WarpPartition {
     int32_t static_e;
 };
 
-__global__ void __launch_bounds__(PCC_WARP_THREADS)
-pcc_step_warp_kernel(DevState p, WarpPartition part, unsigned long long head_step,
+template <bool SPLIT>   // SPLIT: the sends of this MI were already done by pcc_send_kernel
+__global__ void __launch_bounds__(PCC_WARP_THREADS, PCC_WARP_MINBLOCKS)
+pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__ sent_tmp, unsigned long long head_step,
                      const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
                      uint8_t *__restrict__ done, int32_t *__restrict__ counts, double *__restrict__ info)
 {
@@ -405,10 +413,11 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, unsigned long long head_ste
     load_env(p, e, s);
     PhiloxRng rng;
     rng.init(p.seed[e], p.draws[e]);
-    s.rate = apply_rate_delta(s.rate, actions[e], p.c);                          // :412
+    if (!SPLIT) s.rate = apply_rate_delta(s.rate, actions[e], p.c);              // :412
     StepOut o;
     double avg_lat, lat_inc;
-    warp_mi<true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], o.mi, avg_lat, lat_inc);   // :416
+    warp_mi<true, !SPLIT>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], o.mi, avg_lat, lat_inc,
+                          SPLIT ? sent_tmp[e] : 0);                              // :416
     if (!owner) return;
     mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
     s.steps += 1;                                                                // :419
@@ -476,9 +485,9 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     MiOut mo;
     double a, li;
     const int cnt = (int)((p.n - warp_global * E < E) ? (p.n - warp_global * E) : E);
-    warp_mi<false>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], mo, a, li);   // :478
+    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], mo, a, li);   // :478
     bool ovf = mo.overflow;
-    warp_mi<false>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], mo, a, li);   // :479
+    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], mo, a, li);   // :479
     ovf = ovf || mo.overflow;
     if (!owner) return;
     const int HF = p.H * p.F;
@@ -492,6 +501,41 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     p.draws[e] = rng.draws;
     p.ret_acc[e] = 0.0;
     if (ovf) flag_overflow(p, e);
+}
+
+// Phase A as a kernel of its own (split mode): all sends of the MI for every env, one env per lane
+// in cost-sorted order -- 32 chains of similar length per warp.  The first `heavy_warps` warps take
+// only 4 envs each (the heaviest ones) and draw their Philox blocks with 8 lanes per env.
+__global__ void __launch_bounds__(PCC_WARP_THREADS)
+pcc_send_kernel(DevState p, const int32_t *__restrict__ perm, int heavy_warps, const double *__restrict__ actions,
+                int32_t *__restrict__ sent_tmp)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t w = (int64_t)blockIdx.x * (PCC_WARP_THREADS / 32) + (threadIdx.x >> 5);
+    int64_t first;
+    int cnt;
+    if (w < heavy_warps) { first = 4 * w; cnt = 4; }
+    else { first = 4 * (int64_t)heavy_warps + 32 * (w - heavy_warps); cnt = 32; }
+    if (first >= p.n) return;   // whole warp
+    if (first + cnt > p.n) cnt = (int)(p.n - first);
+    const bool owner = (int)lane < cnt;
+    const int64_t e = owner ? (perm ? (int64_t)perm[first + lane] : first + lane) : 0;
+    EnvState s;
+    load_env(p, e, s);
+    PhiloxRng rng;
+    rng.init(p.seed[e], p.draws[e]);
+    s.rate = apply_rate_delta(s.rate, actions[e], p.c);                          // :412
+    const double end = s.cur_time + s.run_dur;                                   // :124
+    const double inv_rate = 1.0 / s.rate;
+    DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
+    LaneChain c;
+    c.t = s.next_send; c.q = s.qd; c.tu = s.t_upd; c.tail = s.tail; c.sent = 0; c.ovf = false;
+    if (cnt <= 8) coop_send_phase(c, s, ring, rng, owner, cnt, s.h2, p.cap, end, inv_rate);
+    else if (owner) lane_send_phase(c, s, ring, rng, s.h2, p.cap, end, inv_rate);
+    if (!owner) return;
+    p.rate[e] = s.rate; p.next_send[e] = c.t; p.qd[e] = c.q; p.t_upd[e] = c.tu; p.tail[e] = c.tail;
+    p.draws[e] = rng.draws;
+    sent_tmp[e] = c.sent | (c.ovf ? (int32_t)0x80000000 : 0);
 }
 
 // ---- work-balanced partition (rebalance) -----------------------------------------------------
@@ -652,7 +696,8 @@ struct pcc_handle_s {
     void *sort_tmp;
     size_t sort_tmp_bytes;
     unsigned long long *cost64, *cum_excl, *target;
-    int32_t *starts, *n_warps;
+    int32_t *starts, *n_warps, *sent_tmp;
+    bool split;
     int64_t max_warps;
     CostModel cm;
     // staging for pcc_step_host
@@ -790,20 +835,20 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     const char *grp = getenv("PCC_B200_GROUP");
     h->group = grp ? atoi(grp) : 8;
     if (h->group != 0 && h->group != 8 && h->group != 16 && h->group != 32) h->group = 8;
-    // execution mode: "warp" (default: a warp owns E envs), "group" (G lanes per env), "scalar" (1 thread per env)
+    // execution mode: "warp" (a warp owns several envs; best for big batches), "group" (G lanes per env;
+    // best when the batch is too small to fill the chip), "scalar" (1 thread per env).  Default: by size.
     const char *mode = getenv("PCC_B200_MODE");
     const char *epw = getenv("PCC_B200_EPW");
+    const bool small_batch = cfg->n_envs <= 16384;
     h->epw = 0;
-    if (!mode || !strcmp(mode, "warp")) {
-        if (epw) h->epw = atoi(epw);
-        else {   // aim at >= ~12 warps per SM (148 SMs), at most 32 envs per warp
-            const int64_t per = cfg->n_envs / (148 * 12);
-            h->epw = per >= 32 ? 32 : per >= 16 ? 16 : per >= 8 ? 8 : 4;
-        }
+    if ((mode && !strcmp(mode, "warp")) || (!mode && !small_batch)) {
+        h->epw = epw ? atoi(epw) : 8;   // static envs per warp, used only when rebalancing is off
         if (h->epw != 4 && h->epw != 8 && h->epw != 16 && h->epw != 32) h->epw = 8;
         h->group = 0;
-    } else if (!strcmp(mode, "scalar")) {
+    } else if (mode && !strcmp(mode, "scalar")) {
         h->group = 0;
+    } else if (!grp) {
+        h->group = small_batch ? 32 : 8;
     }
     if (cfg->rng_kind != PCC_RNG_PHILOX) { h->group = 0; h->epw = 0; }   // MT19937 (fidelity mode): scalar kernels
     const char *reb = getenv("PCC_B200_REBALANCE");
@@ -828,7 +873,7 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         const char *c0 = getenv("PCC_B200_COST0"), *c1 = getenv("PCC_B200_COST1"), *tw = getenv("PCC_B200_TARGET_WARPS");
         h->cm.c0 = c0 ? (float)atof(c0) : 4000.0f;
         h->cm.c1 = c1 ? (float)atof(c1) : 60.0f;
-        h->cm.target_warps = tw ? atoi(tw) : 148 * 16;
+        h->cm.target_warps = tw ? atoi(tw) : 148 * 32;
         h->max_warps = (int64_t)h->cm.target_warps + (int64_t)n / 16 + 8;
         if (h->max_warps > (int64_t)n) h->max_warps = (int64_t)n;
         if (ce == cudaSuccess) ce = cudaMalloc(&h->cost64, 8 * n);
@@ -836,6 +881,9 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         if (ce == cudaSuccess) ce = cudaMalloc(&h->target, 8);
         if (ce == cudaSuccess) ce = cudaMalloc(&h->starts, 4 * (n + 2));
         if (ce == cudaSuccess) ce = cudaMalloc(&h->n_warps, 4);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->sent_tmp, 4 * n);
+        const char *sp = getenv("PCC_B200_SPLIT");
+        h->split = sp ? atoi(sp) != 0 : false;   // two-kernel variant: measured slower, kept for experiments
         if (ce != cudaSuccess) { delete h; return fail(PCC_ECUDA, "rebalance scratch: %s", cudaGetErrorString(ce)); }
     }
     if (init) {
@@ -869,7 +917,7 @@ void pcc_destroy(pcc_handle h)
     cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_reward);
     cudaFree(h->st_done); cudaFree(h->st_counts);
     cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->perm); cudaFree(h->sort_tmp);
-    cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps);
+    cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps); cudaFree(h->sent_tmp);
     delete h;
 }
 
@@ -979,8 +1027,23 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
             nwarps = h->max_warps;
         }
         const unsigned wgrid = (unsigned)((nwarps + 3) / 4);
-        pcc_step_warp_kernel<<<wgrid, PCC_WARP_THREADS, 0, st>>>(h->d, part, h->head, actions_dev, obs_dev, reward_dev,
-                                                                 done_dev, counts_dev, info_dev);
+        if (h->split && part.perm) {
+            const int64_t n = h->cfg.n_envs;
+            int64_t heavy_envs = n / 64;
+            if (heavy_envs > 4096) heavy_envs = 4096;
+            const int heavy_warps = (int)(heavy_envs / 4);
+            const int64_t sw = heavy_warps + (n - 4 * (int64_t)heavy_warps + 31) / 32;
+            pcc_send_kernel<<<(unsigned)((sw + 3) / 4), PCC_WARP_THREADS, 0, st>>>(h->d, h->perm, heavy_warps, actions_dev,
+                                                                                 h->sent_tmp);
+            pcc_step_warp_kernel<true><<<wgrid, PCC_WARP_THREADS, 0, st>>>(h->d, part, h->sent_tmp, h->head, actions_dev,
+                                                                           obs_dev, reward_dev, done_dev, counts_dev,
+                                                                           info_dev);
+            h->launches++;
+        } else {
+            pcc_step_warp_kernel<false><<<wgrid, PCC_WARP_THREADS, 0, st>>>(h->d, part, nullptr, h->head, actions_dev,
+                                                                            obs_dev, reward_dev, done_dev, counts_dev,
+                                                                            info_dev);
+        }
     }
     else if (h->group == 8) PCC_STEP_COOP(8);
     else if (h->group == 16) PCC_STEP_COOP(16);

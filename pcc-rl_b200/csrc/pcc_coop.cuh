@@ -402,7 +402,7 @@ __device__ __forceinline__ double coop_leaf(const Grp<G> &g, const double *a, in
 
 // Streaming re-read of the MI's samples for n > PCC_LEAF: acked, not-dead records of
 // [s_begin, s_end) in ring order, then the one possible out-of-order sample `extra`.
-template <int G, class Ring>
+template <int G, class Ring, int W = 1>
 struct CoopSamples {
     const Grp<G> &g;
     Ring &ring;
@@ -415,19 +415,28 @@ struct CoopSamples {
         : g(g_), ring(r), buf(b), i(o.s_begin), end(o.s_end), dl(dl_), extra(o.extra),
           extra_pending(o.has_extra), fill(0) {}
 
+    // buf must hold PCC_LEAF + W * G samples
     __device__ __forceinline__ void fill_until(int need)   // need <= PCC_LEAF
     {
         while (fill < need && (i != end || extra_pending)) {
             if (i != end) {
-                const uint32_t idx = i + g.gl;
-                const bool valid = (int32_t)(idx - end) < 0;
-                Rec r; r.a = 0.0; r.l = -1.0;
-                if (valid) r = ring.load(idx);
-                const bool keep = valid && !is_dead(r.a) && !sgn(r.l);
-                const unsigned km = g.gballot(keep);
-                if (keep) buf[fill + __popc(km & Grp<G>::lowmask((int)g.gl))] = r.l + dl;   // rtt = fl(ll + dl)
-                fill += __popc(km);
-                i = ((uint32_t)(end - i) < (uint32_t)G) ? end : i + (uint32_t)G;
+                Rec r[W];
+                bool valid[W];
+#pragma unroll
+                for (int w = 0; w < W; w++) {       // W independent loads in flight
+                    const uint32_t idx = i + (uint32_t)(w * G) + g.gl;
+                    valid[w] = (int32_t)(idx - end) < 0;
+                    r[w].a = 0.0; r[w].l = -1.0;
+                    if (valid[w]) r[w] = ring.load(idx);
+                }
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    const bool keep = valid[w] && !is_dead(r[w].a) && !sgn(r[w].l);
+                    const unsigned km = g.gballot(keep);
+                    if (keep) buf[fill + __popc(km & Grp<G>::lowmask((int)g.gl))] = r[w].l + dl;   // rtt = fl(ll + dl)
+                    fill += __popc(km);
+                }
+                i = ((uint32_t)(end - i) < (uint32_t)(W * G)) ? end : i + (uint32_t)(W * G);
             } else {
                 if (g.gl == 0) buf[fill] = extra;
                 fill++;
@@ -438,19 +447,27 @@ struct CoopSamples {
     }
     __device__ __forceinline__ void consume(int cnt)
     {
-        const int rem = fill - cnt;   // < G by construction of fill_until
-        double v = 0.0;
-        if ((int)g.gl < rem) v = buf[cnt + (int)g.gl];
+        const int rem = fill - cnt;   // < W * G by construction of fill_until
+        double v[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const int k = w * G + (int)g.gl;
+            v[w] = (k < rem) ? buf[cnt + k] : 0.0;
+        }
         g.gsync();
-        if ((int)g.gl < rem) buf[(int)g.gl] = v;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const int k = w * G + (int)g.gl;
+            if (k < rem) buf[k] = v[w];
+        }
         fill = rem;
         g.gsync();
     }
 };
 
 // pairwise sum of the next n samples of the stream (numpy's recursion, iterative post-order)
-template <int G, class Ring>
-__device__ __noinline__ double coop_pw_sum(const Grp<G> &g, CoopSamples<G, Ring> &st, int n)
+template <int G, class Ring, int W>
+__device__ __noinline__ double coop_pw_sum(const Grp<G> &g, CoopSamples<G, Ring, W> &st, int n)
 {
     int right_n[PCC_PW_STACK];
     double left_sum[PCC_PW_STACK];

@@ -104,7 +104,12 @@ PCC_HD double res53(uint32_t a, uint32_t b)
 }
 
 #define PCC_PHILOX_DOMAIN 0x50434352u
-PCC_HD void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1)
+#if defined(__CUDA_ARCH__) && defined(PCC_PHILOX_NOINLINE)
+__device__ __noinline__
+#else
+PCC_HD
+#endif
+void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1)
 {
 #if defined(__CUDACC__)
 #pragma unroll

@@ -38,6 +38,73 @@ struct ConsumeOut {
     double cur_time;   // valid for which != 0
 };
 
+// ---- rare paths, kept out of line so the common path stays small in the instruction cache ------
+
+// General hop-1 boundary analysis (pcc_core.cuh::run_mi phase 2): cluster starting at h1 whose first
+// record is a dropped packet -- stragglers + tuple-order minimum over the cluster remainder.
+template <class Ring>
+__device__ __noinline__ void boundary1_slow(Ring ring, uint32_t h1, uint32_t tail, double end, bool &has1,
+                                            uint32_t &m1, double &m1a, double &m1l, bool &m1d)
+{
+    constexpr int G = 32;
+    const Grp<32> g;
+    has1 = false; m1 = 0; m1a = 0.0; m1l = 0.0; m1d = false;
+    uint32_t kk = h1;
+    bool open = (kk != tail);
+    while (open) {
+        bool valid;
+        const Rec r = load_window(g, ring, kk, tail, true, valid);
+        const bool dr = sgn(r.l);
+        const unsigned validm = __ballot_sync(PCC_FULL, valid);
+        const unsigned ndm = __ballot_sync(PCC_FULL, valid && !dr);
+        const int pend = ndm ? (__ffs(ndm) - 1) : G;   // accepted record closes the cluster
+        const bool pending = valid && (int)g.gl <= pend && !sgn(r.a);
+        const bool strag = pending && (r.a < end);
+        if (strag) ring.store_a(kk + g.gl, negd(r.a));
+        window_argmin(g, pending && !strag, r.a, absd(r.l), dr, kk, has1, m1, m1a, m1l, m1d);
+        open = (pend == G) && (validm == 0xffffffffu) && ((uint32_t)(kk + G) != tail);
+        kk += G;
+    }
+    __syncwarp();   // straggler flags are read by the hop-2 scan
+}
+
+// General hop-2 boundary analysis (phase 3): the live record at h2 is a dropped packet.
+template <class Ring>
+__device__ __noinline__ void boundary2_slow(Ring ring, uint32_t h1, uint32_t h2, uint32_t tail, double dl, double end,
+                                            int32_t &acked, int32_t &lost, double &extra, bool &has_extra,
+                                            bool &has2, uint32_t &m2, double &m2b, double &m2l, bool &m2d)
+{
+    constexpr int G = 32;
+    const Grp<32> g;
+    has2 = false; m2 = 0; m2b = 0.0; m2l = 0.0; m2d = false;
+    uint32_t kk = h2;
+    bool open = true;
+    while (open) {
+        bool valid;
+        const Rec r = load_window(g, ring, kk, tail, true, valid);
+        const bool dr = sgn(r.l);
+        const bool dead = is_dead(r.a);
+        const bool c1 = ((int32_t)(kk + g.gl - h1) < 0) || sgn(r.a);
+        const unsigned x1 = __ballot_sync(PCC_FULL, !valid || (!dead && !c1));   // stop BEFORE this record
+        const unsigned x2 = __ballot_sync(PCC_FULL, valid && !dr);               // stop AFTER this record
+        const int p1 = x1 ? (__ffs(x1) - 1) : G;
+        const int p2 = x2 ? (__ffs(x2) - 1) : G;
+        const bool act = (int)g.gl < p1 && (int)g.gl <= p2 && !dead;
+        const double b = absd(r.a) + dl;
+        const double l2 = absd(r.l) + dl;
+        const bool strag = act && (b < end);
+        const unsigned sa = __ballot_sync(PCC_FULL, strag && !dr), sl = __ballot_sync(PCC_FULL, strag && dr);
+        const double ex = __shfl_sync(PCC_FULL, l2, sa ? (__ffs(sa) - 1) : 0);
+        if (sa) { extra = ex; has_extra = true; }   // at most one acked per cluster
+        acked += __popc(sa);
+        lost += __popc(sl);
+        if (strag) ring.store_a(kk + g.gl, u2d(PCC_NEG_INF));
+        window_argmin(g, act && !strag, b, l2, dr, kk, has2, m2, m2b, m2l, m2d);
+        open = (p1 == G) && (p2 == G);
+        kk += G;
+    }
+}
+
 // Phases (2)-(4) of run_mi for ONE env by the whole warp.  All inputs and outputs warp-uniform.
 template <class Ring>
 __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeIn &in, Ring &ring, double *buf,
@@ -72,32 +139,19 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
         h1 += (uint32_t)adv;
         if (stop) break;
     }
+    // boundary: the record at h1 (if any) is pending with a >= end.  If it is an ACCEPTED packet it
+    // is a cluster of its own: no stragglers, and it is the smallest pending hop-1 key.
     bool has1 = false;
-    uint32_t m1 = 0; double m1a = 0.0, m1l = 0.0; bool m1d = false;
-    {
-        uint32_t kk = h1;
-        bool open = (kk != tail);
-        while (open) {
-            bool valid;
-            const Rec r = load_window(g, ring, kk, tail, true, valid);
-            const bool dr = sgn(r.l);
-            const unsigned validm = __ballot_sync(PCC_FULL, valid);
-            const unsigned ndm = __ballot_sync(PCC_FULL, valid && !dr);
-            const int pend = ndm ? (__ffs(ndm) - 1) : G;   // accepted record closes the cluster
-            const bool pending = valid && (int)g.gl <= pend && !sgn(r.a);
-            const bool strag = pending && (r.a < end);
-            if (strag) ring.store_a(kk + g.gl, negd(r.a));
-            window_argmin(g, pending && !strag, r.a, absd(r.l), dr, kk, has1, m1, m1a, m1l, m1d);
-            open = (pend == G) && (validm == 0xffffffffu) && ((uint32_t)(kk + G) != tail);
-            kk += G;
-        }
-        __syncwarp();   // straggler flags are read by the hop-2 scan
+    uint32_t m1 = h1; double m1a = 0.0, m1l = 0.0; bool m1d = false;
+    if (h1 != tail) {
+        const Rec r = ring.load(h1);               // same address in every lane: one broadcast load
+        if (!sgn(r.l)) { has1 = true; m1a = r.a; m1l = r.l; }
+        else boundary1_slow(ring, h1, tail, end, has1, m1, m1a, m1l, m1d);
     }
 
     // ---- hop-2 events with b < end; acked latencies staged for np.mean ---------------------------
-    bool at_live = false;
     for (;;) {
-        unsigned bm[PCC_SCAN_W], am[PCC_SCAN_W], lm[PCC_SCAN_W], lv[PCC_SCAN_W];
+        unsigned bm[PCC_SCAN_W], am[PCC_SCAN_W], lm[PCC_SCAN_W];
         double l2[PCC_SCAN_W];
 #pragma unroll
         for (int w = 0; w < PCC_SCAN_W; w++) {
@@ -111,7 +165,6 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
             bm[w] = __ballot_sync(PCC_FULL, cons);
             am[w] = __ballot_sync(PCC_FULL, cons && !dead && !sgn(r.l));        // :144-145
             lm[w] = __ballot_sync(PCC_FULL, cons && !dead && sgn(r.l));         // :141-142
-            lv[w] = __ballot_sync(PCC_FULL, valid && !dead && c1 && !early);
             l2[w] = r.l + in.dl;                                  // rtt = fl(ll + dl)
         }
         int adv = 0;
@@ -129,7 +182,6 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
                 acked += __popc(a_w);
                 lost += __popc(lm[w] & lead);
                 adv += nl;
-                if (nl < G) at_live = ((lv[w] >> nl) & 1u) != 0u;
             }
             stop = stop || (nl < G);
         }
@@ -137,34 +189,17 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
         if (stop) break;
     }
     out.s_end = h2;
+    // boundary: the record at h2 (if any) is not consumable.  It carries a live hop-2 event iff its
+    // hop-1 event is consumed (then b >= end).  An accepted packet is a cluster of its own.
     bool has2 = false;
-    uint32_t m2 = 0; double m2b = 0.0, m2l = 0.0; bool m2d = false;
-    {
-        uint32_t kk = h2;
-        bool open = at_live;
-        while (open) {
-            bool valid;
-            const Rec r = load_window(g, ring, kk, tail, true, valid);
-            const bool dr = sgn(r.l);
-            const bool dead = is_dead(r.a);
-            const bool c1 = ((int32_t)(kk + g.gl - h1) < 0) || sgn(r.a);
-            const unsigned x1 = __ballot_sync(PCC_FULL, !valid || (!dead && !c1));   // stop BEFORE this record
-            const unsigned x2 = __ballot_sync(PCC_FULL, valid && !dr);               // stop AFTER this record
-            const int p1 = x1 ? (__ffs(x1) - 1) : G;
-            const int p2 = x2 ? (__ffs(x2) - 1) : G;
-            const bool act = (int)g.gl < p1 && (int)g.gl <= p2 && !dead;
-            const double b = absd(r.a) + in.dl;
-            const double l2 = absd(r.l) + in.dl;
-            const bool strag = act && (b < end);
-            const unsigned sa = __ballot_sync(PCC_FULL, strag && !dr), sl = __ballot_sync(PCC_FULL, strag && dr);
-            const double ex = __shfl_sync(PCC_FULL, l2, sa ? (__ffs(sa) - 1) : 0);
-            if (sa) { out.extra = ex; out.has_extra = true; }   // at most one acked per cluster
-            acked += __popc(sa);
-            lost += __popc(sl);
-            if (strag) ring.store_a(kk + g.gl, u2d(PCC_NEG_INF));
-            window_argmin(g, act && !strag, b, l2, dr, kk, has2, m2, m2b, m2l, m2d);
-            open = (p1 == G) && (p2 == G);
-            kk += G;
+    uint32_t m2 = h2; double m2b = 0.0, m2l = 0.0; bool m2d = false;
+    if (h2 != tail) {
+        const Rec r = ring.load(h2);
+        const bool c1 = ((int32_t)(h2 - h1) < 0) || sgn(r.a);
+        if (c1) {
+            if (!sgn(r.l)) { has2 = true; m2b = absd(r.a) + in.dl; m2l = r.l + in.dl; }
+            else boundary2_slow(ring, h1, h2, tail, in.dl, end, acked, lost, out.extra, out.has_extra,
+                                has2, m2, m2b, m2l, m2d);
         }
     }
 
@@ -225,16 +260,15 @@ __device__ __forceinline__ double pw_smem(const Grp<32> &g, const double *a, int
     }
 }
 
-// avg latency (sender_obs.py:119-122) and latency increase (:138-142) of one env's MI, warp-wide
+// n > PCC_LEAF (rare): recursion over the staging buffer, or streaming re-read of the ring
 template <class Ring>
-__device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut &co, Ring &ring, double dl,
-                                              double *buf, bool need_increase, double &avg_lat, double &lat_increase)
+__device__ __noinline__ void mi_means_big(ConsumeOut co, Ring ring, double dl, double *buf, bool need_increase,
+                                          double &avg_lat, double &lat_increase)
 {
+    const Grp<32> g;
     const int n = co.acked;
-    avg_lat = 0.0;
-    lat_increase = 0.0;
-    if (n <= 0) return;
     const int half = n / 2;
+    lat_increase = 0.0;
     if (n <= PCC_WBUF) {
         double sum = 0.0;
         sum += pw_smem(g, buf, n);
@@ -249,13 +283,13 @@ __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut
         MiOut o;
         o.s_begin = co.s_begin; o.s_end = co.s_end; o.extra = co.extra; o.has_extra = co.has_extra;
         {
-            CoopSamples<32, Ring> st(g, ring, buf, o, dl);
+            CoopSamples<32, Ring, 4> st(g, ring, buf, o, dl);
             double sum = 0.0;
             sum += coop_pw_sum(g, st, n);
             avg_lat = sum / (double)n;
         }
         if (need_increase) {
-            CoopSamples<32, Ring> st(g, ring, buf, o, dl);
+            CoopSamples<32, Ring, 4> st(g, ring, buf, o, dl);
             double s1 = 0.0, s2 = 0.0;
             s1 += coop_pw_sum(g, st, half);
             s2 += coop_pw_sum(g, st, n - half);
@@ -263,6 +297,53 @@ __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut
         }
     }
     __syncwarp();
+}
+
+// avg latency (sender_obs.py:119-122) and latency increase (:138-142) of one env's MI, warp-wide
+template <class Ring>
+__device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut &co, Ring &ring, double dl,
+                                              double *buf, bool need_increase, double &avg_lat, double &lat_increase)
+{
+    const int n = co.acked;
+    avg_lat = 0.0;
+    lat_increase = 0.0;
+    if (n <= 0) return;
+    const int half = n / 2;
+    if (n <= PCC_LEAF) {
+        // the common case: total, first half and second half are single numpy leaves; evaluate the
+        // three concurrently on three 8-lane subgroups (lanes 0-7, 8-15, 16-23)
+        const int sub = (int)(g.gl >> 3), j = (int)(g.gl & 7u);
+        const int off = (sub == 2) ? half : 0;
+        const int cnt = (sub == 0) ? n : (sub == 1) ? half : (sub == 2) ? (n - half) : 0;
+        const double *a = buf + off;
+        const int nb = cnt - (cnt % 8);
+        double r = 0.0;
+        if (cnt >= 8) {
+            r = a[j];
+            for (int k = 8; k < nb; k += 8) r += a[k + j];
+        }
+        r += __shfl_xor_sync(PCC_FULL, r, 1);
+        r += __shfl_xor_sync(PCC_FULL, r, 2);
+        r += __shfl_xor_sync(PCC_FULL, r, 4);
+        double res;
+        if (cnt >= 8) { res = r; for (int k = nb; k < cnt; k++) res += a[k]; }
+        else { res = 0.; for (int k = 0; k < cnt; k++) res += a[k]; }
+        const double tot = __shfl_sync(PCC_FULL, res, 0);
+        const double f1 = __shfl_sync(PCC_FULL, res, 8);
+        const double f2 = __shfl_sync(PCC_FULL, res, 16);
+        double sum = 0.0;
+        sum += tot;
+        avg_lat = sum / (double)n;
+        if (need_increase && half >= 1) {
+            double s1 = 0.0, s2 = 0.0;
+            s1 += f1;
+            s2 += f2;
+            lat_increase = s2 / (double)(n - half) - s1 / (double)half;
+        }
+        __syncwarp();
+    } else {
+        mi_means_big(co, ring, dl, buf, need_increase, avg_lat, lat_increase);
+    }
 }
 
 // One packet of the send phase, branch-free (network_sim.py:156-178 -> :66-84).
@@ -313,6 +394,65 @@ __device__ __forceinline__ void lane_send_phase(LaneChain &c, const EnvState &s,
             rng.draws++;
         }
     }
+}
+
+
+// Send phase of a warp that owns few envs (cnt <= 8): the chains stay on the owner lanes, but the
+// loss draws are produced by ALL lanes -- LPE = 32/cnt (power of two) lanes per env, one Philox
+// block (2 draws) per lane and round -- and handed to the owner lane through two ballots.
+template <class Ring>
+__device__ __forceinline__ void coop_send_phase(LaneChain &c, const EnvState &s, Ring &ring, PhiloxRng &rng,
+                                                bool owner, int cnt, uint32_t h2, uint32_t cap, double end,
+                                                double inv_rate)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int lpe = (cnt <= 1) ? 32 : (cnt <= 2) ? 16 : (cnt <= 4) ? 8 : 4;   // lanes per env
+    const int sh = (lpe == 32) ? 5 : (lpe == 16) ? 4 : (lpe == 8) ? 3 : 2;
+    const int serve = (int)(lane >> sh);            // env (owner lane) this lane draws for
+    const unsigned sub = lane & (unsigned)(lpe - 1);
+    const unsigned grp_low = (lpe == 32) ? 0xffffffffu : ((1u << lpe) - 1u);
+    bool more = owner && (c.t < end);
+    while (__any_sync(PCC_FULL, more)) {
+        const unsigned long long sd = __shfl_sync(PCC_FULL, (unsigned long long)rng.seed, serve);
+        const unsigned long long dr = __shfl_sync(PCC_FULL, (unsigned long long)rng.draws, serve);
+        const double lr = __shfl_sync(PCC_FULL, s.lr, serve);
+        uint32_t c0, c1, c2, c3;
+        philox_block(sd, (dr >> 1) + sub, c0, c1, c2, c3);
+        const unsigned be_all = __ballot_sync(PCC_FULL, res53(c0, c1) < lr);
+        const unsigned bo_all = __ballot_sync(PCC_FULL, res53(c2, c3) < lr);
+        if (more) {
+            const unsigned off = (unsigned)(rng.draws & 1ull);
+            const unsigned shl = lane << sh;        // this owner's lanes start at lane * lpe
+            uint64_t dm = interleave_bits((be_all >> shl) & grp_low, (bo_all >> shl) & grp_low) >> off;
+            const int navail = 2 * lpe - (int)off;
+            int k = 0;
+#pragma unroll 2
+            for (; k < navail; ++k) {
+                if (!(c.t < end)) break;
+                const bool rdrop = (dm & 1ull) != 0ull;                            // :73
+                dm >>= 1;
+                const long long yb = __double_as_longlong(c.q - (c.t - c.tu));     // :66-67
+                const double w = __longlong_as_double(yb & ~(yb >> 63));            // max(0.0, y)
+                const double cc = s.d_bw + w;                                       // :77-79
+                const bool full = cc > s.max_qd;
+                const double ll = s.dl + w;                                         // :69-70
+                c.q = rdrop ? c.q : (full ? w : cc);                                // :74-82
+                c.tu = rdrop ? c.tu : c.t;
+                const bool dropped = rdrop || full;
+                Rec r;
+                r.a = c.t + ll;
+                r.l = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
+                if ((uint32_t)(c.tail - h2) >= cap) c.ovf = true;
+                else { ring.store(c.tail, r); c.tail++; }
+                c.t = c.t + inv_rate;                                               // :161
+                c.sent++;
+            }
+            rng.draws += (uint64_t)k;
+            more = (k == navail) && (c.t < end);
+        }
+    }
+    // keep PhiloxRng's cached half consistent for rng.next() (the crossing send)
+    if (owner && (rng.draws & 1ull)) { uint32_t a, b; rng.block(rng.draws >> 1, a, b, rng.w2, rng.w3); }
 }
 
 }  // namespace pcc
