@@ -283,6 +283,14 @@ def main():
     if rank != 0:
         return
     peak, peak_kind = measured_peak_gbs()
+    traffic, traffic_src, kernel_name = None, None, "pcc_step_*"
+    try:   # dram bytes per launch of the dominant kernel, from the committed ncu capture of this workload
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)[args.workload]
+        if n == WORKLOADS[args.workload]["envs"]:
+            traffic, traffic_src, kernel_name = tj["dram_bytes_per_launch"], "profiles/" + tj["source"], tj["kernel"]
+    except Exception:
+        pass
     bytes_total = algorithmic_bytes(n_global * K, g_sent, g_acked)
     achieved = bytes_total / (dev_ms * 1e-3) / 1e9 / world   # per GPU
     line = {
@@ -303,7 +311,8 @@ def main():
         "wall_s_timed_region": wall,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                     "traffic": None, "kernel": "pcc_step_kernel",
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
+                     "algorithmic_bytes_per_launch": bytes_total / (K * world),
                      "algorithmic_bytes_per_env_step": bytes_total / (n_global * K),
                      "packets_sent_per_env_step": g_sent / (n_global * K)},
         "clocks": clocks,

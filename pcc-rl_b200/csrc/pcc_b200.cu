@@ -83,6 +83,7 @@ struct DevRing {
     }
     __device__ __forceinline__ void store_a(uint32_t i, double a) { base[i & mask].a = a; }
     __device__ __forceinline__ const Rec *addr(uint32_t i) const { return base + (i & mask); }
+    __device__ __forceinline__ void prefetch(uint32_t i) const { asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (i & mask))); }
 };
 
 __device__ __forceinline__ void load_env(const DevState &p, int64_t e, EnvState &s)
@@ -108,14 +109,15 @@ __device__ __forceinline__ void flag_overflow(const DevState &p, int64_t e)
 // kernels (v1: one thread per env, every phase scalar; see DESIGN.md for the roofline)
 // ---------------------------------------------------------------------------------------
 template <int RNG>
-__global__ void pcc_step_kernel(DevState p, unsigned long long head_step,
+__global__ void pcc_step_kernel(DevState p, const int32_t *__restrict__ perm, unsigned long long head_step,
                                 const double *__restrict__ actions, double *__restrict__ obs,
                                 double *__restrict__ reward, uint8_t *__restrict__ done,
                                 int32_t *__restrict__ counts, double *__restrict__ info)
 {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0) p.meta[META_HEAD] = head_step + 1ull;
-    if (e >= p.n) return;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0) p.meta[META_HEAD] = head_step + 1ull;
+    if (tid >= p.n) return;
+    const int64_t e = perm ? (int64_t)perm[tid] : tid;   // cost-sorted order: similar work per warp
     EnvState s;
     load_env(p, e, s);
     DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
@@ -698,6 +700,7 @@ struct pcc_handle_s {
     unsigned long long *cost64, *cum_excl, *target;
     int32_t *starts, *n_warps, *sent_tmp;
     bool split;
+    bool scalar_sorted;
     int64_t max_warps;
     CostModel cm;
     // staging for pcc_step_host
@@ -855,7 +858,8 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     h->rebalance_every = reb ? atoi(reb) : 16;
     h->rebalance_now = true;
     h->steps_since_rebalance = 0;
-    if (h->epw && h->rebalance_every > 0) {
+    h->scalar_sorted = (mode && !strcmp(mode, "scalar")) && cfg->rng_kind == PCC_RNG_PHILOX && h->rebalance_every > 0;
+    if ((h->epw || h->scalar_sorted) && h->rebalance_every > 0) {
         const size_t n = (size_t)cfg->n_envs;
         cudaError_t ce = cudaMalloc(&h->sort_keys_in, 4 * n);
         if (ce == cudaSuccess) ce = cudaMalloc(&h->sort_keys_out, 4 * n);
@@ -1002,6 +1006,20 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
     const unsigned cgrid = h->group ? (unsigned)((h->cfg.n_envs * h->group + PCC_COOP_THREADS - 1) / PCC_COOP_THREADS) : 0u;
 #define PCC_STEP_COOP(G_) pcc_step_coop_kernel<G_><<<cgrid, PCC_COOP_THREADS, 0, st>>>( \
         h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev)
+    const int32_t *scalar_perm = nullptr;
+    if (h->scalar_sorted) {
+        if (h->rebalance_now || h->steps_since_rebalance >= h->rebalance_every) {
+            const int64_t n = h->cfg.n_envs;
+            pcc_cost_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d, h->cm, h->sort_keys_in, h->sort_vals_in);
+            CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp, h->sort_tmp_bytes, h->sort_keys_in,
+                                                               h->sort_keys_out, h->sort_vals_in, h->perm, (int)n, 0, 32, st));
+            h->rebalance_now = false;
+            h->steps_since_rebalance = 0;
+            h->launches += 2;
+        }
+        h->steps_since_rebalance++;
+        scalar_perm = h->perm;
+    }
     if (h->epw) {
         WarpPartition part{nullptr, nullptr, nullptr, h->epw};
         int64_t nwarps = (h->cfg.n_envs + h->epw - 1) / h->epw;
@@ -1050,10 +1068,10 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
     else if (h->group == 32) PCC_STEP_COOP(32);
     else if (h->cfg.rng_kind == PCC_RNG_PHILOX)
         pcc_step_kernel<PCC_RNG_PHILOX><<<grid_for(h), h->block, 0, st>>>(
-            h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
+            h->d, scalar_perm, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
     else
         pcc_step_kernel<PCC_RNG_MT19937><<<grid_for(h), h->block, 0, st>>>(
-            h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
+            h->d, nullptr, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
     h->head++;
     h->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -239,6 +239,7 @@ template <class Ring>
 PCC_HD uint32_t scan_hop1(Ring &ring, uint32_t i, uint32_t tail, double bound)
 {
     while (i != tail) {
+        if ((i & 7u) == 0u) ring.prefetch(i + 8u);   // next 128-byte line of this env's ring
         Rec r = ring.load(i);
         if (!sgn(r.a) && !(r.a < bound)) break;
         i++;
@@ -255,6 +256,7 @@ PCC_HD uint32_t scan_hop2(Ring &ring, uint32_t i, uint32_t tail, uint32_t h1, do
 {
     at_live = false;
     while (i != tail) {
+        if ((i & 7u) == 0u) ring.prefetch(i + 8u);
         Rec r = ring.load(i);
         if (!is_dead(r.a)) {
             bool c1 = ((int32_t)(i - h1) < 0) || sgn(r.a);
@@ -398,6 +400,7 @@ struct SampleReader {
     PCC_HD double next()
     {
         while (i != end) {
+            if ((i & 7u) == 0u) ring.prefetch(i + 8u);
             Rec r = ring.load(i);
             i++;
             if (!is_dead(r.a) && !sgn(r.l)) return r.l + dl;   // rtt = fl(ll + dl)

@@ -16,6 +16,7 @@ struct HostRing {
     Rec load(uint32_t i) const { return buf[i & mask]; }
     void store(uint32_t i, Rec r) { buf[i & mask] = r; }
     void store_a(uint32_t i, double a) { buf[i & mask].a = a; }
+    void prefetch(uint32_t) const {}
 };
 
 struct Twin {
