@@ -122,7 +122,7 @@ def run_reference_arm(args, rank, world):
         return
     import oracle
     from pcc_rl_b200 import sample_link_params
-    n = args.envs or WORKLOADS[args.workload]["envs"]
+    n = (args.envs or WORKLOADS[args.workload]["envs"]) * max(1, args.gpus)   # the whole job's env batch
     cores = os.cpu_count() or 1
     seeds = (np.uint64(args.seed) + np.arange(n, dtype=np.uint64))
     ob = oracle.OracleBatch(seeds, n_threads=cores)

@@ -302,6 +302,9 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
 // kernels (v4: a warp owns E envs, see pcc_warp.cuh) -- Philox streams only
 // ---------------------------------------------------------------------------------------
 #define PCC_WARP_THREADS 128
+#ifndef PCC_STAGED_STORES
+#define PCC_STAGED_STORES 0   // 1: stage ring records in shared memory, coalesced copy-out (measured: no gain)
+#endif
 #ifndef PCC_WARP_MINBLOCKS
 #define PCC_WARP_MINBLOCKS 4
 #endif
@@ -309,8 +312,8 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
 // One MI for the E envs of this warp.  `owner` lanes hold their env's state in `s`.
 template <bool WANT_MEANS, bool DO_SEND>
 __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, bool owner, int cnt, int64_t e, EnvState &s,
-                                        PhiloxRng &rng, double dur, double *buf, MiOut &mo, double &avg_lat,
-                                        double &lat_inc, int32_t sent_before = 0)
+                                        PhiloxRng &rng, double dur, double *buf, WarpStage &stage, MiOut &mo,
+                                        double &avg_lat, double &lat_inc, int32_t sent_before = 0)
 {
     const unsigned lane = g.gl;
     const double end = s.cur_time + dur;            // network_sim.py:124
@@ -323,7 +326,11 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
     // phase A: E serial chains side by side (already done by pcc_send_kernel when !DO_SEND)
     if (DO_SEND) {
         if (cnt <= 8) coop_send_phase(c, s, ring, rng, owner, cnt, s.h2, p.cap, end, inv_rate);   // warp-uniform branch
+#if PCC_STAGED_STORES
+        else lane_send_phase_staged(c, s, ring.base, ring.mask, rng, owner, s.h2, p.cap, end, inv_rate, stage);
+#else
         else if (owner) lane_send_phase(c, s, ring, rng, s.h2, p.cap, end, inv_rate);
+#endif
         __syncwarp();
     }
     // phase B: the warp consumes each env's hop-1 / hop-2 events
@@ -393,6 +400,7 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
                      uint8_t *__restrict__ done, int32_t *__restrict__ counts, double *__restrict__ info)
 {
     __shared__ double sbuf[PCC_WARP_THREADS / 32][PCC_WBUF + 32];
+    __shared__ WarpStage sstage[(SPLIT || !PCC_STAGED_STORES) ? 1 : PCC_WARP_THREADS / 32];
     const Grp<32> g;
     const unsigned lane = threadIdx.x & 31u;
     const int64_t w = (int64_t)blockIdx.x * (PCC_WARP_THREADS / 32) + (threadIdx.x >> 5);
@@ -418,7 +426,8 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
     if (!SPLIT) s.rate = apply_rate_delta(s.rate, actions[e], p.c);              // :412
     StepOut o;
     double avg_lat, lat_inc;
-    warp_mi<true, !SPLIT>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], o.mi, avg_lat, lat_inc,
+    warp_mi<true, !SPLIT>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5],
+                          sstage[(SPLIT || !PCC_STAGED_STORES) ? 0 : (threadIdx.x >> 5)], o.mi, avg_lat, lat_inc,
                           SPLIT ? sent_tmp[e] : 0);                              // :416
     if (!owner) return;
     mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
@@ -467,6 +476,7 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
                       double *__restrict__ obs)
 {
     __shared__ double sbuf[PCC_WARP_THREADS / 32][PCC_WBUF + 32];
+    __shared__ WarpStage sstage[PCC_STAGED_STORES ? PCC_WARP_THREADS / 32 : 1];
     const Grp<32> g;
     const unsigned lane = threadIdx.x & 31u;
     const int64_t warp_global = (int64_t)blockIdx.x * (PCC_WARP_THREADS / 32) + (threadIdx.x >> 5);
@@ -487,9 +497,9 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     MiOut mo;
     double a, li;
     const int cnt = (int)((p.n - warp_global * E < E) ? (p.n - warp_global * E) : E);
-    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], mo, a, li);   // :478
+    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], sstage[PCC_STAGED_STORES ? (threadIdx.x >> 5) : 0], mo, a, li);   // :478
     bool ovf = mo.overflow;
-    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], mo, a, li);   // :479
+    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], sstage[PCC_STAGED_STORES ? (threadIdx.x >> 5) : 0], mo, a, li);   // :479
     ovf = ovf || mo.overflow;
     if (!owner) return;
     const int HF = p.H * p.F;

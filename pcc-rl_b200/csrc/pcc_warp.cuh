@@ -23,7 +23,9 @@
 
 namespace pcc {
 
+#ifndef PCC_WBUF
 #define PCC_WBUF 1024   // samples staged per warp (8 KB); MIs with more acks re-read the ring
+#endif
 
 struct ConsumeIn {
     double end, dl, tnext;
@@ -396,6 +398,60 @@ __device__ __forceinline__ void lane_send_phase(LaneChain &c, const EnvState &s,
     }
 }
 
+
+// Same as lane_send_phase, but the records are staged in shared memory (8 per lane) and written to
+// the rings by the whole warp: 8 lanes copy one env's 128-byte line, 4 envs per store instruction.
+// (Per-lane 16-byte stores are 32 wavefronts each and hold their registers until the LSU takes
+// them -- ncu showed 30 % of the send phase stalled on exactly that.)  Warp-uniform control flow.
+#define PCC_STAGE_N 8
+struct WarpStage { double2 rec[32][PCC_STAGE_N + 1]; };   // rows padded to 144 B: conflict-free both ways
+
+__device__ __forceinline__ void lane_send_phase_staged(LaneChain &c, const EnvState &s, Rec *ring_base, uint32_t mask,
+                                                       PhiloxRng &rng, bool owner, uint32_t h2, uint32_t cap,
+                                                       double end, double inv_rate, WarpStage &st)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    bool active = owner && (c.t < end);
+    while (__any_sync(PCC_FULL, active)) {
+        int nst = 0;
+        if (active) {
+#pragma unroll 1
+            while (nst < PCC_STAGE_N && c.t < end) {
+                const double u = rng.next();
+                const bool rdrop = u < s.lr;                                        // :73
+                const long long yb = __double_as_longlong(c.q - (c.t - c.tu));     // :66-67
+                const double w = __longlong_as_double(yb & ~(yb >> 63));            // max(0.0, y)
+                const double cc = s.d_bw + w;                                       // :77-79
+                const bool full = cc > s.max_qd;
+                const double ll = s.dl + w;                                         // :69-70
+                c.q = rdrop ? c.q : (full ? w : cc);                                // :74-82
+                c.tu = rdrop ? c.tu : c.t;
+                const bool dropped = rdrop || full;
+                const double lsigned = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
+                if ((uint32_t)(c.tail + (uint32_t)nst - h2) >= cap) c.ovf = true;   // fatal, reported by the host
+                else { st.rec[lane][nst] = make_double2(c.t + ll, lsigned); nst++; }
+                c.t = c.t + inv_rate;                                               // :161
+                c.sent++;
+            }
+            active = c.t < end;
+        }
+        __syncwarp();
+        const unsigned have = __ballot_sync(PCC_FULL, nst > 0);
+#pragma unroll 1
+        for (int r = 0; r < 8; r++) {
+            if (((have >> (4 * r)) & 0xFu) == 0u) continue;                         // warp-uniform
+            const int j = 4 * r + (int)(lane >> 3);                                 // owner lane of the env served
+            const int k = (int)(lane & 7u);
+            const int nj = __shfl_sync(PCC_FULL, nst, j);
+            const uint32_t tj = __shfl_sync(PCC_FULL, c.tail, j);
+            const unsigned long long bj = __shfl_sync(PCC_FULL, (unsigned long long)ring_base, j);
+            if (k < nj)
+                *reinterpret_cast<double2 *>(reinterpret_cast<Rec *>(bj) + ((tj + (uint32_t)k) & mask)) = st.rec[j][k];
+        }
+        c.tail += (uint32_t)nst;
+        __syncwarp();
+    }
+}
 
 // Send phase of a warp that owns few envs (cnt <= 8): the chains stay on the owner lanes, but the
 // loss draws are produced by ALL lanes -- LPE = 32/cnt (power of two) lanes per env, one Philox
