@@ -49,6 +49,7 @@ static int fail(int code, const char *fmt, const char *a = "", const char *b = "
 // ---------------------------------------------------------------------------------------
 struct DevState {
     double *d_bw, *bw, *dl, *lr, *max_qd, *qd, *t_upd, *rate, *next_send, *cur_time, *run_dur, *conn_min;
+    double *w_full;              // tail-drop threshold in the queue-delay domain (pcc_core.cuh: tail_drop_threshold)
     double *ret_acc, *ret_last;  // reward_sum of the running / of the last finished episode (network_sim.py:390,443,483)
     unsigned long long *seed, *draws;
     uint32_t *tail, *h1, *h2;
@@ -88,7 +89,7 @@ struct DevRing {
 
 __device__ __forceinline__ void load_env(const DevState &p, int64_t e, EnvState &s)
 {
-    s.d_bw = p.d_bw[e]; s.dl = p.dl[e]; s.lr = p.lr[e]; s.max_qd = p.max_qd[e];
+    s.d_bw = p.d_bw[e]; s.dl = p.dl[e]; s.lr = p.lr[e]; s.max_qd = p.max_qd[e]; s.w_full = p.w_full[e];
     s.qd = p.qd[e]; s.t_upd = p.t_upd[e]; s.rate = p.rate[e]; s.next_send = p.next_send[e];
     s.cur_time = p.cur_time[e]; s.run_dur = p.run_dur[e]; s.conn_min = p.conn_min[e];
     s.tail = p.tail[e]; s.h1 = p.h1[e]; s.h2 = p.h2[e]; s.steps = p.steps[e];
@@ -207,7 +208,7 @@ __device__ __forceinline__ void coop_emit(const Grp<G> &g, const DevState &p, in
 
 template <int G>
 __global__ void __launch_bounds__(PCC_COOP_THREADS)
-pcc_step_coop_kernel(DevState p, unsigned long long head_step, const double *__restrict__ actions,
+pcc_step_coop_kernel(DevState p, const int32_t *__restrict__ perm, unsigned long long head_step, const double *__restrict__ actions,
                      double *__restrict__ obs, double *__restrict__ reward, uint8_t *__restrict__ done,
                      int32_t *__restrict__ counts, double *__restrict__ info)
 {
@@ -217,6 +218,7 @@ pcc_step_coop_kernel(DevState p, unsigned long long head_step, const double *__r
     if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
     const bool alive = e < p.n;      // whole groups; dead groups follow the warp's control flow
     if (!alive) e = p.n - 1;
+    if (perm) e = perm[e];           // cost-sorted order: the heaviest envs start first
     GroupSmem<G> &sm = smem[threadIdx.x / G];
     EnvState s;
     load_env(p, e, s);
@@ -225,9 +227,18 @@ pcc_step_coop_kernel(DevState p, unsigned long long head_step, const double *__r
     uint64_t draws = p.draws[e];
     StepOut o;
     s.rate = apply_rate_delta(s.rate, actions[e], p.c);                          // :412
+#ifdef PCC_PROFILE
+    long long prof[8];
+    run_mi_coop(g, alive, s, ring, seed, draws, s.run_dur, sm, o.mi, prof);
+    prof[6] = clock64();
+#else
     run_mi_coop(g, alive, s, ring, seed, draws, s.run_dur, sm, o.mi);           // :416
+#endif
     double avg_lat, lat_inc;
     mi_means_coop(g, alive, o.mi, ring, s.dl, sm, p.need_inc != 0, avg_lat, lat_inc);
+#ifdef PCC_PROFILE
+    prof[7] = clock64();
+#endif
     mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
     s.steps += 1;                                                                // :419
     if (o.st.avg_lat > 0.0) s.run_dur = 0.5 * o.st.avg_lat;                      // :437-438
@@ -249,6 +260,10 @@ pcc_step_coop_kernel(DevState p, unsigned long long head_step, const double *__r
             q[0] = o.st.send_rate; q[1] = o.st.recv_rate; q[2] = o.st.avg_lat; q[3] = o.st.loss_ratio;
             q[4] = o.st.lat_infl; q[5] = o.st.lat_ratio; q[6] = o.st.send_ratio; q[7] = o.st.dur;
             q[8] = s.cur_time; q[9] = s.rate; q[10] = s.run_dur; q[11] = s.conn_min;
+#ifdef PCC_PROFILE   // profiling build: info = cycles per phase (send, hop1, bnd1, hop2, bnd2, cross, means), counts
+            for (int k = 0; k < 7; k++) q[k] = (double)(prof[k + 1] - prof[k]);
+            q[7] = (double)o.mi.sent; q[8] = (double)o.mi.acked; q[9] = (double)(prof[7] - prof[0]);
+#endif
         }
     }
 }
@@ -271,6 +286,7 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     const double bwv = bw[e], dlv = delay[e], sr = start_rate[e];
     // reset_env of pcc_core.cuh (network_sim.py:454-484), cooperatively
     s.d_bw = 1.0 / bwv; s.dl = dlv; s.lr = loss[e]; s.max_qd = (double)queue[e] / bwv;
+    s.w_full = tail_drop_threshold(s.d_bw, s.max_qd);
     s.qd = 0.0; s.t_upd = 0.0; s.rate = sr; s.cur_time = 0.0; s.next_send = 1.0 / sr;
     s.run_dur = 3 * dlv; s.conn_min = 0.0;
     s.tail = p.tail[e]; s.h1 = s.tail; s.h2 = s.tail; s.steps = 0;
@@ -290,7 +306,7 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
         if (obs) obs[(size_t)e * HF + k] = v;
     }
     if (g.gl == 0) {
-        p.d_bw[e] = s.d_bw; p.bw[e] = bwv; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd;
+        p.d_bw[e] = s.d_bw; p.bw[e] = bwv; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd; p.w_full[e] = s.w_full;
         store_env_dynamic(p, e, s);
         p.draws[e] = draws;
         p.ret_acc[e] = 0.0;
@@ -312,8 +328,9 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
 // One MI for the E envs of this warp.  `owner` lanes hold their env's state in `s`.
 template <bool WANT_MEANS, bool DO_SEND>
 __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, bool owner, int cnt, int64_t e, EnvState &s,
-                                        PhiloxRng &rng, double dur, double *buf, WarpStage &stage, MiOut &mo,
-                                        double &avg_lat, double &lat_inc, int32_t sent_before = 0)
+                                        PhiloxRng &rng, double dur, double *buf, int wbuf, WarpStage &stage, MiOut &mo,
+                                        double &avg_lat, double &lat_inc, int32_t sent_before = 0,
+                                        long long *prof = nullptr)
 {
     const unsigned lane = g.gl;
     const double end = s.cur_time + dur;            // network_sim.py:124
@@ -323,9 +340,10 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
     c.t = s.next_send; c.q = s.qd; c.tu = s.t_upd; c.tail = s.tail;
     c.sent = sent_before & 0x7fffffff; c.ovf = sent_before < 0;
     mo.start = s.cur_time;                          // reset_obs :319-324
+    PCC_TICK(0);
     // phase A: E serial chains side by side (already done by pcc_send_kernel when !DO_SEND)
     if (DO_SEND) {
-        if (cnt <= 8) coop_send_phase(c, s, ring, rng, owner, cnt, s.h2, p.cap, end, inv_rate);   // warp-uniform branch
+        if (cnt == 1) coop_send_phase(c, s, ring, rng, owner, cnt, s.h2, p.cap, end, inv_rate);   // warp-uniform branch
 #if PCC_STAGED_STORES
         else lane_send_phase_staged(c, s, ring.base, ring.mask, rng, owner, s.h2, p.cap, end, inv_rate, stage);
 #else
@@ -333,6 +351,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
 #endif
         __syncwarp();
     }
+    PCC_TICK(1);
     // phase B: the warp consumes each env's hop-1 / hop-2 events
     int which = 0, acked = 0, lost = 0;
     double ct = 0.0;
@@ -357,18 +376,29 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
         in.tail = __shfl_sync(PCC_FULL, c.tail, j);
         in.h1 = __shfl_sync(PCC_FULL, s.h1, j);
         in.h2 = __shfl_sync(PCC_FULL, s.h2, j);
+        in.wbuf = wbuf;
+#ifdef PCC_PROFILE
+        const long long tc0 = clock64();
+#endif
         const long long ej = __shfl_sync(PCC_FULL, (long long)e, j);
         DevRing rj{p.rings + (size_t)ej * p.cap, p.cap - 1u};
         ConsumeOut co;
         consume_mi_warp(g, in, rj, buf, co);
         double a = 0.0, li = 0.0;
-        if (WANT_MEANS) mi_means_warp(g, co, rj, in.dl, buf, p.need_inc != 0, a, li);
+#ifdef PCC_PROFILE
+        const long long tc1 = clock64();
+#endif
+        if (WANT_MEANS) mi_means_warp(g, co, rj, in.dl, buf, wbuf, p.need_inc != 0, a, li);
+#ifdef PCC_PROFILE
+        if (prof && (int)lane == j) { prof[2] = tc1 - tc0; prof[3] = clock64() - tc1; }
+#endif
         if ((int)lane == j) {
             s.h1 = co.h1; s.h2 = co.h2;
             acked = co.acked; lost = co.lost; which = co.which; ct = co.cur_time;
             avg_lat = a; lat_inc = li;
         }
     }
+    PCC_TICK(4);
     // phase C (per lane): the crossing event if it is the pacing timer (:156-178)
     if (owner) {
         if (which == 0) {
@@ -391,6 +421,7 @@ struct WarpPartition {
     const int32_t *starts;    // [n_warps + 1] offsets into perm, or null
     const int32_t *n_warps;   // device scalar
     int32_t static_e;
+    int32_t wbuf;             // staging capacity (samples) per warp
 };
 
 template <bool SPLIT>   // SPLIT: the sends of this MI were already done by pcc_send_kernel
@@ -399,11 +430,12 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
                      const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
                      uint8_t *__restrict__ done, int32_t *__restrict__ counts, double *__restrict__ info)
 {
-    __shared__ double sbuf[PCC_WARP_THREADS / 32][PCC_WBUF + 32];
+    extern __shared__ double dyn_smem[];      // per warp: warp_smem_bytes(part.wbuf)
     __shared__ WarpStage sstage[(SPLIT || !PCC_STAGED_STORES) ? 1 : PCC_WARP_THREADS / 32];
+    double *wsm = dyn_smem + (size_t)(threadIdx.x >> 5) * (warp_smem_bytes(part.wbuf) / 8);
     const Grp<32> g;
     const unsigned lane = threadIdx.x & 31u;
-    const int64_t w = (int64_t)blockIdx.x * (PCC_WARP_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
     int64_t first;
     int cnt;
@@ -426,9 +458,15 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
     if (!SPLIT) s.rate = apply_rate_delta(s.rate, actions[e], p.c);              // :412
     StepOut o;
     double avg_lat, lat_inc;
-    warp_mi<true, !SPLIT>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5],
+#ifdef PCC_PROFILE
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tk0 = clock64();
+#else
+    long long *prof = nullptr;
+#endif
+    warp_mi<true, !SPLIT>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf,
                           sstage[(SPLIT || !PCC_STAGED_STORES) ? 0 : (threadIdx.x >> 5)], o.mi, avg_lat, lat_inc,
-                          SPLIT ? sent_tmp[e] : 0);                              // :416
+                          SPLIT ? sent_tmp[e] : 0, prof);                        // :416
     if (!owner) return;
     mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
     s.steps += 1;                                                                // :419
@@ -465,6 +503,11 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
         q[0] = o.st.send_rate; q[1] = o.st.recv_rate; q[2] = o.st.avg_lat; q[3] = o.st.loss_ratio;
         q[4] = o.st.lat_infl; q[5] = o.st.lat_ratio; q[6] = o.st.send_ratio; q[7] = o.st.dur;
         q[8] = s.cur_time; q[9] = s.rate; q[10] = s.run_dur; q[11] = s.conn_min;
+#ifdef PCC_PROFILE   // profiling build: info = cycles (send phase of the warp, consume, means of this env, phase B of the warp), counts
+        q[0] = (double)(prof[1] - prof[0]); q[1] = (double)prof[2]; q[2] = (double)prof[3];
+        q[3] = (double)(prof[4] - prof[1]); q[4] = (double)cnt; q[5] = 0; q[6] = 0;
+        q[7] = (double)o.mi.sent; q[8] = (double)o.mi.acked; q[9] = (double)(clock64() - tk0);
+#endif
     }
 }
 
@@ -475,7 +518,6 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
                       const double *__restrict__ loss, const double *__restrict__ start_rate,
                       double *__restrict__ obs)
 {
-    __shared__ double sbuf[PCC_WARP_THREADS / 32][PCC_WBUF + 32];
     __shared__ WarpStage sstage[PCC_STAGED_STORES ? PCC_WARP_THREADS / 32 : 1];
     const Grp<32> g;
     const unsigned lane = threadIdx.x & 31u;
@@ -489,6 +531,7 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     const double bwv = bw[e], dlv = delay[e], sr = start_rate[e];
     // reset_env of pcc_core.cuh (network_sim.py:454-484)
     s.d_bw = 1.0 / bwv; s.dl = dlv; s.lr = loss[e]; s.max_qd = (double)queue[e] / bwv;
+    s.w_full = tail_drop_threshold(s.d_bw, s.max_qd);
     s.qd = 0.0; s.t_upd = 0.0; s.rate = sr; s.cur_time = 0.0; s.next_send = 1.0 / sr;
     s.run_dur = 3 * dlv; s.conn_min = 0.0;
     s.tail = p.tail[e]; s.h1 = s.tail; s.h2 = s.tail; s.steps = 0;
@@ -497,9 +540,9 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     MiOut mo;
     double a, li;
     const int cnt = (int)((p.n - warp_global * E < E) ? (p.n - warp_global * E) : E);
-    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], sstage[PCC_STAGED_STORES ? (threadIdx.x >> 5) : 0], mo, a, li);   // :478
+    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, nullptr, 0, sstage[PCC_STAGED_STORES ? (threadIdx.x >> 5) : 0], mo, a, li);   // :478
     bool ovf = mo.overflow;
-    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, sbuf[threadIdx.x >> 5], sstage[PCC_STAGED_STORES ? (threadIdx.x >> 5) : 0], mo, a, li);   // :479
+    warp_mi<false, true>(g, p, owner, cnt, e, s, rng, s.run_dur, nullptr, 0, sstage[PCC_STAGED_STORES ? (threadIdx.x >> 5) : 0], mo, a, li);   // :479
     ovf = ovf || mo.overflow;
     if (!owner) return;
     const int HF = p.H * p.F;
@@ -508,7 +551,7 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
         p.hist[(size_t)e * HF + k] = v;
         if (obs) obs[(size_t)e * HF + k] = v;
     }
-    p.d_bw[e] = s.d_bw; p.bw[e] = bwv; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd;
+    p.d_bw[e] = s.d_bw; p.bw[e] = bwv; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd; p.w_full[e] = s.w_full;
     store_env_dynamic(p, e, s);
     p.draws[e] = rng.draws;
     p.ret_acc[e] = 0.0;
@@ -552,7 +595,7 @@ pcc_send_kernel(DevState p, const int32_t *__restrict__ perm, int heavy_warps, c
 
 // ---- work-balanced partition (rebalance) -----------------------------------------------------
 // cost model of one env-MI in SM cycles: fixed cooperative overhead + per-packet work
-struct CostModel { float c0, c1; int32_t target_warps; };
+struct CostModel { float c0, c1; int32_t target_warps; float heavy_packets; };
 
 __global__ void pcc_cost_kernel(DevState p, CostModel cm, uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
 {
@@ -585,15 +628,19 @@ __global__ void pcc_target_kernel(const uint32_t *__restrict__ sorted_cost, int6
     }
 }
 
-__global__ void pcc_costfloor_kernel(const uint32_t *__restrict__ sorted_cost, int64_t n,
+__global__ void pcc_costfloor_kernel(const uint32_t *__restrict__ sorted_cost, int64_t n, CostModel cm,
                                      const unsigned long long *__restrict__ target,
                                      unsigned long long *__restrict__ cost64)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned long long fl = target[0] / 32ull + 1ull;
+    const unsigned long long t = target[0];
+    const unsigned long long fl = t / 32ull + 1ull;
     const unsigned long long c = sorted_cost[i];
-    cost64[i] = c > fl ? c : fl;
+    // an env expected to send more than heavy_packets gets a warp to itself (cost = T): its chain then
+    // runs with 32-lane Philox support (114 cycles/packet measured) instead of stalling 31 co-tenants
+    const float pk = ((float)c - cm.c0) / cm.c1;
+    cost64[i] = (pk > cm.heavy_packets) ? t : (c > fl ? c : fl);
 }
 
 // warp id of sorted position i = floor(exclusive prefix cost / T); ids are gap-free (cost' <= T)
@@ -637,7 +684,7 @@ __global__ void pcc_reset_kernel(DevState p, const uint8_t *__restrict__ mask,
         rng.init(p.mt + (size_t)e * 625);
         ovf = reset_env(s, ring, rng, bw[e], delay[e], loss[e], (int64_t)queue[e], start_rate[e]);
     }
-    p.d_bw[e] = s.d_bw; p.bw[e] = bw[e]; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd;
+    p.d_bw[e] = s.d_bw; p.bw[e] = bw[e]; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd; p.w_full[e] = s.w_full;
     store_env_dynamic(p, e, s);
     p.ret_acc[e] = 0.0;                                 // self.reward_sum = 0.0  (:483)
     if (ovf) flag_overflow(p, e);
@@ -711,6 +758,7 @@ struct pcc_handle_s {
     int32_t *starts, *n_warps, *sent_tmp;
     bool split;
     bool scalar_sorted;
+    int wbuf, warp_threads;   // warp kernel: staging capacity per warp, threads per block
     int64_t max_warps;
     CostModel cm;
     // staging for pcc_step_host
@@ -722,14 +770,14 @@ struct pcc_handle_s {
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t off_d[14], off_u64[2], off_u32[4], off_hist, off_mt, off_meta, total;
+    size_t off_d[15], off_u64[2], off_u32[4], off_hist, off_mt, off_meta, total;
 };
 
 static Layout make_layout(const pcc_config *c)
 {
     Layout L;
     size_t o = 0, n = (size_t)c->n_envs;
-    for (int i = 0; i < 14; i++) { L.off_d[i] = o; o = align_up(o + 8 * n); }
+    for (int i = 0; i < 15; i++) { L.off_d[i] = o; o = align_up(o + 8 * n); }
     for (int i = 0; i < 2; i++) { L.off_u64[i] = o; o = align_up(o + 8 * n); }
     for (int i = 0; i < 4; i++) { L.off_u32[i] = o; o = align_up(o + 4 * n); }
     L.off_hist = o; o = align_up(o + 8 * n * (size_t)c->history_len * (size_t)c->n_features);
@@ -820,9 +868,9 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     Layout L = make_layout(cfg);
     char *b = (char *)state_dev;
     DevState &d = h->d;
-    double **dcols[14] = {&d.d_bw, &d.bw, &d.dl, &d.lr, &d.max_qd, &d.qd, &d.t_upd, &d.rate,
-                          &d.next_send, &d.cur_time, &d.run_dur, &d.conn_min, &d.ret_acc, &d.ret_last};
-    for (int i = 0; i < 14; i++) *dcols[i] = (double *)(b + L.off_d[i]);
+    double **dcols[15] = {&d.d_bw, &d.bw, &d.dl, &d.lr, &d.max_qd, &d.qd, &d.t_upd, &d.rate,
+                          &d.next_send, &d.cur_time, &d.run_dur, &d.conn_min, &d.ret_acc, &d.ret_last, &d.w_full};
+    for (int i = 0; i < 15; i++) *dcols[i] = (double *)(b + L.off_d[i]);
     d.seed = (unsigned long long *)(b + L.off_u64[0]);
     d.draws = (unsigned long long *)(b + L.off_u64[1]);
     d.tail = (uint32_t *)(b + L.off_u32[0]);
@@ -864,11 +912,25 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         h->group = small_batch ? 32 : 8;
     }
     if (cfg->rng_kind != PCC_RNG_PHILOX) { h->group = 0; h->epw = 0; }   // MT19937 (fidelity mode): scalar kernels
+    {
+        const char *wb = getenv("PCC_B200_WBUF");
+        h->wbuf = wb ? atoi(wb) : (small_batch ? 4096 : 2048);
+        if (h->wbuf < 128) h->wbuf = 128;
+        h->warp_threads = (h->wbuf > 1024) ? 64 : PCC_WARP_THREADS;
+        if (h->epw) {
+            const size_t dyn = (size_t)(h->warp_threads / 32) * warp_smem_bytes(h->wbuf);
+            cudaError_t ce = cudaFuncSetAttribute(pcc_step_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(pcc_step_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (ce != cudaSuccess) { delete h; return fail(PCC_ECUDA, "dynamic shared memory: %s", cudaGetErrorString(ce)); }
+        }
+    }
     const char *reb = getenv("PCC_B200_REBALANCE");
     h->rebalance_every = reb ? atoi(reb) : 16;
     h->rebalance_now = true;
     h->steps_since_rebalance = 0;
-    h->scalar_sorted = (mode && !strcmp(mode, "scalar")) && cfg->rng_kind == PCC_RNG_PHILOX && h->rebalance_every > 0;
+    // scalar and group modes can also visit the envs in cost-sorted order (sort only, no partition)
+    h->scalar_sorted = (h->epw == 0) && cfg->rng_kind == PCC_RNG_PHILOX && h->rebalance_every > 0 &&
+                       getenv("PCC_B200_SORT") != nullptr;   // measured: no gain for these modes
     if ((h->epw || h->scalar_sorted) && h->rebalance_every > 0) {
         const size_t n = (size_t)cfg->n_envs;
         cudaError_t ce = cudaMalloc(&h->sort_keys_in, 4 * n);
@@ -885,11 +947,12 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         if (scan_bytes > h->sort_tmp_bytes) h->sort_tmp_bytes = scan_bytes;
         if (ce == cudaSuccess) ce = cudaMalloc(&h->sort_tmp, h->sort_tmp_bytes);
         const char *c0 = getenv("PCC_B200_COST0"), *c1 = getenv("PCC_B200_COST1"), *tw = getenv("PCC_B200_TARGET_WARPS");
-        h->cm.c0 = c0 ? (float)atof(c0) : 4000.0f;
+        h->cm.c0 = c0 ? (float)atof(c0) : 7000.0f;
         h->cm.c1 = c1 ? (float)atof(c1) : 60.0f;
+        const char *hp = getenv("PCC_B200_HEAVY");
+        h->cm.heavy_packets = hp ? (float)atof(hp) : 1024.0f;
         h->cm.target_warps = tw ? atoi(tw) : 148 * 32;
-        h->max_warps = (int64_t)h->cm.target_warps + (int64_t)n / 16 + 8;
-        if (h->max_warps > (int64_t)n) h->max_warps = (int64_t)n;
+        h->max_warps = (int64_t)n;   // worst case: every env heavy; idle warps exit at once
         if (ce == cudaSuccess) ce = cudaMalloc(&h->cost64, 8 * n);
         if (ce == cudaSuccess) ce = cudaMalloc(&h->cum_excl, 8 * n);
         if (ce == cudaSuccess) ce = cudaMalloc(&h->target, 8);
@@ -1015,7 +1078,7 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned cgrid = h->group ? (unsigned)((h->cfg.n_envs * h->group + PCC_COOP_THREADS - 1) / PCC_COOP_THREADS) : 0u;
 #define PCC_STEP_COOP(G_) pcc_step_coop_kernel<G_><<<cgrid, PCC_COOP_THREADS, 0, st>>>( \
-        h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev)
+        h->d, scalar_perm, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev)
     const int32_t *scalar_perm = nullptr;
     if (h->scalar_sorted) {
         if (h->rebalance_now || h->steps_since_rebalance >= h->rebalance_every) {
@@ -1031,7 +1094,9 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
         scalar_perm = h->perm;
     }
     if (h->epw) {
-        WarpPartition part{nullptr, nullptr, nullptr, h->epw};
+        WarpPartition part{nullptr, nullptr, nullptr, h->epw, h->wbuf};
+        const int wpb = h->warp_threads / 32;
+        const size_t dyn = (size_t)wpb * warp_smem_bytes(h->wbuf);
         int64_t nwarps = (h->cfg.n_envs + h->epw - 1) / h->epw;
         if (h->rebalance_every > 0) {
             if (h->rebalance_now || h->steps_since_rebalance >= h->rebalance_every) {
@@ -1043,7 +1108,7 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
                                                                    h->sort_keys_out, h->sort_vals_in, h->perm, (int)n,
                                                                    0, 32, st));
                 pcc_target_kernel<<<1, 1024, 0, st>>>(h->sort_keys_out, n, h->cm, h->target);
-                pcc_costfloor_kernel<<<kg, 256, 0, st>>>(h->sort_keys_out, n, h->target, h->cost64);
+                pcc_costfloor_kernel<<<kg, 256, 0, st>>>(h->sort_keys_out, n, h->cm, h->target, h->cost64);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(h->sort_tmp, h->sort_tmp_bytes, h->cost64, h->cum_excl, (int)n, st));
                 pcc_heads_kernel<<<kg, 256, 0, st>>>(h->cum_excl, n, h->target, h->starts, h->n_warps, (long long)h->max_warps, h->d.meta);
                 h->rebalance_now = false;
@@ -1054,7 +1119,7 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
             part.perm = h->perm; part.starts = h->starts; part.n_warps = h->n_warps;
             nwarps = h->max_warps;
         }
-        const unsigned wgrid = (unsigned)((nwarps + 3) / 4);
+        const unsigned wgrid = (unsigned)((nwarps + wpb - 1) / wpb);
         if (h->split && part.perm) {
             const int64_t n = h->cfg.n_envs;
             int64_t heavy_envs = n / 64;
@@ -1063,12 +1128,12 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
             const int64_t sw = heavy_warps + (n - 4 * (int64_t)heavy_warps + 31) / 32;
             pcc_send_kernel<<<(unsigned)((sw + 3) / 4), PCC_WARP_THREADS, 0, st>>>(h->d, h->perm, heavy_warps, actions_dev,
                                                                                  h->sent_tmp);
-            pcc_step_warp_kernel<true><<<wgrid, PCC_WARP_THREADS, 0, st>>>(h->d, part, h->sent_tmp, h->head, actions_dev,
+            pcc_step_warp_kernel<true><<<wgrid, h->warp_threads, dyn, st>>>(h->d, part, h->sent_tmp, h->head, actions_dev,
                                                                            obs_dev, reward_dev, done_dev, counts_dev,
                                                                            info_dev);
             h->launches++;
         } else {
-            pcc_step_warp_kernel<false><<<wgrid, PCC_WARP_THREADS, 0, st>>>(h->d, part, nullptr, h->head, actions_dev,
+            pcc_step_warp_kernel<false><<<wgrid, h->warp_threads, dyn, st>>>(h->d, part, nullptr, h->head, actions_dev,
                                                                             obs_dev, reward_dev, done_dev, counts_dev,
                                                                             info_dev);
         }

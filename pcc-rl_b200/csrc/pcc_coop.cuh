@@ -120,16 +120,23 @@ __device__ __forceinline__ void window_argmin(const Grp<G> &g, bool cand, double
 template <int G>
 struct GroupSmem {
     double2 stage[2 * G];        // records of one send chunk
-    double buf[PCC_LEAF + G];    // acked-latency staging for np.mean
+    double buf[PCC_LEAF + ((G == 32) ? 4 : 1) * G];    // acked-latency staging for np.mean
 };
 
 // One monitor interval.  Every lane of a group holds the same EnvState copy on entry and on
 // exit.  `alive` = this group has an env (warp-uniform control flow needs all lanes present).
 // On exit, if out.acked <= PCC_LEAF, sm.buf[0..out.acked) holds the MI's samples in order.
+#ifdef PCC_PROFILE
+#define PCC_TICK(k) do { if (prof) prof[k] = clock64(); } while (0)
+#else
+#define PCC_TICK(k)
+#endif
 template <int G, class Ring>
 __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvState &s, Ring &ring, uint64_t seed,
-                                            uint64_t &draws, double dur, GroupSmem<G> &sm, MiOut &out)
+                                            uint64_t &draws, double dur, GroupSmem<G> &sm, MiOut &out,
+                                            long long *prof = nullptr)
 {
+    PCC_TICK(0);
     const double end = s.cur_time + dur;            // network_sim.py:124
     const double inv_rate = 1.0 / s.rate;           // :161
     const uint32_t cap = ring.capacity();
@@ -175,8 +182,8 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
                     dm >>= 1;
                     const long long yb = __double_as_longlong(q - (tt - tu));   // :66-67
                     const double w = __longlong_as_double(yb & ~(yb >> 63));    // max(0.0, y)
-                    const double c = s.d_bw + w;                                // :77-79
-                    const bool full = c > s.max_qd;
+                    const double c = s.d_bw + w;                                // :82
+                    const bool full = w > s.w_full;                             // :77-79 (tail_drop_threshold)
                     const double ll = s.dl + w;                                 // :69-70
                     q = rdrop ? q : (full ? w : c);                             // :74-82
                     tu = rdrop ? tu : tt;
@@ -204,6 +211,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
     t = g.bcast(t, 0); qd = g.bcast(qd, 0); t_upd = g.bcast(t_upd, 0);
     ovf = g.bcast((int)ovf, 0) != 0;
     __syncwarp();   // record stores above are read by other lanes below
+    PCC_TICK(1);
 
     // ---- (2) hop-1 events with a < end ------------------------------------------------------
     {
@@ -228,6 +236,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
             scanning = scanning && !stop;
         }
     }
+    PCC_TICK(2);
     bool has1 = false;
     uint32_t m1 = 0; double m1a = 0.0, m1l = 0.0; bool m1d = false;
     {
@@ -250,6 +259,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
         __syncwarp();   // straggler flags are read by the hop-2 scan
     }
 
+    PCC_TICK(3);
     // ---- (3) hop-2 events with b < end; acked latencies staged for np.mean --------------------
     bool at_live = false;
     {
@@ -297,6 +307,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
         }
     }
     out.s_end = h2;
+    PCC_TICK(4);
     bool has2 = false;
     uint32_t m2 = 0; double m2b = 0.0, m2l = 0.0; bool m2d = false;
     {
@@ -328,6 +339,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
         }
     }
 
+    PCC_TICK(5);
     // ---- (4) the event that crosses `end` (group-uniform values, no votes) --------------------
     int which;
     if (has1 && (!has2 || m1a <= m2b)) which = (m1a <= t) ? 1 : 0;
@@ -346,7 +358,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
         if (u < s.lr) dropped = true;
         else {
             qd = w; t_upd = t;
-            if (s.d_bw + qd > s.max_qd) dropped = true;
+            if (w > s.w_full) dropped = true;
             else { qd += s.d_bw; dropped = false; }
         }
         Rec r; r.a = t + ll; r.l = dropped ? negd(ll) : ll;
@@ -519,14 +531,15 @@ __device__ __forceinline__ void mi_means_coop(const Grp<G> &g, bool alive, const
             lat_increase = s2 / (double)(n - half) - s1 / (double)half;
         }
     } else if (n > PCC_LEAF) {
+        constexpr int SW = (G == 32) ? 4 : 1;   // windows per streaming round
         {
-            CoopSamples<G, Ring> st(g, ring, sm.buf, o, dl);
+            CoopSamples<G, Ring, SW> st(g, ring, sm.buf, o, dl);
             double sum = 0.0;
             sum += coop_pw_sum(g, st, n);
             avg_lat = sum / (double)n;
         }
         if (need_increase) {
-            CoopSamples<G, Ring> st(g, ring, sm.buf, o, dl);
+            CoopSamples<G, Ring, SW> st(g, ring, sm.buf, o, dl);
             double s1 = 0.0, s2 = 0.0;
             s1 += coop_pw_sum(g, st, half);
             s2 += coop_pw_sum(g, st, n - half);

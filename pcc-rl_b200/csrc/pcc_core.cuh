@@ -195,6 +195,23 @@ struct Mt19937Rng {
     }
 };
 
+// network_sim.py:77-79 drops a packet when fl(extra_delay + queue_delay) > max_queue_delay.  Rounding
+// is monotone, so {w >= 0 : fl(d_bw + w) <= max_qd} is an interval [0, w_full] (or empty): the test
+// is EXACTLY  w > w_full.  Evaluating it on w instead of on the sum takes one binary64 operation
+// off the loop-carried dependency chain of the queue recurrence.
+PCC_HD double tail_drop_threshold(double d_bw, double max_qd)
+{
+    if (d_bw + 0.0 > max_qd) return -1.0;            // even an empty queue is "full"
+    double t = max_qd - d_bw;
+    if (t < 0.0) t = 0.0;
+    while (d_bw + t > max_qd) t = nextafter(t, -1.0);            // step down until admissible
+    for (;;) {                                                   // step up while still admissible
+        const double u = nextafter(t, 1.0e300);
+        if (d_bw + u <= max_qd) t = u; else break;
+    }
+    return t;
+}
+
 // ---------------------------------------------------------------------------------------
 // Per-env scalar state (register copy; the kernels keep it structure-of-arrays in HBM).
 // ---------------------------------------------------------------------------------------
@@ -204,6 +221,7 @@ struct EnvState {
     double dl;        // propagation delay
     double lr;        // loss rate
     double max_qd;    // queue_size / bw       (network_sim.py:64)
+    double w_full;    // largest w with fl(d_bw + w) <= max_qd: tail drop  <=>  w > w_full  (see tail_drop_threshold)
     double qd;        // Link.queue_delay
     double t_upd;     // Link.queue_delay_update_time
     // sender / network
@@ -298,7 +316,7 @@ PCC_HD void run_mi(EnvState &s, Ring &ring, Rng &rng, double dur, MiOut &out)
             dropped = true;                                                                \
         } else {                                                                           \
             qd = w; t_upd = t;                               /* :75-76 */                  \
-            if (s.d_bw + qd > s.max_qd) dropped = true;      /* :79 */                     \
+            if (w > s.w_full) dropped = true;                /* :79, see tail_drop_threshold */ \
             else { qd += s.d_bw; dropped = false; }          /* :82 */                     \
         }                                                                                  \
         Rec r; r.a = t + ll; r.l = dropped ? negd(ll) : ll;  /* :173-175; 0.0 + ll == ll */ \
@@ -581,6 +599,7 @@ PCC_HD bool reset_env(EnvState &s, Ring &ring, Rng &rng, double bw, double dl, d
     s.dl = dl;
     s.lr = lr;
     s.max_qd = (double)queue_size / bw;
+    s.w_full = tail_drop_threshold(s.d_bw, s.max_qd);
     s.qd = 0.0; s.t_upd = 0.0;
     s.rate = start_rate;
     s.cur_time = 0.0;

@@ -23,13 +23,21 @@
 
 namespace pcc {
 
-#ifndef PCC_WBUF
-#define PCC_WBUF 1024   // samples staged per warp (8 KB); MIs with more acks re-read the ring
-#endif
+// Per-warp shared memory (dynamic): [wbuf + 32] doubles of acked-latency staging, then a LeafScratch.
+// wbuf is a launch parameter (1024 for big batches, 4096 when the batch is small and occupancy
+// is not the limit); MIs with more acks than wbuf re-read the ring (streaming path).
+#define PCC_MAX_LEAVES 160
+struct LeafScratch {
+    double sum[PCC_MAX_LEAVES];
+    int off[PCC_MAX_LEAVES];
+    int cnt[PCC_MAX_LEAVES];
+};
+__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch); }
 
 struct ConsumeIn {
     double end, dl, tnext;
     uint32_t tail, h1, h2;
+    int wbuf;          // capacity of the staging buffer
 };
 struct ConsumeOut {
     uint32_t h1, h2, s_begin, s_end;
@@ -178,7 +186,7 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
             const unsigned a_w = stop ? 0u : (am[w] & lead);
             if ((a_w >> g.gl) & 1u) {
                 const int pos = acked + __popc(a_w & Grp<G>::lowmask((int)g.gl));
-                if (pos < PCC_WBUF) buf[pos] = l2[w];
+                if (pos < in.wbuf) buf[pos] = l2[w];
             }
             if (!stop) {
                 acked += __popc(a_w);
@@ -222,38 +230,54 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
         else if (g.gl == 0) ring.store_a(m2, u2d(PCC_NEG_INF));
     }
     // the one possible out-of-order sample is the MI's last sample
-    if (out.has_extra && acked <= PCC_WBUF && g.gl == 0) buf[acked - 1] = out.extra;
+    if (out.has_extra && acked <= in.wbuf && g.gl == 0) buf[acked - 1] = out.extra;
     __syncwarp();
     out.which = which;
     out.h1 = h1; out.h2 = h2;
     out.acked = acked; out.lost = lost;
 }
 
-// numpy's pairwise sum over a[0..n) held in shared memory (n <= PCC_WBUF): the recursion of
-// DOUBLE_pairwise_sum with coop_leaf at the leaves.  Warp-uniform.
-__device__ __forceinline__ double pw_smem(const Grp<32> &g, const double *a, int n)
+// ---- np.mean for 128 < n <= wbuf: all samples are in shared memory --------------------------------
+// numpy's pairwise recursion (n > 128: n2 = n/2 rounded down to a multiple of 8; sum(left) + sum(right))
+// bottoms out in leaves of 65..128 elements.  List the leaves left to right ...
+__device__ __forceinline__ int enum_leaves(int base, int n, int *off, int *cnt, int at)
 {
-    if (n <= PCC_LEAF) return coop_leaf(g, a, n);
-    int right_n[8];
-    const double *right_p[8];
-    double left_sum[8];
-    bool have_left[8];
+    int so[16], sn[16], sp = 0;
+    so[0] = base; sn[0] = n; sp = 1;
+    while (sp) {
+        --sp;
+        const int o = so[sp], m = sn[sp];
+        if (m <= PCC_LEAF) { if (at < PCC_MAX_LEAVES) { off[at] = o; cnt[at] = m; } ++at; }
+        else {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            so[sp] = o + n2; sn[sp] = m - n2; ++sp;   // right (popped second)
+            so[sp] = o; sn[sp] = n2; ++sp;            // left  (popped first)
+        }
+    }
+    return at;
+}
+// ... and fold the leaf sums back in the recursion's order (iterative post-order).
+__device__ __forceinline__ double fold_leaves(int n, const double *sums, int &idx)
+{
+    int right_n[16];
+    double left_sum[16];
+    bool have_left[16];
     int sp = 0;
     int cur = n;
-    const double *p = a;
     for (;;) {
         while (cur > PCC_LEAF) {
             int n2 = cur / 2;
             n2 -= n2 % 8;
-            right_n[sp] = cur - n2; right_p[sp] = p + n2; have_left[sp] = false; sp++;
+            right_n[sp] = cur - n2; have_left[sp] = false; sp++;
             cur = n2;
         }
-        double res = coop_leaf(g, p, cur);
+        double res = sums[idx++];
         for (;;) {
             if (sp == 0) return res;
             if (!have_left[sp - 1]) {
                 left_sum[sp - 1] = res; have_left[sp - 1] = true;
-                cur = right_n[sp - 1]; p = right_p[sp - 1];
+                cur = right_n[sp - 1];
                 break;
             }
             res = left_sum[sp - 1] + res;
@@ -262,41 +286,80 @@ __device__ __forceinline__ double pw_smem(const Grp<32> &g, const double *a, int
     }
 }
 
-// n > PCC_LEAF (rare): recursion over the staging buffer, or streaming re-read of the ring
+// Leaves are independent: four at a time, one per 8-lane subgroup (numpy's 8 accumulators + xor tree).
+__device__ __noinline__ void means_from_smem(const double *buf, LeafScratch *ls, int n, bool need_increase,
+                                             double &avg_lat, double &lat_increase)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int half = n / 2;
+    int L = 0;
+    if (lane == 0) {
+        L = enum_leaves(0, n, ls->off, ls->cnt, 0);
+        if (need_increase && half >= 1) {
+            L = enum_leaves(0, half, ls->off, ls->cnt, L);
+            L = enum_leaves(half, n - half, ls->off, ls->cnt, L);
+        }
+    }
+    L = __shfl_sync(PCC_FULL, L, 0);
+    __syncwarp();
+    const int sg = (int)(lane >> 3), j = (int)(lane & 7u);
+    for (int base = 0; base < L; base += 4) {          // warp-uniform
+        const int li = base + sg;
+        const bool on = li < L;
+        const int c = on ? ls->cnt[li] : 0;
+        const double *a = buf + (on ? ls->off[li] : 0);
+        const int nb = c - (c % 8);
+        double r = 0.0;
+        if (c >= 8) {
+            r = a[j];
+            for (int k = 8; k < nb; k += 8) r += a[k + j];
+        }
+        r += __shfl_xor_sync(PCC_FULL, r, 1);
+        r += __shfl_xor_sync(PCC_FULL, r, 2);
+        r += __shfl_xor_sync(PCC_FULL, r, 4);
+        double res;
+        if (c >= 8) { res = r; for (int k = nb; k < c; k++) res += a[k]; }
+        else { res = 0.; for (int k = 0; k < c; k++) res += a[k]; }
+        if (on && j == 0) ls->sum[li] = res;
+    }
+    __syncwarp();
+    int idx = 0;
+    double sum = 0.0;
+    sum += fold_leaves(n, ls->sum, idx);
+    avg_lat = sum / (double)n;                                              // sender_obs.py:119-122
+    lat_increase = 0.0;
+    if (need_increase && half >= 1) {                                       // :138-142
+        double s1 = 0.0, s2 = 0.0;
+        s1 += fold_leaves(half, ls->sum, idx);
+        s2 += fold_leaves(n - half, ls->sum, idx);
+        lat_increase = s2 / (double)(n - half) - s1 / (double)half;
+    }
+    __syncwarp();
+}
+
+// n > wbuf (very rare): streaming re-read of the ring
 template <class Ring>
-__device__ __noinline__ void mi_means_big(ConsumeOut co, Ring ring, double dl, double *buf, bool need_increase,
-                                          double &avg_lat, double &lat_increase)
+__device__ __noinline__ void mi_means_stream(ConsumeOut co, Ring ring, double dl, double *buf, bool need_increase,
+                                             double &avg_lat, double &lat_increase)
 {
     const Grp<32> g;
     const int n = co.acked;
     const int half = n / 2;
     lat_increase = 0.0;
-    if (n <= PCC_WBUF) {
+    MiOut o;
+    o.s_begin = co.s_begin; o.s_end = co.s_end; o.extra = co.extra; o.has_extra = co.has_extra;
+    {
+        CoopSamples<32, Ring, 4> st(g, ring, buf, o, dl);
         double sum = 0.0;
-        sum += pw_smem(g, buf, n);
+        sum += coop_pw_sum(g, st, n);
         avg_lat = sum / (double)n;
-        if (need_increase && half >= 1) {
-            double s1 = 0.0, s2 = 0.0;
-            s1 += pw_smem(g, buf, half);
-            s2 += pw_smem(g, buf + half, n - half);
-            lat_increase = s2 / (double)(n - half) - s1 / (double)half;
-        }
-    } else {
-        MiOut o;
-        o.s_begin = co.s_begin; o.s_end = co.s_end; o.extra = co.extra; o.has_extra = co.has_extra;
-        {
-            CoopSamples<32, Ring, 4> st(g, ring, buf, o, dl);
-            double sum = 0.0;
-            sum += coop_pw_sum(g, st, n);
-            avg_lat = sum / (double)n;
-        }
-        if (need_increase) {
-            CoopSamples<32, Ring, 4> st(g, ring, buf, o, dl);
-            double s1 = 0.0, s2 = 0.0;
-            s1 += coop_pw_sum(g, st, half);
-            s2 += coop_pw_sum(g, st, n - half);
-            lat_increase = s2 / (double)(n - half) - s1 / (double)half;
-        }
+    }
+    if (need_increase) {
+        CoopSamples<32, Ring, 4> st(g, ring, buf, o, dl);
+        double s1 = 0.0, s2 = 0.0;
+        s1 += coop_pw_sum(g, st, half);
+        s2 += coop_pw_sum(g, st, n - half);
+        lat_increase = s2 / (double)(n - half) - s1 / (double)half;
     }
     __syncwarp();
 }
@@ -304,7 +367,8 @@ __device__ __noinline__ void mi_means_big(ConsumeOut co, Ring ring, double dl, d
 // avg latency (sender_obs.py:119-122) and latency increase (:138-142) of one env's MI, warp-wide
 template <class Ring>
 __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut &co, Ring &ring, double dl,
-                                              double *buf, bool need_increase, double &avg_lat, double &lat_increase)
+                                              double *buf, int wbuf, bool need_increase, double &avg_lat,
+                                              double &lat_increase)
 {
     const int n = co.acked;
     avg_lat = 0.0;
@@ -343,8 +407,10 @@ __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut
             lat_increase = s2 / (double)(n - half) - s1 / (double)half;
         }
         __syncwarp();
+    } else if (n <= wbuf) {
+        means_from_smem(buf, reinterpret_cast<LeafScratch *>(buf + wbuf + 32), n, need_increase, avg_lat, lat_increase);
     } else {
-        mi_means_big(co, ring, dl, buf, need_increase, avg_lat, lat_increase);
+        mi_means_stream(co, ring, dl, buf, need_increase, avg_lat, lat_increase);
     }
 }
 
@@ -363,7 +429,7 @@ __device__ __forceinline__ void lane_send_one(LaneChain &c, const EnvState &s, R
     const long long yb = __double_as_longlong(c.q - (c.t - c.tu));     // :66-67
     const double w = __longlong_as_double(yb & ~(yb >> 63));            // max(0.0, y)
     const double cc = s.d_bw + w;                                       // :77-79
-    const bool full = cc > s.max_qd;
+    const bool full = w > s.w_full;                                      // tail_drop_threshold
     const double ll = s.dl + w;                                         // :69-70
     c.q = rdrop ? c.q : (full ? w : cc);                                // :74-82
     c.tu = rdrop ? c.tu : c.t;
@@ -422,7 +488,7 @@ __device__ __forceinline__ void lane_send_phase_staged(LaneChain &c, const EnvSt
                 const long long yb = __double_as_longlong(c.q - (c.t - c.tu));     // :66-67
                 const double w = __longlong_as_double(yb & ~(yb >> 63));            // max(0.0, y)
                 const double cc = s.d_bw + w;                                       // :77-79
-                const bool full = cc > s.max_qd;
+                const bool full = w > s.w_full;                                      // tail_drop_threshold
                 const double ll = s.dl + w;                                         // :69-70
                 c.q = rdrop ? c.q : (full ? w : cc);                                // :74-82
                 c.tu = rdrop ? c.tu : c.t;
@@ -490,7 +556,7 @@ __device__ __forceinline__ void coop_send_phase(LaneChain &c, const EnvState &s,
                 const long long yb = __double_as_longlong(c.q - (c.t - c.tu));     // :66-67
                 const double w = __longlong_as_double(yb & ~(yb >> 63));            // max(0.0, y)
                 const double cc = s.d_bw + w;                                       // :77-79
-                const bool full = cc > s.max_qd;
+                const bool full = w > s.w_full;                                      // tail_drop_threshold
                 const double ll = s.dl + w;                                         // :69-70
                 c.q = rdrop ? c.q : (full ? w : cc);                                // :74-82
                 c.tu = rdrop ? c.tu : c.t;

@@ -49,7 +49,7 @@ def test_workspace_bytes_and_validation():
     sb, rb = C.c_uint64(), C.c_uint64()
     assert L.pcc_workspace_bytes(C.byref(cfg), C.byref(sb), C.byref(rb)) == 0
     assert rb.value == 4096 * 65536 * 16
-    assert sb.value >= 4096 * (14 * 8 + 2 * 8 + 4 * 4 + 30 * 8)
+    assert sb.value >= 4096 * (15 * 8 + 2 * 8 + 4 * 4 + 30 * 8)
     for field, bad in (("ring_capacity", 1000), ("history_len", 0), ("n_features", 13), ("n_envs", 0),
                        ("rng_kind", 7), ("abi_version", 99)):
         c2 = lib.PccConfig.from_buffer_copy(cfg)

@@ -118,3 +118,33 @@ def test_twin_reports_ring_overflow():
     t.seed_philox(1)
     t.reset(500.0, 0.5, 1000, 0.0, 750.0)
     assert t.overflow
+
+
+def test_tail_drop_threshold_is_exact():
+    """pcc_core.cuh: tail_drop_threshold -- `w > w_full` must equal the reference's test
+    `1/bw + w > max_queue_delay` (network_sim.py:77-79) for EVERY w >= 0, in particular in the ulp
+    neighbourhood of the threshold."""
+    import ctypes as C
+    import twin_util
+    L = twin_util.lib()
+    L.twin_tail_drop_threshold.restype = C.c_double
+    L.twin_tail_drop_threshold.argtypes = [C.c_double, C.c_double]
+    g = np.random.default_rng(0)
+    for _ in range(3000):
+        bw = float(np.exp(g.uniform(np.log(1.0), np.log(1e6))))
+        queue = int(1 + np.exp(g.uniform(0, 9)))
+        d_bw, max_qd = 1.0 / bw, queue / bw
+        wf = L.twin_tail_drop_threshold(d_bw, max_qd)
+        assert wf >= 0.0
+        cands = [0.0, wf, max_qd, max_qd - d_bw, g.uniform(0, 2 * max_qd)]
+        w = wf
+        for _k in range(4):
+            w = np.nextafter(w, np.inf); cands.append(float(w))
+        w = wf
+        for _k in range(4):
+            w = np.nextafter(w, -np.inf)
+            if w >= 0:
+                cands.append(float(w))
+        for w in cands:
+            assert (d_bw + w > max_qd) == (w > wf), (bw, queue, w, wf)
+    assert L.twin_tail_drop_threshold(1.0, 0.5) == -1.0   # never admissible: every packet is tail-dropped

@@ -94,3 +94,5 @@ double twin_rate(Twin *t) { return t->s.rate; }
 int twin_overflow(Twin *t) { return t->overflow; }
 uint32_t twin_inflight(Twin *t) { return t->s.tail - t->s.h2; }
 }
+
+extern "C" double twin_tail_drop_threshold(double d_bw, double max_qd) { return pcc::tail_drop_threshold(d_bw, max_qd); }
