@@ -343,7 +343,30 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
     PCC_TICK(0);
     // phase A: E serial chains side by side (already done by pcc_send_kernel when !DO_SEND)
     if (DO_SEND) {
-        if (cnt == 1) coop_send_phase(c, s, ring, rng, owner, cnt, s.h2, p.cap, end, inv_rate);   // warp-uniform branch
+        if (cnt == 1 && buf != nullptr) {
+            // a heavy env alone in its warp: the 32-lane chunked send phase of the group kernel (chain on
+            // lane 0, Philox on all lanes, records staged in shared memory) -- 114 cycles per packet
+            EnvState sb;
+            sb.lr = __shfl_sync(PCC_FULL, s.lr, 0); sb.dl = __shfl_sync(PCC_FULL, s.dl, 0);
+            sb.d_bw = __shfl_sync(PCC_FULL, s.d_bw, 0); sb.w_full = __shfl_sync(PCC_FULL, s.w_full, 0);
+            double bt = __shfl_sync(PCC_FULL, c.t, 0), bq = __shfl_sync(PCC_FULL, c.q, 0), btu = __shfl_sync(PCC_FULL, c.tu, 0);
+            uint32_t btail = __shfl_sync(PCC_FULL, c.tail, 0);
+            const uint32_t bh2 = __shfl_sync(PCC_FULL, s.h2, 0);
+            const unsigned long long bseed = __shfl_sync(PCC_FULL, (unsigned long long)rng.seed, 0);
+            uint64_t bdraws = __shfl_sync(PCC_FULL, (unsigned long long)rng.draws, 0);
+            const double bend = __shfl_sync(PCC_FULL, end, 0), binv = __shfl_sync(PCC_FULL, inv_rate, 0);
+            const long long be0 = __shfl_sync(PCC_FULL, (long long)e, 0);
+            DevRing r0{p.rings + (size_t)be0 * p.cap, p.cap - 1u};
+            int32_t bsent = 0;
+            bool bovf = false;
+            double2 *stage2 = reinterpret_cast<double2 *>(reinterpret_cast<char *>(buf) + (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch));
+            coop_send_chunks(g, true, sb, r0, bseed, bdraws, bend, binv, stage2, bt, bq, btu, btail, bh2, bsent, bovf);
+            if (owner) {
+                c.t = bt; c.q = bq; c.tu = btu; c.tail = btail; c.sent += bsent; c.ovf = c.ovf || bovf;
+                rng.init(rng.seed, bdraws);
+            }
+        }
+        else if (cnt == 1) coop_send_phase(c, s, ring, rng, owner, cnt, s.h2, p.cap, end, inv_rate);   // reset path (no smem)
 #if PCC_STAGED_STORES
         else lane_send_phase_staged(c, s, ring.base, ring.mask, rng, owner, s.h2, p.cap, end, inv_rate, stage);
 #else
@@ -896,17 +919,17 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     const char *grp = getenv("PCC_B200_GROUP");
     h->group = grp ? atoi(grp) : 8;
     if (h->group != 0 && h->group != 8 && h->group != 16 && h->group != 32) h->group = 8;
-    // execution mode: "warp" (a warp owns several envs; best for big batches), "group" (G lanes per env;
-    // best when the batch is too small to fill the chip), "scalar" (1 thread per env).  Default: by size.
+    // execution mode: "warp" (default: a warp owns one heavy env or several light ones), "group" (G lanes
+    // per env, all envs alike), "scalar" (1 thread per env).
     const char *mode = getenv("PCC_B200_MODE");
     const char *epw = getenv("PCC_B200_EPW");
     const bool small_batch = cfg->n_envs <= 16384;
     h->epw = 0;
-    if ((mode && !strcmp(mode, "warp")) || (!mode && !small_batch)) {
+    if (!mode || !strcmp(mode, "warp")) {
         h->epw = epw ? atoi(epw) : 8;   // static envs per warp, used only when rebalancing is off
         if (h->epw != 4 && h->epw != 8 && h->epw != 16 && h->epw != 32) h->epw = 8;
         h->group = 0;
-    } else if (mode && !strcmp(mode, "scalar")) {
+    } else if (!strcmp(mode, "scalar")) {
         h->group = 0;
     } else if (!grp) {
         h->group = small_batch ? 32 : 8;
@@ -950,7 +973,7 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         h->cm.c0 = c0 ? (float)atof(c0) : 7000.0f;
         h->cm.c1 = c1 ? (float)atof(c1) : 60.0f;
         const char *hp = getenv("PCC_B200_HEAVY");
-        h->cm.heavy_packets = hp ? (float)atof(hp) : 1024.0f;
+        h->cm.heavy_packets = hp ? (float)atof(hp) : (cfg->n_envs <= 16384 ? 128.0f : 1024.0f);   // small batches: latency first
         h->cm.target_warps = tw ? atoi(tw) : 148 * 32;
         h->max_warps = (int64_t)n;   // worst case: every env heavy; idle warps exit at once
         if (ce == cudaSuccess) ce = cudaMalloc(&h->cost64, 8 * n);

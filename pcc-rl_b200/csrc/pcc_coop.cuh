@@ -123,6 +123,70 @@ struct GroupSmem {
     double buf[PCC_LEAF + ((G == 32) ? 4 : 1) * G];    // acked-latency staging for np.mean
 };
 
+// Phase (1) of an MI for a group of G lanes: all sends with t < end.  Lane 0 of the group runs the
+// branch-free queue recurrence over chunks of up to 2G packets; the loss draws of a chunk come from
+// all G lanes (one Philox block each, two ballots); records are staged in shared memory and copied
+// to the ring by the whole group.  Every lane holds the same (t, qd, t_upd, tail, draws, sent) on
+// entry and on exit.  Warp-uniform control flow: all 32 lanes of the warp must call it together.
+template <int G, class Ring>
+__device__ __forceinline__ void coop_send_chunks(const Grp<G> &g, bool alive, const EnvState &s, Ring &ring,
+                                                 uint64_t seed, uint64_t &draws, double end, double inv_rate,
+                                                 double2 *stage, double &t, double &qd, double &t_upd,
+                                                 uint32_t &tail, uint32_t h2, int32_t &sent, bool &ovf)
+{
+    const uint32_t cap = ring.capacity();
+    bool more = alive && (t < end);
+    while (__any_sync(PCC_FULL, more)) {
+        const unsigned off = (unsigned)(draws & 1ull);
+        uint32_t c0, c1, c2, c3;
+        philox_block(seed, (draws >> 1) + g.gl, c0, c1, c2, c3);
+        const unsigned be = g.ballot(res53(c0, c1) < s.lr);   // draw 2*blk   of lane's block  (:73)
+        const unsigned bo = g.ballot(res53(c2, c3) < s.lr);   // draw 2*blk+1
+        uint64_t dm = interleave_bits(be, bo) >> off;         // bit k = random drop of the chunk's k-th packet
+        const int navail = 2 * G - (int)off;
+        int k = 0;
+        if (g.gl == 0 && more) {
+            if ((uint32_t)(tail - h2) + (uint32_t)navail > cap) { ovf = true; }   // fatal, reported by the host
+            else {
+                double tt = t, q = qd, tu = t_upd;
+#pragma unroll 2
+                for (; k < navail; ++k) {
+                    if (!(tt < end)) break;
+                    const bool rdrop = (dm & 1ull) != 0ull;
+                    dm >>= 1;
+                    const long long yb = __double_as_longlong(q - (tt - tu));   // :66-67
+                    const double w = __longlong_as_double(yb & ~(yb >> 63));    // max(0.0, y)
+                    const double c = s.d_bw + w;                                // :82
+                    const bool full = w > s.w_full;                             // :77-79 (tail_drop_threshold)
+                    const double ll = s.dl + w;                                 // :69-70
+                    q = rdrop ? q : (full ? w : c);                             // :74-82
+                    tu = rdrop ? tu : tt;
+                    const bool dropped = rdrop || full;
+                    const double lsigned = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
+                    stage[k] = make_double2(tt + ll, lsigned);                  // :173-175
+                    tt = tt + inv_rate;                                         // :161
+                }
+                t = tt; qd = q; t_upd = tu;
+            }
+        }
+        const int packed = g.bcast((int)(k | ((k == navail && t < end && !ovf) ? 0x100 : 0)), 0);
+        k = packed & 0xff;
+        __syncwarp();
+        for (int j = (int)g.gl; j < k; j += G) {
+            const double2 v = stage[j];
+            Rec r; r.a = v.x; r.l = v.y;
+            ring.store(tail + (uint32_t)j, r);
+        }
+        __syncwarp();
+        if (more) { tail += (uint32_t)k; draws += (uint64_t)k; sent += k; }
+        more = more && ((packed & 0x100) != 0);
+    }
+    // make the chain lane's state the group's state
+    t = g.bcast(t, 0); qd = g.bcast(qd, 0); t_upd = g.bcast(t_upd, 0);
+    ovf = g.bcast((int)ovf, 0) != 0;
+    __syncwarp();   // record stores above are read by other lanes below
+}
+
 // One monitor interval.  Every lane of a group holds the same EnvState copy on entry and on
 // exit.  `alive` = this group has an env (warp-uniform control flow needs all lanes present).
 // On exit, if out.acked <= PCC_LEAF, sm.buf[0..out.acked) holds the MI's samples in order.
@@ -161,56 +225,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
     }
 
     // ---- (1) sends with t < end: chain on lane 0, loss draws from all lanes ---------------
-    bool more = alive && (t < end);
-    while (__any_sync(PCC_FULL, more)) {
-        const unsigned off = (unsigned)(draws & 1ull);
-        uint32_t c0, c1, c2, c3;
-        philox_block(seed, (draws >> 1) + g.gl, c0, c1, c2, c3);
-        const unsigned be = g.ballot(res53(c0, c1) < s.lr);   // draw 2*blk   of lane's block  (:73)
-        const unsigned bo = g.ballot(res53(c2, c3) < s.lr);   // draw 2*blk+1
-        uint64_t dm = interleave_bits(be, bo) >> off;         // bit k = random drop of the chunk's k-th packet
-        const int navail = 2 * G - (int)off;
-        int k = 0;
-        if (g.gl == 0 && more) {
-            if ((uint32_t)(tail - h2) + (uint32_t)navail > cap) { ovf = true; }   // fatal, reported by the host
-            else {
-                double tt = t, q = qd, tu = t_upd;
-#pragma unroll 2
-                for (; k < navail; ++k) {
-                    if (!(tt < end)) break;
-                    const bool rdrop = (dm & 1ull) != 0ull;
-                    dm >>= 1;
-                    const long long yb = __double_as_longlong(q - (tt - tu));   // :66-67
-                    const double w = __longlong_as_double(yb & ~(yb >> 63));    // max(0.0, y)
-                    const double c = s.d_bw + w;                                // :82
-                    const bool full = w > s.w_full;                             // :77-79 (tail_drop_threshold)
-                    const double ll = s.dl + w;                                 // :69-70
-                    q = rdrop ? q : (full ? w : c);                             // :74-82
-                    tu = rdrop ? tu : tt;
-                    const bool dropped = rdrop || full;
-                    const double lsigned = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
-                    sm.stage[k] = make_double2(tt + ll, lsigned);              // :173-175
-                    tt = tt + inv_rate;                                         // :161
-                }
-                t = tt; qd = q; t_upd = tu;
-            }
-        }
-        const int packed = g.bcast((int)(k | ((k == navail && t < end && !ovf) ? 0x100 : 0)), 0);
-        k = packed & 0xff;
-        __syncwarp();
-        for (int j = (int)g.gl; j < k; j += G) {
-            const double2 v = sm.stage[j];
-            Rec r; r.a = v.x; r.l = v.y;
-            ring.store(tail + (uint32_t)j, r);
-        }
-        __syncwarp();
-        if (more) { tail += (uint32_t)k; draws += (uint64_t)k; sent += k; }
-        more = more && ((packed & 0x100) != 0);
-    }
-    // make the chain lane's state the group's state
-    t = g.bcast(t, 0); qd = g.bcast(qd, 0); t_upd = g.bcast(t_upd, 0);
-    ovf = g.bcast((int)ovf, 0) != 0;
-    __syncwarp();   // record stores above are read by other lanes below
+    coop_send_chunks(g, alive, s, ring, seed, draws, end, inv_rate, sm.stage, t, qd, t_upd, tail, h2, sent, ovf);
     PCC_TICK(1);
 
     // ---- (2) hop-1 events with a < end ------------------------------------------------------

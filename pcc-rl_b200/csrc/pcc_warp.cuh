@@ -32,7 +32,8 @@ struct LeafScratch {
     int off[PCC_MAX_LEAVES];
     int cnt[PCC_MAX_LEAVES];
 };
-__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch); }
+// ... followed by 64 double2 of record staging for the single-env send phase (coop_send_chunks<32>)
+__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch) + 64 * 16; }
 
 struct ConsumeIn {
     double end, dl, tnext;
