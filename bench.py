@@ -250,6 +250,27 @@ def main():
     b2b_ms = D.max_over_ranks(s.elapsed_time(e), dev)
     env.check()
 
+    # ---------------- pass 2b: fused rollout, 64 monitor intervals per launch ----------------
+    del env
+    env = make_env()
+    env.reset()
+    RK = 64
+    n_roll = max(1, K // RK)
+    for t in range(W):
+        env.step(actions[t])
+    ract = actions[W:W + RK]
+    if ract.shape[0] < RK:
+        ract = torch.randn((RK, n), generator=gen, device=dev, dtype=torch.float64) * ACTION_SIGMA
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n_roll):
+        env.rollout(RK, actions=ract, want_obs=False, want_counts=False)
+    e.record()
+    barrier()
+    roll_ms = D.max_over_ranks(s.elapsed_time(e), dev)
+    env.check()
+
     # ---------------- pass 3: end to end through host buffers (pcc_step_host) ----------------
     del env
     env = make_env()
@@ -304,6 +325,9 @@ def main():
                    "parallelism": "env-batch sharding x%d, no data-path collective" % world},
         "back_to_back": {"value": n_global * K / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K,
                          "note": "K steps enqueued back to back, one event bracket, warm L2"},
+        "rollout": {"value": n_global * RK * n_roll / (roll_ms * 1e-3), "ms_per_step": roll_ms / (RK * n_roll),
+                    "steps_per_launch": RK, "launches": n_roll,
+                    "note": "pcc_rollout: 64 MIs per launch with in-kernel auto-reset, same actions; bit-identical to 64 steps"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 8 * n,
                 "d2h_bytes_per_step": n * (8 * hf + 8 + 1), "ms_per_step": 1e3 * e2e_s / K,
                 "api": "PccBatchEnv.step_host -> pcc_step_host (pinned host buffers, synchronous)"},

@@ -18,6 +18,7 @@
  *                                -> Sender.record_run / SenderHistory   :291-293; common/sender_obs.py:56-73
  *                                -> MI metrics                          common/sender_obs.py:110-191
  *   pcc_get_mt_state / pcc_set_mt_state   random.getstate() / random.setstate()
+ *   pcc_rollout                the env side of PPO1's rollout loop      gym/stable_solve.py:52-58 (+ policy :30-45)
  *
  * Conventions
  *   - Every function returns 0 on success, a negative PCC_E* code otherwise; the message is
@@ -158,6 +159,31 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
  * buffers should be page-locked for full copy bandwidth. */
 int pcc_step_host(pcc_handle h, const double *actions_host, double *obs_host, double *reward_host,
                   uint8_t *done_host, int32_t *counts_host, void *stream);
+
+/* On-device policy for pcc_rollout: the MLP of stable_solve.py:30-45 (obs -> h1 -> h2 -> 1, tanh hidden
+ * layers, linear output = mean of the Gaussian action).  All pointers are device pointers to binary64,
+ * row-major [out][in].  stochastic != 0 adds exp(log_std) * N(0,1) drawn from a Philox stream keyed by
+ * (noise_seed; env, step). */
+typedef struct pcc_policy {
+    const double *w1, *b1, *w2, *b2, *w3, *b3;
+    int32_t n_in, h1, h2, stochastic;
+    double log_std;
+    uint64_t noise_seed;
+} pcc_policy;
+
+/* Fused rollout: n_steps monitor intervals for every env in ONE launch (what PPO1's
+ * traj_segment_generator does around SimulatedNetworkEnv.step, stable_solve.py:52-58).  Each step is
+ * exactly pcc_step followed, for finished envs, by pcc_reset with the next row of the parameter bank.
+ *   actions_dev       double[n_steps][n_envs], or NULL to use `policy`
+ *   reset_params_dev  double[n_episodes][5][n_envs]: bw, delay, queue, loss, start_rate of the
+ *                     episodes each env starts DURING this rollout, in order (row 0 = its first reset)
+ *   obs_dev           double[n_steps][n_envs][history_len*n_features]  (optional) observation AFTER the
+ *                     step -- for a finished env the first observation of its next episode
+ *   actions_out_dev   double[n_steps][n_envs] (optional) the actions taken
+ *   reward_dev, done_dev, counts_dev   [n_steps][n_envs] (counts optional, [..][3]) */
+int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const pcc_policy *policy,
+                const double *reset_params_dev, int32_t n_episodes, double *obs_dev, double *actions_out_dev,
+                double *reward_dev, uint8_t *done_dev, int32_t *counts_dev, void *stream);
 
 /* Synchronises `stream` and reports sticky device-side errors (PCC_EOVERFLOW). */
 int pcc_check(pcc_handle h, void *stream);

@@ -24,6 +24,12 @@ class PccConfig(C.Structure):
                 ("reserved0", C.c_int32), ("ring_capacity", C.c_int64), ("consts", PccConsts)]
 
 
+class PccPolicy(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("w3", C.c_void_p), ("b3", C.c_void_p), ("n_in", C.c_int32), ("h1", C.c_int32),
+                ("h2", C.c_int32), ("stochastic", C.c_int32), ("log_std", C.c_double), ("noise_seed", C.c_uint64)]
+
+
 class PccError(RuntimeError):
     def __init__(self, code, msg):
         RuntimeError.__init__(self, "libpcc_b200 error %d: %s" % (code, msg))
@@ -33,7 +39,7 @@ class PccError(RuntimeError):
 # every symbol include/pcc_b200.h declares
 EXPORTS = ["pcc_default_consts", "pcc_default_config", "pcc_ring_capacity_for", "pcc_workspace_bytes",
            "pcc_create", "pcc_destroy", "pcc_attach", "pcc_seed", "pcc_get_mt_state", "pcc_set_mt_state",
-           "pcc_reset", "pcc_step", "pcc_step_host", "pcc_check", "pcc_get_column", "pcc_launch_count",
+           "pcc_reset", "pcc_step", "pcc_step_host", "pcc_rollout", "pcc_check", "pcc_get_column", "pcc_launch_count",
            "pcc_last_error", "pcc_abi_version"]
 
 _lib = None
@@ -73,6 +79,7 @@ def load(rebuild_if_stale=True):
     L.pcc_reset.argtypes = [vp, u8p, dp, dp, vp, dp, dp, dp, vp]
     L.pcc_step.argtypes = [vp, dp, dp, dp, u8p, vp, dp, vp]
     L.pcc_step_host.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
+    L.pcc_rollout.argtypes = [vp, C.c_int32, dp, C.POINTER(PccPolicy), dp, C.c_int32, dp, dp, dp, u8p, vp, vp]
     L.pcc_check.argtypes = [vp, vp]
     L.pcc_get_column.argtypes = [vp, C.c_char_p, dp, vp]
     L.pcc_launch_count.argtypes = [vp]

@@ -196,6 +196,64 @@ class PccBatchEnv(object):
             self.reset(mask=finished)
         return self.obs, self.reward, done, info
 
+    def rollout(self, n_steps, actions=None, policy=None, want_obs=True, want_counts=True):
+        """n_steps monitor intervals for every env in ONE kernel launch (fused rollout), with in-kernel
+        auto-reset.  Equivalent, bit for bit, to n_steps calls of step().
+
+        actions: [n_steps, n_envs] float64 cuda tensor, or None to use `policy` = dict(w1, b1, w2, b2, w3,
+        b3: float64 cuda tensors of the MLP obs -> h1 -> h2 -> 1 with tanh hidden layers; log_std, stochastic,
+        noise_seed optional).  Returns dict(obs [K,N,H*F] (observation after each step), actions [K,N],
+        reward [K,N], done [K,N] bool, counts [K,N,3])."""
+        torch = self.torch
+        K, n = int(n_steps), self.n_envs
+        # parameters of the episodes that START during this rollout (host bookkeeping is deterministic)
+        n_resets = (self._steps + K) // self.max_steps
+        n_eps = int(n_resets.max()) if n > 0 else 0
+        bank = np.zeros((max(n_eps, 1), 5, n))
+        for j in range(n_eps):
+            sel = n_resets > j
+            saved = self._episode.copy()
+            self._episode = saved + j
+            pj = self._sample(sel)
+            self._episode = saved
+            for r, k in enumerate(("bw", "lat", "queue", "loss", "start_rate")):
+                bank[j, r, sel] = pj[k][sel]
+                self.params[k][sel] = pj[k][sel]
+        bank_dev = torch.as_tensor(bank, dtype=torch.float64).to(self.device)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        out = dict(reward=torch.empty((K, n), **f64), done=torch.empty((K, n), dtype=torch.uint8, device=self.device),
+                   actions=torch.empty((K, n), **f64))
+        out["obs"] = torch.empty((K, n, self.obs_dim), **f64) if want_obs else None
+        out["counts"] = torch.empty((K, n, 3), dtype=torch.int32, device=self.device) if want_counts else None
+        act_ptr, pol_ref, keep = None, None, []
+        if actions is not None:
+            a = torch.as_tensor(actions).to(self.device, torch.float64).reshape(K, n).contiguous()
+            keep.append(a)
+            act_ptr = a.data_ptr()
+        else:
+            pol = _lib.PccPolicy()
+            ws = {k: policy[k].to(self.device, torch.float64).contiguous() for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
+            keep.append(ws)
+            for k, v in ws.items():
+                setattr(pol, k, v.data_ptr())
+            pol.n_in, pol.h1, pol.h2 = ws["w1"].shape[1], ws["w1"].shape[0], ws["w2"].shape[0]
+            assert ws["w2"].shape[1] == pol.h1 and ws["w3"].numel() == pol.h2 and pol.n_in == self.obs_dim
+            pol.log_std = float(policy.get("log_std", 0.0))
+            pol.stochastic = int(bool(policy.get("stochastic", False)))
+            pol.noise_seed = int(policy.get("noise_seed", 0)) & 0xFFFFFFFFFFFFFFFF
+            pol_ref = C.byref(pol)
+        p = lambda t: t.data_ptr() if t is not None else None
+        _lib.check(self.L.pcc_rollout(self.h, K, act_ptr, pol_ref, bank_dev.data_ptr(), n_eps, p(out["obs"]),
+                                      out["actions"].data_ptr(), out["reward"].data_ptr(), out["done"].data_ptr(),
+                                      p(out["counts"]), self._stream()))
+        self._keep = (bank_dev, keep)
+        self._steps = (self._steps + K) % self.max_steps
+        self._episode += n_resets
+        if want_obs:
+            self.obs.copy_(out["obs"][K - 1])
+        out["done"] = out["done"].bool()
+        return out
+
     def step_device(self, actions_f64):
         """Lowest-overhead step: `actions_f64` is a contiguous float64 cuda tensor [n_envs]; no
         auto-reset, no host bookkeeping beyond the step counter.  Returns None (read env.obs etc.)."""

@@ -534,6 +534,181 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused rollout: K monitor intervals per launch.  Every warp keeps its envs
+// for the whole rollout -- state in registers, in-kernel auto-reset from a pre-sampled parameter
+// bank, optional on-device policy (the MLP of stable_solve.py:30-45) -- so there is no per-MI grid
+// barrier and the per-step imbalance between envs averages out over the K steps.
+// ---------------------------------------------------------------------------------------
+struct PolicyDev {
+    const double *w1, *b1, *w2, *b2, *w3, *b3;   // row-major [out][in]; null w1 = no policy
+    int32_t n_in, h1, h2;
+    double log_std;
+    unsigned long long noise_seed;
+    int32_t stochastic;
+};
+struct RolloutArgs {
+    int32_t K;
+    const double *actions;       // [K][n] or null
+    PolicyDev pol;
+    const double *bank;          // [n_episodes][5][n]: bw, delay, queue, loss, start_rate
+    int32_t n_episodes;
+    double *obs;                 // [K][n][H*F] or null
+    double *act_out;             // [K][n] or null
+    double *reward;              // [K][n]
+    uint8_t *done;               // [K][n]
+    int32_t *counts;             // [K][n][3] or null
+};
+
+#define PCC_POLICY_MAXH 64
+// action = MLP(obs) [+ exp(log_std) * N(0,1)]: tanh hidden layers, linear output (MlpPolicy of PPO1)
+__device__ __noinline__ double policy_action(PolicyDev pol, const double *hrow, int slot_oldest, int H, int F, int64_t e,
+                                             unsigned long long t)
+{
+    double a1[PCC_POLICY_MAXH], a2[PCC_POLICY_MAXH];
+    double obs_row[128];
+    for (int h = 0; h < H; h++) {          // oldest -> newest
+        int sl = slot_oldest + h;
+        if (sl >= H) sl -= H;
+        for (int f = 0; f < F; f++) obs_row[h * F + f] = hrow[sl * F + f];
+    }
+    for (int i = 0; i < pol.h1; i++) {
+        double acc = pol.b1[i];
+        for (int j = 0; j < pol.n_in; j++) acc += pol.w1[i * pol.n_in + j] * obs_row[j];
+        a1[i] = tanh(acc);
+    }
+    for (int i = 0; i < pol.h2; i++) {
+        double acc = pol.b2[i];
+        for (int j = 0; j < pol.h1; j++) acc += pol.w2[i * pol.h1 + j] * a1[j];
+        a2[i] = tanh(acc);
+    }
+    double out = pol.b3[0];
+    for (int j = 0; j < pol.h2; j++) out += pol.w3[j] * a2[j];
+    if (pol.stochastic) {   // Box-Muller on a Philox block keyed by (noise_seed; env, step)
+        uint32_t c0 = (uint32_t)e, c1 = (uint32_t)(e >> 32), c2 = (uint32_t)t, c3 = 0x4e4f4953u;   // 'NOIS'
+        philox4x32_10(c0, c1, c2, c3, (uint32_t)pol.noise_seed, (uint32_t)(pol.noise_seed >> 32));
+        const double u1 = (res53(c0, c1) + 1.1102230246251565e-16), u2 = res53(c2, c3);
+        out += exp(pol.log_std) * sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+    return out;
+}
+
+// in-kernel reset of the lanes in `need` (network_sim.py:469-484).  Inlined: passing the env state by
+// reference to an out-of-line function would pin it to the stack for the whole rollout loop.
+__device__ __forceinline__ void rollout_reset(const DevState &p, bool need, int cnt, int64_t e, EnvState &s, PhiloxRng &rng,
+                                              const double *bank, int ep, WarpStage &dummy, bool &ovf)
+{
+    const Grp<32> g;
+    if (need) {
+        const size_t n = (size_t)p.n;
+        const double *b = bank + (size_t)ep * 5 * n;
+        const double bwv = b[0 * n + e], dlv = b[1 * n + e], qv = b[2 * n + e], lossv = b[3 * n + e], sr = b[4 * n + e];
+        s.d_bw = 1.0 / bwv; s.dl = dlv; s.lr = lossv; s.max_qd = (double)(long long)qv / bwv;
+        s.w_full = tail_drop_threshold(s.d_bw, s.max_qd);
+        s.qd = 0.0; s.t_upd = 0.0; s.rate = sr; s.cur_time = 0.0; s.next_send = 1.0 / sr;
+        s.run_dur = 3 * dlv; s.conn_min = 0.0;
+        s.h1 = s.tail; s.h2 = s.tail; s.steps = 0;
+        p.d_bw[e] = s.d_bw; p.bw[e] = bwv; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd; p.w_full[e] = s.w_full;
+    }
+    MiOut mo;
+    double a, li;
+    warp_mi<false, true>(g, p, need, cnt, e, s, rng, s.run_dur, nullptr, 0, dummy, mo, a, li);   // :478
+    ovf = mo.overflow;
+    warp_mi<false, true>(g, p, need, cnt, e, s, rng, s.run_dur, nullptr, 0, dummy, mo, a, li);   // :479
+    ovf = ovf || mo.overflow;
+}
+
+__global__ void __launch_bounds__(PCC_WARP_THREADS, PCC_WARP_MINBLOCKS)
+pcc_rollout_kernel(DevState p, WarpPartition part, unsigned long long head0, RolloutArgs a)
+{
+    extern __shared__ double dyn_smem[];      // per warp: warp_smem_bytes(part.wbuf)
+    __shared__ WarpStage sstage[1];
+    double *wsm = dyn_smem + (size_t)(threadIdx.x >> 5) * (warp_smem_bytes(part.wbuf) / 8);
+    const Grp<32> g;
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head0 + (unsigned long long)a.K;
+    int64_t first;
+    int cnt;
+    if (part.starts) {
+        const int nw = *part.n_warps;
+        if (w >= nw) return;                       // whole warp
+        first = part.starts[w];
+        cnt = (int)(part.starts[w + 1] - first);
+    } else {
+        first = w * part.static_e;
+        if (first >= p.n) return;
+        cnt = (int)((p.n - first < part.static_e) ? (p.n - first) : part.static_e);
+    }
+    const bool owner = (int)lane < cnt;
+    const int64_t e = owner ? (part.perm ? (int64_t)part.perm[first + lane] : first + lane) : 0;
+    EnvState s;
+    load_env(p, e, s);
+    PhiloxRng rng;
+    rng.init(p.seed[e], p.draws[e]);
+    const int H = p.H, F = p.F, HF = H * F;
+    double *hrow = p.hist + (size_t)e * HF;
+    double ret_acc = p.ret_acc[e];
+    int ep = 0;
+    bool any_ovf = false;
+#pragma unroll 1
+    for (int k = 0; k < a.K; k++) {
+        const size_t kn = (size_t)k * (size_t)p.n + (size_t)e;
+        const int slot_new = (int)((head0 + (unsigned long long)k) % (unsigned long long)H);
+        // ---- action: given, or from the policy on the current observation -------------------
+        double act = 0.0;
+        if (owner) {
+            if (a.actions) act = a.actions[kn];
+            else act = policy_action(a.pol, hrow, slot_new, H, F, e, head0 + (unsigned long long)k);   // slot_new = oldest row now
+            if (a.act_out) a.act_out[kn] = act;
+            s.rate = apply_rate_delta(s.rate, act, p.c);                         // :412
+        }
+        StepOut o;
+        double avg_lat, lat_inc;
+        warp_mi<true, true>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf, sstage[0], o.mi, avg_lat, lat_inc);   // :416
+        bool need_reset = false;
+        if (owner) {
+            mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
+            s.steps += 1;                                                        // :419
+            if (o.st.avg_lat > 0.0) s.run_dur = 0.5 * o.st.avg_lat;              // :437-438
+            o.done = s.steps >= p.c.max_steps;                                   // :444
+            any_ovf = any_ovf || o.mi.overflow;
+            for (int f = 0; f < F; f++) hrow[slot_new * F + f] = metric_value(o.st, p.ids[f]);
+            a.reward[kn] = o.st.reward;
+            a.done[kn] = o.done ? 1 : 0;
+            ret_acc += o.st.reward;                                              // :443
+            if (o.done) { p.ret_last[e] = ret_acc; ret_acc = 0.0; }
+            if (a.counts) { a.counts[3 * kn + 0] = o.mi.sent; a.counts[3 * kn + 1] = o.mi.acked; a.counts[3 * kn + 2] = o.mi.lost; }
+            need_reset = o.done;
+        }
+        // ---- auto-reset with the next parameters of the bank (warp-uniform branch) ------------
+        if (__any_sync(PCC_FULL, need_reset)) {
+            if (need_reset && ep >= a.n_episodes) { atomicAdd(&p.meta[META_PART_ERR], 1ull); need_reset = false; }
+            bool ovf = false;
+            rollout_reset(p, need_reset, cnt, e, s, rng, a.bank, ep, sstage[0], ovf);
+            if (need_reset) {
+                any_ovf = any_ovf || ovf;
+                ep++;
+                for (int i = 0; i < HF; i++) hrow[i] = metric_empty(p.ids[i % F]);
+            }
+        }
+        // ---- observation after the step (and after a reset): oldest -> newest ----------------
+        if (owner && a.obs) {
+            double *ob = a.obs + kn * (size_t)HF;
+            for (int h = 0; h < H; h++) {
+                int sl = slot_new + 1 + h;
+                if (sl >= H) sl -= H;
+                for (int f = 0; f < F; f++) ob[h * F + f] = hrow[sl * F + f];
+            }
+        }
+    }
+    if (!owner) return;
+    store_env_dynamic(p, e, s);
+    p.draws[e] = rng.draws;
+    p.ret_acc[e] = ret_acc;
+    if (any_ovf) flag_overflow(p, e);
+}
+
 template <int E>
 __global__ void __launch_bounds__(PCC_WARP_THREADS)
 pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double *__restrict__ bw,
@@ -1093,6 +1268,24 @@ int pcc_reset(pcc_handle h, const uint8_t *mask_dev, const double *bw_dev, const
     return PCC_OK;
 }
 
+// cost-sort the envs (descending) and cut the list into warps of ~equal cost (see WarpPartition)
+static int rebalance(pcc_handle h, cudaStream_t st)
+{
+    const int64_t n = h->cfg.n_envs;
+    const unsigned kg = (unsigned)((n + 255) / 256);
+    pcc_cost_kernel<<<kg, 256, 0, st>>>(h->d, h->cm, h->sort_keys_in, h->sort_vals_in);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp, h->sort_tmp_bytes, h->sort_keys_in,
+                                                       h->sort_keys_out, h->sort_vals_in, h->perm, (int)n, 0, 32, st));
+    pcc_target_kernel<<<1, 1024, 0, st>>>(h->sort_keys_out, n, h->cm, h->target);
+    pcc_costfloor_kernel<<<kg, 256, 0, st>>>(h->sort_keys_out, n, h->cm, h->target, h->cost64);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(h->sort_tmp, h->sort_tmp_bytes, h->cost64, h->cum_excl, (int)n, st));
+    pcc_heads_kernel<<<kg, 256, 0, st>>>(h->cum_excl, n, h->target, h->starts, h->n_warps, (long long)h->max_warps, h->d.meta);
+    h->rebalance_now = false;
+    h->steps_since_rebalance = 0;
+    h->launches += 6;
+    return PCC_OK;
+}
+
 int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *reward_dev,
              uint8_t *done_dev, int32_t *counts_dev, double *info_dev, void *stream)
 {
@@ -1123,20 +1316,8 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
         int64_t nwarps = (h->cfg.n_envs + h->epw - 1) / h->epw;
         if (h->rebalance_every > 0) {
             if (h->rebalance_now || h->steps_since_rebalance >= h->rebalance_every) {
-                // cost-sort the envs (descending) and cut the list into warps of ~equal cost
-                const int64_t n = h->cfg.n_envs;
-                const unsigned kg = (unsigned)((n + 255) / 256);
-                pcc_cost_kernel<<<kg, 256, 0, st>>>(h->d, h->cm, h->sort_keys_in, h->sort_vals_in);
-                CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp, h->sort_tmp_bytes, h->sort_keys_in,
-                                                                   h->sort_keys_out, h->sort_vals_in, h->perm, (int)n,
-                                                                   0, 32, st));
-                pcc_target_kernel<<<1, 1024, 0, st>>>(h->sort_keys_out, n, h->cm, h->target);
-                pcc_costfloor_kernel<<<kg, 256, 0, st>>>(h->sort_keys_out, n, h->cm, h->target, h->cost64);
-                CUDA_TRY(cub::DeviceScan::ExclusiveSum(h->sort_tmp, h->sort_tmp_bytes, h->cost64, h->cum_excl, (int)n, st));
-                pcc_heads_kernel<<<kg, 256, 0, st>>>(h->cum_excl, n, h->target, h->starts, h->n_warps, (long long)h->max_warps, h->d.meta);
-                h->rebalance_now = false;
-                h->steps_since_rebalance = 0;
-                h->launches += 6;
+                int rc = rebalance(h, st);
+                if (rc) return rc;
             }
             h->steps_since_rebalance++;
             part.perm = h->perm; part.starts = h->starts; part.n_warps = h->n_warps;
@@ -1171,6 +1352,50 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
         pcc_step_kernel<PCC_RNG_MT19937><<<grid_for(h), h->block, 0, st>>>(
             h->d, nullptr, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
     h->head++;
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PCC_OK;
+}
+
+int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const pcc_policy *policy,
+                const double *reset_params_dev, int32_t n_episodes, double *obs_dev, double *actions_out_dev,
+                double *reward_dev, uint8_t *done_dev, int32_t *counts_dev, void *stream)
+{
+    if (!h || !reward_dev || !done_dev) return fail(PCC_EINVAL, "null pointer");
+    if (n_steps < 1) return fail(PCC_EINVAL, "n_steps must be positive");
+    if (!actions_dev && !(policy && policy->w1)) return fail(PCC_EINVAL, "pcc_rollout needs actions or a policy");
+    if (!h->epw) return fail(PCC_EINVAL, "pcc_rollout needs the warp execution mode (Philox streams)");
+    if (n_episodes < 0 || (n_episodes > 0 && !reset_params_dev)) return fail(PCC_EINVAL, "bad reset parameter bank");
+    if (policy && policy->w1 &&
+        (policy->n_in != h->cfg.history_len * h->cfg.n_features || policy->h1 < 1 || policy->h1 > PCC_POLICY_MAXH ||
+         policy->h2 < 1 || policy->h2 > PCC_POLICY_MAXH || h->cfg.history_len * h->cfg.n_features > 128))
+        return fail(PCC_EINVAL, "policy shape does not fit (n_in = history_len * n_features <= 128, hidden <= 64)");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    WarpPartition part{nullptr, nullptr, nullptr, h->epw, h->wbuf};
+    const int wpb = h->warp_threads / 32;
+    const size_t dyn = (size_t)wpb * warp_smem_bytes(h->wbuf);
+    int64_t nwarps = (h->cfg.n_envs + h->epw - 1) / h->epw;
+    if (h->rebalance_every > 0) {
+        int rc = rebalance(h, st);
+        if (rc) return rc;
+        part.perm = h->perm; part.starts = h->starts; part.n_warps = h->n_warps;
+        nwarps = h->max_warps;
+        h->rebalance_now = true;    // costs will have drifted by the end of the rollout
+    }
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.K = n_steps; a.actions = actions_dev; a.bank = reset_params_dev; a.n_episodes = n_episodes;
+    a.obs = obs_dev; a.act_out = actions_out_dev; a.reward = reward_dev; a.done = done_dev; a.counts = counts_dev;
+    if (policy && policy->w1 && !actions_dev) {
+        a.pol.w1 = policy->w1; a.pol.b1 = policy->b1; a.pol.w2 = policy->w2; a.pol.b2 = policy->b2;
+        a.pol.w3 = policy->w3; a.pol.b3 = policy->b3; a.pol.n_in = policy->n_in; a.pol.h1 = policy->h1; a.pol.h2 = policy->h2;
+        a.pol.log_std = policy->log_std; a.pol.noise_seed = policy->noise_seed; a.pol.stochastic = policy->stochastic;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(pcc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    const unsigned wgrid = (unsigned)((nwarps + wpb - 1) / wpb);
+    pcc_rollout_kernel<<<wgrid, h->warp_threads, dyn, st>>>(h->d, part, h->head, a);
+    h->head += (unsigned long long)n_steps;
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return PCC_OK;

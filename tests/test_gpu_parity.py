@@ -251,3 +251,69 @@ def test_cuda_ring_overflow_is_reported():
     with pytest.raises(_lib.PccError) as ei:
         env.check()
     assert ei.value.code == _lib.PCC_EOVERFLOW
+
+
+def test_cuda_rollout_equals_stepwise():
+    """pcc_rollout (K monitor intervals in one launch, in-kernel auto-reset) is bit-identical to K calls
+    of pcc_step + pcc_reset, including across an episode boundary."""
+    import torch
+    n, K1, K2 = 512, 390, 60          # the second rollout crosses step 400: every env resets inside it
+    acts = np.random.default_rng(21).normal(0, 1.5, (K1 + K2, n))
+    a = _env(n_envs=n, seed=77, want_info=False)
+    b = _env(n_envs=n, seed=77, want_info=False)
+    assert torch.equal(a.reset(), b.reset())
+    k = 0
+    for K in (K1, K2):
+        out = a.rollout(K, actions=torch.as_tensor(acts[k:k + K], device=a.device))
+        for t in range(K):
+            obs, r, d, info = b.step(acts[k + t])
+            assert torch.equal(out["counts"][t], info["counts"]), (k, t)
+            assert torch.equal(out["reward"][t], r) and torch.equal(out["done"][t], d), (k, t)
+            assert torch.equal(out["obs"][t], obs), (k, t)
+        k += K
+    assert bool(out["done"].any())
+    assert np.array_equal(a._steps, b._steps) and np.array_equal(a._episode, b._episode)
+    for name in ("cur_time", "run_dur", "rate", "episode_return", "last_episode_return", "bw"):
+        assert torch.equal(a.column(name), b.column(name)), name
+    # and the two envs stay interchangeable afterwards
+    o1 = a.step(acts[0])
+    o2 = b.step(acts[0])
+    assert torch.equal(o1[0], o2[0]) and torch.equal(o1[1], o2[1])
+    a.check()
+
+
+def test_cuda_rollout_with_on_device_policy():
+    """Closed loop: the MLP policy (stable_solve.py:30-45: 30 -> 32 -> 16 -> 1, tanh) runs inside the rollout
+    kernel.  Its actions must be the torch fp64 MLP of the previous observation, and replaying those actions
+    step by step must reproduce the rollout exactly."""
+    import torch
+    n, K = 256, 80
+    g = torch.Generator().manual_seed(3)
+    pol = dict(w1=torch.randn(32, 30, generator=g, dtype=torch.float64) * 0.3, b1=torch.randn(32, generator=g, dtype=torch.float64) * 0.1,
+               w2=torch.randn(16, 32, generator=g, dtype=torch.float64) * 0.3, b2=torch.randn(16, generator=g, dtype=torch.float64) * 0.1,
+               w3=torch.randn(1, 16, generator=g, dtype=torch.float64) * 2.0, b3=torch.randn(1, generator=g, dtype=torch.float64) * 0.1)
+    a = _env(n_envs=n, seed=5, max_steps=50)     # short episodes: resets happen inside the rollout
+    b = _env(n_envs=n, seed=5, max_steps=50)
+    obs0 = a.reset().clone()
+    b.reset()
+    out = a.rollout(K, policy=pol)
+    dev = a.device
+    W = {k: v.to(dev) for k, v in pol.items()}
+    mlp = lambda o: (torch.tanh(torch.tanh(o @ W["w1"].T + W["b1"]) @ W["w2"].T + W["b2"]) @ W["w3"].T + W["b3"]).squeeze(-1)
+    prev = obs0
+    for t in range(K):
+        want = mlp(prev)
+        assert torch.allclose(out["actions"][t], want, rtol=1e-12, atol=1e-12), t
+        obs, r, d, info = b.step(out["actions"][t])
+        assert torch.equal(out["obs"][t], obs) and torch.equal(out["reward"][t], r) and torch.equal(out["done"][t], d), t
+        prev = out["obs"][t]
+    assert bool(out["done"].any())
+    # stochastic actions: Gaussian noise around the same mean, reproducible for a given noise seed
+    c = _env(n_envs=n, seed=5, max_steps=50); c.reset()
+    d_ = _env(n_envs=n, seed=5, max_steps=50); d_.reset()
+    sp = dict(pol, stochastic=True, log_std=-1.0, noise_seed=9)
+    o1 = c.rollout(10, policy=sp)
+    o2 = d_.rollout(10, policy=sp)
+    assert torch.equal(o1["actions"], o2["actions"]) and torch.equal(o1["reward"], o2["reward"])
+    noise = (o1["actions"][0] - mlp(obs0)) / np.exp(-1.0)
+    assert 0.8 < float(noise.std()) < 1.2 and abs(float(noise.mean())) < 0.25
