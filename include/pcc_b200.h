@@ -197,6 +197,26 @@ int pcc_get_column(pcc_handle h, const char *name, double *dst_dev, void *stream
 /* Number of kernel launches issued by this handle so far (pcc_step = 1 launch). */
 int64_t pcc_launch_count(pcc_handle h);
 
+/* ---- several senders per link (BASELINE config 5) ------------------------------------------------------
+ * The reference's Network takes lists of senders (gym/network_sim.py:100-126, 140-178) although its env
+ * creates one.  Semantics here: all senders share links [l0, l1]; heap ties are broken by sender index;
+ * step applies actions[i] to sender i (:409-412 generalised); every sender has its own MI, history, obs and
+ * reward (:194,205 on its own MI); the MI duration follows sender 0 (:437-438 as written).  Generic per-env
+ * event heap, one env per thread: exact, not fast.  cfg->ring_capacity sizes the heap (x n_senders events)
+ * and the per-sender RTT sample buffers; Philox streams only.  Arrays: [n_envs][n_senders]... row-major. */
+typedef struct pcc_multi_handle_s *pcc_multi_handle;
+int pcc_multi_workspace_bytes(const pcc_config *cfg, int32_t n_senders, uint64_t *bytes);
+int pcc_multi_create(pcc_multi_handle *out, const pcc_config *cfg, int32_t n_senders, void *workspace_dev);
+void pcc_multi_destroy(pcc_multi_handle h);
+int pcc_multi_seed(pcc_multi_handle h, const uint64_t *seeds_dev, void *stream);
+int pcc_multi_reset(pcc_multi_handle h, const uint8_t *mask_dev, const double *bw_dev, const double *delay_dev,
+                    const int64_t *queue_dev, const double *loss_dev, const double *start_rates_dev /*[n][S]*/,
+                    double *obs_dev /*[n][S][H*F], optional*/, void *stream);
+int pcc_multi_step(pcc_multi_handle h, const double *actions_dev /*[n][S]*/, double *obs_dev /*[n][S][H*F]*/,
+                   double *reward_dev /*[n][S]*/, uint8_t *done_dev /*[n]*/, int32_t *counts_dev /*[n][S][3], optional*/,
+                   void *stream);
+int pcc_multi_check(pcc_multi_handle h, void *stream);
+
 const char *pcc_last_error(void);
 int pcc_abi_version(void);
 

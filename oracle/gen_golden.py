@@ -124,6 +124,55 @@ def gen_philox(ns, name, seed, params, n_steps, actions, history_len=10,
           features=features, steps_per_episode=n_steps)
 
 
+def gen_multi(ns, name, seed, bw, lat, queue, loss, rates, n_steps, actions):
+    """Several senders on one bottleneck: the reference's Network/Link/Sender classes with the external
+    patch Sender.__lt__ = id order and the env glue of network_sim.py:406-484 per sender."""
+    S = len(rates)
+    feats = DEFAULT_FEATURES.split(",")
+    real_random, had_lt = ns.random, getattr(ns.Sender, "__lt__", None)
+    ns.Sender.__lt__ = lambda a, b: a.id < b.id
+    ns.random = rh.StreamShim([PhiloxStream(seed)])
+    try:
+        with rh.quiet_tmp_cwd():
+            links = [ns.Link(bw, lat, queue, loss), ns.Link(bw, lat, queue, loss)]
+            senders = [ns.Sender(r, [links[0], links[1]], 0, feats, history_len=10) for r in rates]
+            run_dur = 3 * lat
+            net = ns.Network(senders, links)
+            net.run_for_dur(run_dur)
+            net.run_for_dur(run_dur)
+            obs_l, rew_l, cnt_l, ct_l, rd_l = [], [], [], [], []
+            cur0 = net.cur_time
+            for t in range(n_steps):
+                for s_, a in zip(senders, actions[t]):
+                    s_.apply_rate_delta(float(a))
+                net.run_for_dur(run_dur)
+                o_t, r_t, c_t = [], [], []
+                for i, s_ in enumerate(senders):
+                    s_.record_run()
+                    o_t.append(np.array(s_.get_obs()).reshape(-1))
+                    mi = s_.get_run_data()
+                    r_t.append((10.0 * mi.get("recv rate") / (8 * 1500) - 1e3 * mi.get("avg latency")
+                                - 2e3 * mi.get("loss ratio")) * 0.001)
+                    if i == 0:
+                        avg0 = mi.get("avg latency")
+                    mi.get("latency ratio")
+                    c_t.append((s_.sent, s_.acked, s_.lost))
+                if avg0 > 0.0:
+                    run_dur = 0.5 * avg0
+                obs_l.append(o_t); rew_l.append(r_t); cnt_l.append(c_t); ct_l.append(net.cur_time); rd_l.append(run_dur)
+    finally:
+        ns.random = real_random
+        if had_lt is None:
+            del ns.Sender.__lt__
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "multi_" + name + ".npz"), seed=np.array(seed), rng=np.array("philox"),
+                        params=np.array([bw, lat, float(queue), loss]), rates=np.array(rates),
+                        action=np.array(actions), obs=np.array(obs_l), reward=np.array(rew_l),
+                        counts=np.array(cnt_l, dtype=np.int64), cur_time=np.array(ct_l), run_dur=np.array(rd_l),
+                        cur_time0=np.array(cur0))
+    print("wrote multi_%s: %d steps x %d senders" % (name, n_steps, S))
+
+
 def main():
     ns = rh.load_reference()
     # --- the reference exactly as shipped (global MT19937 stream) ---
@@ -147,6 +196,13 @@ def main():
                features="send rate,recv rate,avg latency,loss ratio")
     gen_philox(ns, "highbw_idle", 20, [(83333.0, 0.001, 1000, 0.0, 0.01)], 100, acts(100, 2.0))
     gen_philox(ns, "bigseed", 0xFEDCBA9876543210, [(333.0, 0.07, 6, 0.05, 1.3)], 60, acts(60, 2.0))
+    # --- BASELINE config 5: two (three) senders per link, points of the bw x delay grid ---
+    macts = lambda n, S, s=2.0: [[g.gauss(0.0, s) for _ in range(S)] for _ in range(n)]
+    gen_multi(ns, "2s_lowbw", 31, 83.3, 0.05, 10, 0.0, [120.0, 60.0], 100, macts(100, 2))
+    gen_multi(ns, "2s_midbw_loss", 32, 833.0, 0.02, 30, 0.02, [500.0, 700.0], 100, macts(100, 2))
+    gen_multi(ns, "2s_highbw_shortlat", 33, 83333.0, 0.001, 100, 0.0, [900.0, 40.0], 100, macts(100, 2))
+    gen_multi(ns, "2s_longlat", 34, 400.0, 0.5, 5, 0.01, [300.0, 300.0], 60, macts(60, 2))
+    gen_multi(ns, "3s_tinyqueue", 35, 200.0, 0.03, 2, 0.05, [150.0, 150.0, 150.0], 80, macts(80, 3))
 
 
 if __name__ == "__main__":

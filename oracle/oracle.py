@@ -68,6 +68,8 @@ def lib():
     L.pcco_queue_len.argtypes = [vp]
     L.pcco_total_events.restype = C.c_longlong
     L.pcco_total_events.argtypes = [vp]
+    L.pcco_reset_multi.argtypes = [vp, i, d, d, l, d, pd]
+    L.pcco_step_multi.argtypes = [vp, pd, pd, pd, pi, pl]
     L.pcco_np_mean.restype = d
     L.pcco_np_mean.argtypes = [pd, l]
     L.pcco_batch_run.restype = d
@@ -150,6 +152,23 @@ class OracleEnv(object):
         self.L.pcco_step(self.h, float(action), _p(self._obs, C.c_double), C.byref(r), C.byref(dn),
                          _p(self._counts, C.c_long), _p(self._info, C.c_double))
         return self._obs.copy(), r.value, bool(dn.value), self._counts.copy(), self._info.copy()
+
+    # -- several senders on one bottleneck (config 5) --
+    def reset_multi(self, bw, lat, queue, loss, start_rates):
+        r = np.ascontiguousarray(start_rates, dtype=np.float64)
+        self.n_senders = len(r)
+        self.L.pcco_reset_multi(self.h, len(r), bw, lat, int(queue), loss, _p(r, C.c_double))
+
+    def step_multi(self, actions):
+        S = self.n_senders
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        obs = np.zeros((S, self.history_len * self.n_features))
+        rew = np.zeros(S)
+        cnt = np.zeros((S, 3), dtype=np.int64)
+        dn = C.c_int()
+        self.L.pcco_step_multi(self.h, _p(a, C.c_double), _p(obs, C.c_double), _p(rew, C.c_double), C.byref(dn),
+                               _p(cnt, C.c_long))
+        return obs, rew, bool(dn.value), cnt
 
     @property
     def cur_time(self):

@@ -661,3 +661,77 @@ double pcco_run_dur(const pcco_env *e) { return e->run_dur; }
 double pcco_rate(const pcco_env *e) { return e->senders[0].rate; }
 long pcco_queue_len(const pcco_env *e) { return e->q.n; }
 long long pcco_total_events(const pcco_env *e) { return e->total_events; }
+
+/* ------------------------------------------------------------------------------------ */
+/* Several senders on the same two links (BASELINE config 5).              */
+/* The reference's Network handles lists of senders (network_sim.py:100-126, 140-178);   */
+/* its env only ever creates one.  Semantics fixed here (and pinned against the reference */
+/* classes with the external patch Sender.__lt__ = id order, tests/test_oracle_multi.py): */
+/*   - all senders share links [l0, l1] (one shared bottleneck queue), dest = 0;          */
+/*   - heap ties are broken by sender index (position 2 of the event tuple);              */
+/*   - step(actions[S]) applies actions[i] to sender i (network_sim.py:409-412 generalised),*/
+/*     reward i uses sender i's own MI with the formula of :194,205, every sender records */
+/*     its MI, run_dur follows sender 0's average latency (:437-438 as written);          */
+/*   - one uniform draw per sent packet from the env's single stream, in event order.     */
+/* ------------------------------------------------------------------------------------ */
+static double reward_of(const pcco_mi *m)
+{
+    double throughput = mi_recv_rate(m), latency = mi_avg_latency(m), loss = mi_loss_ratio(m);
+    double reward = (10.0 * throughput / (8 * BYTES_PER_PACKET) - 1e3 * latency - 2e3 * loss);
+    return reward * REWARD_SCALE;
+}
+
+void pcco_reset_multi(pcco_env *e, int n_senders, double bw, double lat, long queue_size, double loss,
+                      const double *start_rates)
+{
+    link_init(&e->links[0], bw, lat, queue_size, loss);
+    link_init(&e->links[1], bw, lat, queue_size, loss);
+    e->n_senders = n_senders;
+    e->run_dur = 3 * lat;
+    e->q.n = 0;
+    e->cur_time = 0.0;
+    for (int i = 0; i < n_senders; i++) {
+        pcco_sender *s = &e->senders[i];
+        s->rate = start_rates[i]; s->starting_rate = start_rates[i];
+        s->has_min = 0; s->conn_min = 0.0;
+        for (int h = 0; h < e->history_len; h++)
+            for (int f = 0; f < e->n_features; f++) {
+                int id = e->feature_ids[f];
+                s->hist[h].v[f] = metric_empty[id] / metric_scale[id];
+            }
+        sender_reset_obs(e, s);                               /* queue_initial_packets :107-111 */
+        pcco_event first = {1.0 / s->rate, i, 1, 0, 0.0, 0};
+        heap_push(&e->q, first);
+    }
+    e->steps_taken = 0;
+    run_for_dur(e, e->run_dur);
+    run_for_dur(e, e->run_dur);
+}
+
+/* obs [S][H*F], rewards [S], counts [S][3] */
+void pcco_step_multi(pcco_env *e, const double *actions, double *obs, double *rewards, int *done, long *counts)
+{
+    const int hf = e->history_len * e->n_features;
+    for (int i = 0; i < e->n_senders; i++) sender_apply_rate_delta(&e->senders[i], actions[i]);
+    run_for_dur(e, e->run_dur);
+    double avg0 = 0.0;
+    for (int i = 0; i < e->n_senders; i++) {
+        pcco_sender *s = &e->senders[i];
+        pcco_mi m = sender_get_run_data(e, s);
+        rewards[i] = reward_of(&m);
+        for (int h = 0; h + 1 < e->history_len; h++) s->hist[h] = s->hist[h + 1];
+        pcco_mi_row *row = &s->hist[e->history_len - 1];
+        for (int f = 0; f < e->n_features; f++) {
+            int id = e->feature_ids[f];
+            row->v[f] = mi_metric(&m, s, id) / metric_scale[id];
+        }
+        (void)mi_latency_ratio(&m, s);   /* event record of step(): touches the conn-min entry (idempotent) */
+        for (int h = 0; h < e->history_len; h++)
+            for (int f = 0; f < e->n_features; f++) obs[i * hf + h * e->n_features + f] = s->hist[h].v[f];
+        if (counts) { counts[3 * i] = s->sent; counts[3 * i + 1] = s->acked; counts[3 * i + 2] = s->lost; }
+        if (i == 0) avg0 = mi_avg_latency(&m);
+    }
+    e->steps_taken += 1;
+    if (avg0 > 0.0) e->run_dur = 0.5 * avg0;
+    *done = (e->steps_taken >= e->max_steps);
+}

@@ -6,6 +6,7 @@ from . import build as build_mod
 from . import _lib, sender_obs, params
 from .params import LinkRanges, sample_link_params
 from .batch_env import PccBatchEnv
+from .multi_env import PccMultiSenderEnv, grid_sweep_params
 
 
 def build(force=False, verbose=False):

@@ -40,7 +40,8 @@ class PccError(RuntimeError):
 EXPORTS = ["pcc_default_consts", "pcc_default_config", "pcc_ring_capacity_for", "pcc_workspace_bytes",
            "pcc_create", "pcc_destroy", "pcc_attach", "pcc_seed", "pcc_get_mt_state", "pcc_set_mt_state",
            "pcc_reset", "pcc_step", "pcc_step_host", "pcc_rollout", "pcc_check", "pcc_get_column", "pcc_launch_count",
-           "pcc_last_error", "pcc_abi_version"]
+           "pcc_last_error", "pcc_abi_version", "pcc_multi_workspace_bytes", "pcc_multi_create", "pcc_multi_destroy",
+           "pcc_multi_seed", "pcc_multi_reset", "pcc_multi_step", "pcc_multi_check"]
 
 _lib = None
 
@@ -81,6 +82,14 @@ def load(rebuild_if_stale=True):
     L.pcc_step_host.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
     L.pcc_rollout.argtypes = [vp, C.c_int32, dp, C.POINTER(PccPolicy), dp, C.c_int32, dp, dp, dp, u8p, vp, vp]
     L.pcc_check.argtypes = [vp, vp]
+    L.pcc_multi_workspace_bytes.argtypes = [C.POINTER(PccConfig), C.c_int32, C.POINTER(C.c_uint64)]
+    L.pcc_multi_create.argtypes = [C.POINTER(vp), C.POINTER(PccConfig), C.c_int32, vp]
+    L.pcc_multi_destroy.argtypes = [vp]
+    L.pcc_multi_destroy.restype = None
+    L.pcc_multi_seed.argtypes = [vp, vp, vp]
+    L.pcc_multi_reset.argtypes = [vp, u8p, dp, dp, vp, dp, dp, dp, vp]
+    L.pcc_multi_step.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
+    L.pcc_multi_check.argtypes = [vp, vp]
     L.pcc_get_column.argtypes = [vp, C.c_char_p, dp, vp]
     L.pcc_launch_count.argtypes = [vp]
     L.pcc_launch_count.restype = C.c_int64

@@ -24,6 +24,7 @@
 #include "pcc_core.cuh"
 #include "pcc_coop.cuh"
 #include "pcc_warp.cuh"
+#include "pcc_multi_core.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -1470,5 +1471,226 @@ int pcc_get_column(pcc_handle h, const char *name, double *dst_dev, void *stream
 }
 
 int64_t pcc_launch_count(pcc_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+// =======================================================================================
+// Several senders per link (BASELINE config 5): generic heap simulator, one env per thread.
+// Workspace per env: MEnv header, hist[S][H][F], heap[heap_cap] events, samples[S][cap_s].
+// =======================================================================================
+struct MEnv {
+    MNet net;
+    MSender snd[PCC_MAX_SENDERS];
+    unsigned long long seed, draws;
+};
+struct MultiDev {
+    MEnv *envs;
+    double *hist;        // [n][S][H][F], per env a ring over H slots (handle-global head)
+    MEvent *heaps;       // [n][heap_cap]
+    double *samples;     // [n][S][cap_s]
+    unsigned long long *meta;   // [1] = overflow count
+    int64_t n;
+    int32_t S, H, F, heap_cap, cap_s;
+    int32_t ids[PCC_MAX_FEATURES];
+    int32_t need_inc;
+    Consts c;
+};
+struct DevHeap {
+    MEvent *base; int cap;
+    __device__ __forceinline__ int capacity() const { return cap; }
+    __device__ __forceinline__ MEvent get(int i) const { return base[i]; }
+    __device__ __forceinline__ void set(int i, const MEvent &e) { base[i] = e; }
+};
+
+__global__ void pcc_multi_reset_kernel(MultiDev p, const uint8_t *__restrict__ mask, const double *__restrict__ bw,
+                                       const double *__restrict__ delay, const long long *__restrict__ queue,
+                                       const double *__restrict__ loss, const double *__restrict__ rates,
+                                       double *__restrict__ obs)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n || (mask && !mask[e])) return;
+    MEnv &me = p.envs[e];
+    MNet net = me.net;
+    MSender snd[PCC_MAX_SENDERS];
+    PhiloxRng rng;
+    rng.init(me.seed, me.draws);
+    DevHeap heap{p.heaps + (size_t)e * p.heap_cap, p.heap_cap};
+    double r[PCC_MAX_SENDERS];
+    for (int i = 0; i < p.S; i++) r[i] = rates[(size_t)e * p.S + i];
+    const bool ok = multi_reset(net, snd, p.S, heap, p.samples + (size_t)e * p.S * p.cap_s, p.cap_s, rng, bw[e], delay[e],
+                                (int64_t)queue[e], loss[e], r);
+    me.net = net;
+    for (int i = 0; i < p.S; i++) me.snd[i] = snd[i];
+    me.draws = rng.draws;
+    if (!ok) atomicAdd(&p.meta[1], 1ull);
+    const int HF = p.H * p.F;
+    for (int i = 0; i < p.S; i++)
+        for (int k = 0; k < HF; k++) {
+            const double v = metric_empty(p.ids[k % p.F]);
+            p.hist[((size_t)e * p.S + i) * HF + k] = v;
+            if (obs) obs[((size_t)e * p.S + i) * HF + k] = v;
+        }
+}
+
+__global__ void pcc_multi_step_kernel(MultiDev p, unsigned long long head_step, const double *__restrict__ actions,
+                                      double *__restrict__ obs, double *__restrict__ reward, uint8_t *__restrict__ done,
+                                      int32_t *__restrict__ counts)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    MEnv &me = p.envs[e];
+    MNet net = me.net;
+    MSender snd[PCC_MAX_SENDERS];
+    for (int i = 0; i < p.S; i++) snd[i] = me.snd[i];
+    PhiloxRng rng;
+    rng.init(me.seed, me.draws);
+    DevHeap heap{p.heaps + (size_t)e * p.heap_cap, p.heap_cap};
+    double acts[PCC_MAX_SENDERS], rows[PCC_MAX_SENDERS * PCC_MAX_FEATURES], rew[PCC_MAX_SENDERS];
+    int32_t cnt[PCC_MAX_SENDERS * 3];
+    for (int i = 0; i < p.S; i++) acts[i] = actions[(size_t)e * p.S + i];
+    bool dn;
+    const bool ok = multi_step(net, snd, p.S, heap, p.samples + (size_t)e * p.S * p.cap_s, p.cap_s, rng, acts, p.c, p.ids,
+                               p.F, p.need_inc != 0, rows, rew, cnt, dn);
+    me.net = net;
+    for (int i = 0; i < p.S; i++) me.snd[i] = snd[i];
+    me.draws = rng.draws;
+    if (!ok) atomicAdd(&p.meta[1], 1ull);
+    const int H = p.H, F = p.F, HF = H * F;
+    const int slot_new = (int)(head_step % (unsigned long long)H);
+    for (int i = 0; i < p.S; i++) {
+        double *hrow = p.hist + ((size_t)e * p.S + i) * HF;
+        double *ob = obs + ((size_t)e * p.S + i) * HF;
+        for (int f = 0; f < F; f++) hrow[slot_new * F + f] = rows[i * F + f];
+        for (int h = 0; h < H; h++) {
+            int sl = slot_new + 1 + h;
+            if (sl >= H) sl -= H;
+            for (int f = 0; f < F; f++) ob[h * F + f] = hrow[sl * F + f];
+        }
+        reward[(size_t)e * p.S + i] = rew[i];
+        if (counts) for (int k = 0; k < 3; k++) counts[((size_t)e * p.S + i) * 3 + k] = cnt[3 * i + k];
+    }
+    done[e] = dn ? 1 : 0;
+}
+
+__global__ void pcc_multi_seed_kernel(MultiDev p, const unsigned long long *__restrict__ seeds)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    p.envs[e].seed = seeds[e];
+    p.envs[e].draws = 0ull;
+}
+
+struct pcc_multi_handle_s {
+    pcc_config cfg;
+    MultiDev d;
+    unsigned long long head;
+};
+
+static void multi_layout(const pcc_config *cfg, int S, size_t off[5], size_t &total)
+{
+    const size_t n = (size_t)cfg->n_envs, HF = (size_t)cfg->history_len * cfg->n_features;
+    size_t o = 0;
+    off[0] = o; o = align_up(o + n * sizeof(MEnv));
+    off[1] = o; o = align_up(o + n * S * HF * 8);
+    off[2] = o; o = align_up(o + n * (size_t)S * (size_t)cfg->ring_capacity * sizeof(MEvent));
+    off[3] = o; o = align_up(o + n * (size_t)S * (size_t)cfg->ring_capacity * 8);
+    off[4] = o; o = align_up(o + 64);
+    total = o;
+}
+
+extern "C" {
+
+int pcc_multi_workspace_bytes(const pcc_config *cfg, int32_t n_senders, uint64_t *bytes)
+{
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (n_senders < 1 || n_senders > PCC_MAX_SENDERS) return fail(PCC_EINVAL, "n_senders out of range (1..4)");
+    size_t off[5], total;
+    multi_layout(cfg, n_senders, off, total);
+    if (bytes) *bytes = total;
+    return PCC_OK;
+}
+
+int pcc_multi_create(pcc_multi_handle *out, const pcc_config *cfg, int32_t n_senders, void *workspace_dev)
+{
+    uint64_t bytes = 0;
+    int rc = pcc_multi_workspace_bytes(cfg, n_senders, &bytes);
+    if (rc) return rc;
+    if (!out || !workspace_dev || ((uintptr_t)workspace_dev & 255)) return fail(PCC_EINVAL, "bad workspace pointer");
+    if (cfg->rng_kind != PCC_RNG_PHILOX) return fail(PCC_EINVAL, "the multi-sender path supports Philox streams only");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(PCC_ENODEV, "no CUDA device: libpcc_b200 has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    pcc_multi_handle h = new (std::nothrow) pcc_multi_handle_s();
+    if (!h) return fail(PCC_EINVAL, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    size_t off[5], total;
+    multi_layout(cfg, n_senders, off, total);
+    char *b = (char *)workspace_dev;
+    MultiDev &d = h->d;
+    d.envs = (MEnv *)(b + off[0]); d.hist = (double *)(b + off[1]); d.heaps = (MEvent *)(b + off[2]);
+    d.samples = (double *)(b + off[3]); d.meta = (unsigned long long *)(b + off[4]);
+    d.n = cfg->n_envs; d.S = n_senders; d.H = cfg->history_len; d.F = cfg->n_features;
+    d.heap_cap = (int32_t)(cfg->ring_capacity * n_senders); d.cap_s = (int32_t)cfg->ring_capacity;
+    for (int i = 0; i < PCC_MAX_FEATURES; i++) d.ids[i] = i < cfg->n_features ? cfg->feature_ids[i] : 0;
+    d.need_inc = features_need_increase(d.ids, d.F) ? 1 : 0;
+    d.c.max_rate = cfg->consts.max_rate; d.c.min_rate = cfg->consts.min_rate; d.c.delta_scale = cfg->consts.delta_scale;
+    d.c.reward_scale = cfg->consts.reward_scale; d.c.max_steps = cfg->consts.max_steps;
+    d.c.bytes_per_packet = cfg->consts.bytes_per_packet;
+    cudaError_t e = cudaMemset(b + off[0], 0, off[1] - off[0]);
+    if (e == cudaSuccess) e = cudaMemset(b + off[4], 0, 64);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "multi init: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return PCC_OK;
+}
+
+void pcc_multi_destroy(pcc_multi_handle h) { delete h; }
+
+int pcc_multi_seed(pcc_multi_handle h, const uint64_t *seeds_dev, void *stream)
+{
+    if (!h || !seeds_dev) return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    pcc_multi_seed_kernel<<<(unsigned)((h->d.n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d, (const unsigned long long *)seeds_dev);
+    CUDA_TRY(cudaGetLastError());
+    return PCC_OK;
+}
+
+int pcc_multi_reset(pcc_multi_handle h, const uint8_t *mask_dev, const double *bw_dev, const double *delay_dev,
+                    const int64_t *queue_dev, const double *loss_dev, const double *start_rates_dev, double *obs_dev,
+                    void *stream)
+{
+    if (!h || !bw_dev || !delay_dev || !queue_dev || !loss_dev || !start_rates_dev) return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    pcc_multi_reset_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
+        h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rates_dev, obs_dev);
+    CUDA_TRY(cudaGetLastError());
+    return PCC_OK;
+}
+
+int pcc_multi_step(pcc_multi_handle h, const double *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev,
+                   int32_t *counts_dev, void *stream)
+{
+    if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    pcc_multi_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
+        h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev);
+    h->head++;
+    CUDA_TRY(cudaGetLastError());
+    return PCC_OK;
+}
+
+int pcc_multi_check(pcc_multi_handle h, void *stream)
+{
+    if (!h) return fail(PCC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned long long meta[2];
+    CUDA_TRY(cudaMemcpy(meta, h->d.meta, sizeof(meta), cudaMemcpyDeviceToHost));
+    if (meta[1]) return fail(PCC_EOVERFLOW, "event heap / sample buffer overflow: ring_capacity too small for these link parameters");
+    return PCC_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,99 @@
+"""PccMultiSenderEnv: N independent links, each shared by S senders (BASELINE config 5: the bw x delay grid
+sweep with 2 senders per link).  Batched counterpart of driving the reference's Network with several Sender
+objects (gym/network_sim.py:100-178); semantics in include/pcc_b200.h / DESIGN.md.  Exact, not fast: one env
+per thread with a per-env event heap."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, sender_obs
+
+
+def grid_sweep_params(bw_mbps=(1.0, 1000.0), lat_ms=(1.0, 500.0), n_bw=32, n_lat=32, queue=50, loss=0.0,
+                      bytes_per_packet=1500):
+    """Log-spaced grid of the sweep; bandwidth in the reference's unit (packets/s of 1500 B)."""
+    bw = np.exp(np.linspace(np.log(bw_mbps[0]), np.log(bw_mbps[1]), n_bw)) * 1e6 / (8 * bytes_per_packet)
+    lat = np.exp(np.linspace(np.log(lat_ms[0]), np.log(lat_ms[1]), n_lat)) * 1e-3
+    B, Lm = np.meshgrid(bw, lat, indexing="ij")
+    n = B.size
+    return dict(bw=B.reshape(-1), lat=Lm.reshape(-1), queue=np.full(n, int(queue), dtype=np.int64),
+                loss=np.full(n, float(loss)))
+
+
+class PccMultiSenderEnv(object):
+    def __init__(self, n_envs, n_senders=2, history_len=10, features=sender_obs.DEFAULT_FEATURES, device=None, seed=0,
+                 ring_capacity=8192, max_steps=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("pcc_rl_b200 needs a CUDA device; there is no CPU fallback")
+        self.torch, self.L = torch, _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.n_envs, self.S = int(n_envs), int(n_senders)
+        self.feature_ids = sender_obs.feature_ids(features)
+        self.obs_dim = history_len * len(self.feature_ids)
+        cfg = _lib.PccConfig()
+        self.L.pcc_default_config(C.byref(cfg))
+        cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        cfg.n_envs, cfg.history_len, cfg.n_features = self.n_envs, history_len, len(self.feature_ids)
+        for i, fid in enumerate(self.feature_ids):
+            cfg.feature_ids[i] = fid
+        cfg.ring_capacity = int(ring_capacity)
+        if max_steps is not None:
+            cfg.consts.max_steps = int(max_steps)
+        self.cfg = cfg
+        nb = C.c_uint64()
+        _lib.check(self.L.pcc_multi_workspace_bytes(C.byref(cfg), self.S, C.byref(nb)))
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+            self.h = C.c_void_p()
+            _lib.check(self.L.pcc_multi_create(C.byref(self.h), C.byref(cfg), self.S, self.ws.data_ptr()))
+            f64 = dict(dtype=torch.float64, device=self.device)
+            self.obs = torch.empty((self.n_envs, self.S, self.obs_dim), **f64)
+            self.reward = torch.empty((self.n_envs, self.S), **f64)
+            self.done = torch.empty(self.n_envs, dtype=torch.uint8, device=self.device)
+            self.counts = torch.empty((self.n_envs, self.S, 3), dtype=torch.int32, device=self.device)
+        self.seed(seed)
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pcc_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, seed=0, seeds=None):
+        if seeds is None:
+            seeds = np.uint64(int(seed) & 0xFFFFFFFFFFFFFFFF) + np.arange(self.n_envs, dtype=np.uint64)
+        t = self.torch.from_numpy(np.ascontiguousarray(seeds, dtype=np.uint64).view(np.int64)).to(self.device)
+        _lib.check(self.L.pcc_multi_seed(self.h, t.data_ptr(), self._stream()))
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def reset(self, params, start_rates):
+        """params: dict bw, lat, queue, loss (length n_envs); start_rates: [n_envs, n_senders] packets/s."""
+        torch = self.torch
+        dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(self.device)
+        bw, lat, loss = (dev(params[k], torch.float64) for k in ("bw", "lat", "loss"))
+        q = dev(params["queue"], torch.int64)
+        r = dev(np.asarray(start_rates, dtype=np.float64).reshape(self.n_envs, self.S), torch.float64)
+        _lib.check(self.L.pcc_multi_reset(self.h, None, bw.data_ptr(), lat.data_ptr(), q.data_ptr(), loss.data_ptr(),
+                                          r.data_ptr(), self.obs.data_ptr(), self._stream()))
+        self._keep = (bw, lat, loss, q, r)
+        return self.obs
+
+    def step(self, actions):
+        torch = self.torch
+        a = torch.as_tensor(actions).to(self.device, torch.float64).reshape(self.n_envs, self.S).contiguous()
+        _lib.check(self.L.pcc_multi_step(self.h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+                                         self.done.data_ptr(), self.counts.data_ptr(), self._stream()))
+        self._keep_a = a
+        return self.obs, self.reward, self.done.bool(), {"counts": self.counts}
+
+    def check(self):
+        _lib.check(self.L.pcc_multi_check(self.h, self._stream()))

@@ -1,0 +1,54 @@
+"""-m gpu: BASELINE config 5 -- link-parameter grid sweep (bw 1-1000 Mbit/s x delay 1-500 ms), two senders per
+link -- the CUDA multi-sender path against the reference's golden outputs and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from golden_util import GOLDEN_DIR, golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_names("multi_"))
+def test_cuda_multi_sender_matches_reference_golden(name):
+    import pcc_rl_b200
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    bw, lat, queue, loss = z["params"]
+    S = len(z["rates"])
+    env = pcc_rl_b200.PccMultiSenderEnv(1, n_senders=S, ring_capacity=1 << 15)
+    env.seed(seeds=np.array([int(z["seed"])], dtype=np.uint64))
+    env.reset(dict(bw=[bw], lat=[lat], queue=[int(queue)], loss=[loss]), z["rates"][None, :])
+    for t in range(len(z["action"])):
+        obs, rew, done, info = env.step(z["action"][t][None, :])
+        assert np.array_equal(info["counts"].cpu().numpy()[0], z["counts"][t]), (name, t)
+        assert np.array_equal(obs.cpu().numpy()[0], z["obs"][t]) and np.array_equal(rew.cpu().numpy()[0], z["reward"][t])
+    env.check()
+
+
+def test_cuda_config5_grid_sweep_vs_oracle():
+    """32 x 32 grid of (bandwidth, delay), 2 senders per link, 60 steps: every grid point against the oracle."""
+    import pcc_rl_b200
+    p = pcc_rl_b200.grid_sweep_params(n_bw=32, n_lat=32, queue=40, loss=0.01)
+    n, S, steps = 1024, 2, 60
+    g = np.random.default_rng(7)
+    rates = g.uniform(40, 1000, (n, S))
+    env = pcc_rl_b200.PccMultiSenderEnv(n, n_senders=S, seed=500, ring_capacity=1 << 13)
+    env.reset(p, rates)
+    orcs = []
+    for i in range(n):
+        o = oracle.OracleEnv()
+        o.seed_philox(500 + i)
+        o.reset_multi(p["bw"][i], p["lat"][i], int(p["queue"][i]), p["loss"][i], rates[i])
+        orcs.append(o)
+    for t in range(steps):
+        a = g.normal(0, 2.0, (n, S))
+        obs, rew, done, info = env.step(a)
+        obs_h, rew_h, cnt_h = obs.cpu().numpy(), rew.cpu().numpy(), info["counts"].cpu().numpy()
+        for i in range(n):
+            o_obs, o_rew, o_done, o_cnt = orcs[i].step_multi(a[i])
+            assert np.array_equal(o_cnt, cnt_h[i]), (t, i)
+            assert np.array_equal(o_obs, obs_h[i]) and np.array_equal(o_rew, rew_h[i]), (t, i)
+    env.check()
+    assert int(info["counts"][:, :, 0].min()) >= 0

@@ -1,0 +1,98 @@
+"""pcc_multi_core.cuh (several senders on one bottleneck, the product's generic heap path) compiled for the host,
+against the reference's golden outputs and against the oracle on random grid-sweep points."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import twin_util
+from golden_util import GOLDEN_DIR, golden_names
+
+
+def _lib():
+    L = twin_util.lib()
+    vp, d, i = C.c_void_p, C.c_double, C.c_int
+    pd = C.POINTER(C.c_double)
+    L.twin_multi_create.restype = vp
+    L.twin_multi_create.argtypes = [i, i, C.POINTER(C.c_int), i, i]
+    L.twin_multi_destroy.argtypes = [vp]
+    L.twin_multi_seed.argtypes = [vp, C.c_uint64]
+    L.twin_multi_reset.argtypes = [vp, d, d, C.c_int64, d, pd]
+    L.twin_multi_step.argtypes = [vp, pd, pd, pd, C.POINTER(i), C.POINTER(C.c_int32)]
+    for n in ("twin_multi_cur_time", "twin_multi_run_dur"):
+        getattr(L, n).restype = d
+        getattr(L, n).argtypes = [vp]
+    L.twin_multi_ok.argtypes = [vp]
+    return L
+
+
+class TwinMulti(object):
+    def __init__(self, S, capacity=1 << 15):
+        self.L = _lib()
+        ids = np.asarray(oracle.feature_ids(), dtype=np.int32)
+        self.S = S
+        self.h = self.L.twin_multi_create(S, 10, ids.ctypes.data_as(C.POINTER(C.c_int)), len(ids), capacity)
+
+    def __del__(self):
+        self.L.twin_multi_destroy(self.h)
+
+    def reset(self, seed, bw, lat, queue, loss, rates):
+        self.L.twin_multi_seed(self.h, int(seed))
+        r = np.ascontiguousarray(rates, dtype=np.float64)
+        self.L.twin_multi_reset(self.h, bw, lat, int(queue), loss, r.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        obs = np.zeros((self.S, 30)); rew = np.zeros(self.S); cnt = np.zeros((self.S, 3), dtype=np.int32)
+        dn = C.c_int()
+        pd = C.POINTER(C.c_double)
+        self.L.twin_multi_step(self.h, a.ctypes.data_as(pd), obs.ctypes.data_as(pd), rew.ctypes.data_as(pd), C.byref(dn),
+                               cnt.ctypes.data_as(C.POINTER(C.c_int32)))
+        return obs, rew, bool(dn.value), cnt
+
+    cur_time = property(lambda self: self.L.twin_multi_cur_time(self.h))
+    run_dur = property(lambda self: self.L.twin_multi_run_dur(self.h))
+    ok = property(lambda self: bool(self.L.twin_multi_ok(self.h)))
+
+
+@pytest.mark.parametrize("name", golden_names("multi_"))
+def test_twin_multi_matches_reference_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    bw, lat, queue, loss = z["params"]
+    t = TwinMulti(len(z["rates"]))
+    t.reset(int(z["seed"]), bw, lat, int(queue), loss, z["rates"])
+    assert t.cur_time == float(z["cur_time0"])
+    for k in range(len(z["action"])):
+        obs, rew, done, cnt = t.step(z["action"][k])
+        assert np.array_equal(cnt, z["counts"][k]), (name, k)
+        assert np.array_equal(obs, z["obs"][k]) and np.array_equal(rew, z["reward"][k]), (name, k)
+        assert t.cur_time == z["cur_time"][k] and t.run_dur == z["run_dur"][k]
+    assert t.ok
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_twin_multi_equals_oracle_on_grid_points(seed):
+    g = np.random.default_rng(300 + seed)
+    for trial in range(3):
+        S = int(g.choice([2, 2, 3, 4]))
+        bw = float(np.exp(g.uniform(np.log(83.0), np.log(83333.0))))      # 1..1000 Mbit/s
+        lat = float(np.exp(g.uniform(np.log(0.001), np.log(0.5))))        # 1..500 ms
+        queue = 1 + int(np.exp(g.uniform(0, 6)))
+        loss = float(g.choice([0.0, 0.02, 0.3]))
+        rates = g.uniform(40, 1000, S)
+        o = oracle.OracleEnv()
+        o.seed_philox(seed)
+        o.reset_multi(bw, lat, queue, loss, rates)
+        t = TwinMulti(S)
+        t.reset(seed, bw, lat, queue, loss, rates)
+        assert o.cur_time == t.cur_time
+        for k in range(150):
+            a = g.normal(0, 2.5, S)
+            x = o.step_multi(a)
+            y = t.step(a)
+            assert np.array_equal(x[3], y[3]), (seed, trial, k)
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2], (seed, trial, k)
+            assert o.cur_time == t.cur_time and o.run_dur == t.run_dur
+        assert t.ok

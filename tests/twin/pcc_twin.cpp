@@ -96,3 +96,64 @@ uint32_t twin_inflight(Twin *t) { return t->s.tail - t->s.h2; }
 }
 
 extern "C" double twin_tail_drop_threshold(double d_bw, double max_qd) { return pcc::tail_drop_threshold(d_bw, max_qd); }
+
+// ---- several senders on one bottleneck (pcc_multi_core.cuh), host build -------------------------------------
+#include "../../pcc-rl_b200/csrc/pcc_multi_core.cuh"
+
+struct HostHeap {
+    std::vector<MEvent> *v;
+    int capacity() const { return (int)v->size(); }
+    MEvent get(int i) const { return (*v)[i]; }
+    void set(int i, const MEvent &e) { (*v)[i] = e; }
+};
+struct TwinMulti {
+    int S, H, F, cap_s; int ids[PCC_MAX_FEATURES]; bool need_inc;
+    Consts c; MNet net; MSender snd[PCC_MAX_SENDERS];
+    std::vector<MEvent> heap; std::vector<double> samples, hist;   // hist [S][H][F], oldest first
+    PhiloxRng ph; bool ok;
+};
+extern "C" {
+TwinMulti *twin_multi_create(int n_senders, int history_len, const int *feature_ids, int n_features, int capacity)
+{
+    TwinMulti *t = new TwinMulti();
+    t->S = n_senders; t->H = history_len; t->F = n_features; t->cap_s = capacity;
+    for (int i = 0; i < n_features; i++) t->ids[i] = feature_ids[i];
+    t->need_inc = features_need_increase(t->ids, t->F);
+    t->c.max_rate = 1000.0; t->c.min_rate = 40.0; t->c.delta_scale = 0.025; t->c.reward_scale = 0.001;
+    t->c.max_steps = 400; t->c.bytes_per_packet = 1500;
+    t->heap.resize((size_t)capacity * n_senders + 8);
+    t->samples.resize((size_t)capacity * n_senders);
+    t->hist.assign((size_t)n_senders * history_len * n_features, 0.0);
+    t->ph.init(0, 0); t->ok = true;
+    return t;
+}
+void twin_multi_destroy(TwinMulti *t) { delete t; }
+void twin_multi_seed(TwinMulti *t, uint64_t seed) { t->ph.init(seed, 0); }
+void twin_multi_reset(TwinMulti *t, double bw, double dl, int64_t queue, double lr, const double *rates)
+{
+    HostHeap hp{&t->heap};
+    t->ok = multi_reset(t->net, t->snd, t->S, hp, t->samples.data(), t->cap_s, t->ph, bw, dl, queue, lr, rates) && t->ok;
+    for (int i = 0; i < t->S; i++)
+        for (int h = 0; h < t->H; h++)
+            for (int f = 0; f < t->F; f++) t->hist[((size_t)i * t->H + h) * t->F + f] = metric_empty(t->ids[f]);
+}
+void twin_multi_step(TwinMulti *t, const double *actions, double *obs, double *rewards, int *done, int32_t *counts)
+{
+    HostHeap hp{&t->heap};
+    double rows[PCC_MAX_SENDERS * PCC_MAX_FEATURES];
+    bool dn;
+    t->ok = multi_step(t->net, t->snd, t->S, hp, t->samples.data(), t->cap_s, t->ph, actions, t->c, t->ids, t->F,
+                       t->need_inc, rows, rewards, counts, dn) && t->ok;
+    const size_t hf = (size_t)t->H * t->F;
+    for (int i = 0; i < t->S; i++) {
+        double *hs = t->hist.data() + i * hf;
+        memmove(hs, hs + t->F, sizeof(double) * (hf - t->F));
+        for (int f = 0; f < t->F; f++) hs[hf - t->F + f] = rows[i * t->F + f];
+    }
+    memcpy(obs, t->hist.data(), sizeof(double) * t->hist.size());
+    *done = dn;
+}
+double twin_multi_cur_time(TwinMulti *t) { return t->net.cur_time; }
+double twin_multi_run_dur(TwinMulti *t) { return t->net.run_dur; }
+int twin_multi_ok(TwinMulti *t) { return t->ok; }
+}
