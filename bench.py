@@ -36,6 +36,8 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     "config2": dict(envs=4096, desc="4 096 envs on 1xB200, link params sampled from ICML'19 ranges, history_len=10"),
     "config3": dict(envs=65536, desc="65 536 envs on 1xB200, per-reset randomized bw/lat/queue/loss, 1 sender per env"),
+    "config4": dict(envs=65536, desc="65 536 envs per GPU (524 288 on 8), PPO-style rollout end to end: on-device MLP policy "
+                                     "30-32-16-1 + env step fused (pcc_rollout, 64 MIs per launch), NCCL gather of episode returns"),
 }
 ACTION_SIGMA = 1.0   # a ~ N(0,1), BASELINE.md §3
 
@@ -160,6 +162,57 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def run_config4(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
+    """BASELINE config 4: K-step rollout (default 8 192 = PPO1's timesteps_per_actorbatch, stable_solve.py:52) with the
+    policy on the device; `value` = env-steps/s of the whole rollout incl. policy, auto-resets and the return gather."""
+    K, RK = args.steps, 64
+    env = pcc_rl_b200.PccBatchEnv(n_envs=n, device=dev, seed=args.seed, global_offset=rank * n, n_global=n_global)
+    env.reset()
+    g = torch.Generator(device=dev)
+    g.manual_seed(args.seed + 7)    # same random-init policy on every rank
+    r = lambda *sh, sc: torch.randn(*sh, generator=g, device=dev, dtype=torch.float64) * sc
+    pol = dict(w1=r(32, 30, sc=0.2), b1=r(32, sc=0.05), w2=r(16, 32, sc=0.2), b2=r(16, sc=0.05), w3=r(1, 16, sc=0.5),
+               b3=r(1, sc=0.05), stochastic=True, log_std=-0.7, noise_seed=args.seed + rank)
+    for _ in range(max(1, args.warmup // RK)):
+        env.rollout(RK, policy=pol, want_obs=False, want_counts=False)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = env.launches
+    t0 = time.perf_counter()
+    s.record()
+    finished, steps_done = [], 0
+    while steps_done < K:
+        k = min(RK, K - steps_done)
+        out = env.rollout(k, policy=pol, want_obs=False, want_counts=False)
+        steps_done += k
+        if bool(out["done"].any()):
+            finished.append(env.column("last_episode_return")[out["done"].any(0)])
+    e.record()
+    rets = torch.cat(finished) if finished else torch.zeros(0, dtype=torch.float64, device=dev)
+    stats = D.gather_episode_returns(rets)          # NCCL all-gather of [count, sum, sum^2]
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    wall = D.max_over_ranks(time.perf_counter() - t0, dev)
+    dev_ms = D.max_over_ranks(s.elapsed_time(e), dev)
+    env.check()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "env-steps/sec (batched MI sim)", "value": n_global * K / wall, "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * wall / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config4: " + WORKLOADS["config4"]["desc"], "envs_per_gpu": n, "global_envs": n_global,
+                       "policy": "random-init MLP 30-32-16-1 (tanh), stochastic", "steps_per_launch": RK},
+            "device_ms_per_step": dev_ms / K, "gpu_launches": int(env.launches - launches0),
+            "e2e": {"value": n_global * K / wall, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "closed loop on the device: nothing crosses PCIe per step"},
+            "episode_returns": {"count": stats["count"], "mean": stats["mean"]}}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,6 +230,10 @@ def main():
     n = args.envs or WORKLOADS[args.workload]["envs"]
     n_global = n * world
     K, W = args.steps, args.warmup
+
+    if args.workload == "config4":
+        run_config4(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global)
+        return
 
     def make_env():
         return pcc_rl_b200.PccBatchEnv(n_envs=n, device=dev, seed=args.seed, global_offset=rank * n,
