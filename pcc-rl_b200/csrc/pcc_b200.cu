@@ -794,7 +794,7 @@ pcc_send_kernel(DevState p, const int32_t *__restrict__ perm, int heavy_warps, c
 
 // ---- work-balanced partition (rebalance) -----------------------------------------------------
 // cost model of one env-MI in SM cycles: fixed cooperative overhead + per-packet work
-struct CostModel { float c0, c1; int32_t target_warps; float heavy_packets; };
+struct CostModel { float c0, c1; int32_t target_warps; float heavy_packets; int32_t max_envs; };
 
 __global__ void pcc_cost_kernel(DevState p, CostModel cm, uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
 {
@@ -834,7 +834,7 @@ __global__ void pcc_costfloor_kernel(const uint32_t *__restrict__ sorted_cost, i
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long t = target[0];
-    const unsigned long long fl = t / 32ull + 1ull;
+    const unsigned long long fl = t / (unsigned long long)cm.max_envs + 1ull;   // caps a warp at max_envs envs
     const unsigned long long c = sorted_cost[i];
     // an env expected to send more than heavy_packets gets a warp to itself (cost = T): its chain then
     // runs with 32-lane Philox support (114 cycles/packet measured) instead of stalling 31 co-tenants
@@ -1148,6 +1148,9 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         const char *c0 = getenv("PCC_B200_COST0"), *c1 = getenv("PCC_B200_COST1"), *tw = getenv("PCC_B200_TARGET_WARPS");
         h->cm.c0 = c0 ? (float)atof(c0) : 7000.0f;
         h->cm.c1 = c1 ? (float)atof(c1) : 60.0f;
+        const char *me = getenv("PCC_B200_MAX_ENVS");
+        h->cm.max_envs = me ? atoi(me) : (cfg->n_envs <= 16384 ? 8 : 32);   // small batches: short warps, the chip is not full anyway
+        if (h->cm.max_envs < 1 || h->cm.max_envs > 32) h->cm.max_envs = 32;
         const char *hp = getenv("PCC_B200_HEAVY");
         h->cm.heavy_packets = hp ? (float)atof(hp) : (cfg->n_envs <= 16384 ? 128.0f : 1024.0f);   // small batches: latency first
         h->cm.target_warps = tw ? atoi(tw) : 148 * 32;

@@ -119,7 +119,7 @@ __device__ __forceinline__ void window_argmin(const Grp<G> &g, bool cand, double
 // Per-group shared-memory scratch
 template <int G>
 struct GroupSmem {
-    double2 stage[2 * G];        // records of one send chunk
+    double2 stage[2 * G + 1];    // records of one send chunk (slot k + 1 = packet k)
     double buf[PCC_LEAF + ((G == 32) ? 4 : 1) * G];    // acked-latency staging for np.mean
 };
 
@@ -148,23 +148,56 @@ __device__ __forceinline__ void coop_send_chunks(const Grp<G> &g, bool alive, co
         if (g.gl == 0 && more) {
             if ((uint32_t)(tail - h2) + (uint32_t)navail > cap) { ovf = true; }   // fatal, reported by the host
             else {
-                double tt = t, q = qd, tu = t_upd;
+                // Measured on B200 (tools/chain_microbench.cu): the bare recurrence costs 42 cycles per packet;
+                // a data-dependent exit test adds 27 (DADD -> DSETP -> unpredicted branch every iteration), send
+                // times read back from shared memory add 35, the record store in the same iteration adds 25 --
+                // a lone warp issues in order, so everything that waits stalls the recurrence behind it.  Hence:
+                // (a) count-only pre-loop: how many send times t_k = fl(t_{k-1} + 1/rate) (:161) are < end
+                //     (skipped when the whole chunk provably fits: the recurrence drifts from t + k/rate by at most
+                //     k half-ulps, vastly less than the one extra 1/rate of margin)
+                double tt = t;
+                int cntk = 0;
+                if (t + (double)(navail + 1) * inv_rate < end) cntk = navail;
+                else {
+#pragma unroll 16
+                    for (int j = 0; j < 2 * G; ++j) {
+                        cntk += (j < navail && tt < end) ? 1 : 0;  // monotone: counts a prefix
+                        tt = tt + inv_rate;
+                    }
+                }
+                // (b) counted main loop: send time by recurrence, the queue recurrence (:66-84) in speculative form
+                //     (both candidates of q' from y = q - x before the selects), and the record of packet k-1
+                //     finished while packet k's recurrence is in flight (stage[k] = record of packet k-1)
+                const double k0 = (0.0 > s.w_full) ? 0.0 : s.d_bw;   // q' when the queue has drained (w = 0)
+                const bool full0 = 0.0 > s.w_full;
+                double q = qd, tu = t_upd;
+                double pw = 0.0, pt = 0.0;
+                bool pd = false;
+                tt = t;
 #pragma unroll 2
-                for (; k < navail; ++k) {
-                    if (!(tt < end)) break;
-                    const bool rdrop = (dm & 1ull) != 0ull;
+                for (; k < cntk; ++k) {
+                    const bool rdrop = (dm & 1ull) != 0ull;                    // :73
                     dm >>= 1;
-                    const long long yb = __double_as_longlong(q - (tt - tu));   // :66-67
-                    const double w = __longlong_as_double(yb & ~(yb >> 63));    // max(0.0, y)
-                    const double c = s.d_bw + w;                                // :82
-                    const bool full = w > s.w_full;                             // :77-79 (tail_drop_threshold)
-                    const double ll = s.dl + w;                                 // :69-70
-                    q = rdrop ? q : (full ? w : c);                             // :74-82
+                    const double y = q - (tt - tu);                            // :66-67
+                    const double pll = s.dl + pw;                              // :69-70 (previous packet)
+                    const double pls = __longlong_as_double(__double_as_longlong(pll) | (pd ? (long long)PCC_SIGN : 0ll));
+                    stage[k] = make_double2(pt + pll, pls);                    // :173-175 (previous packet)
+                    const double cpos = s.d_bw + y;                            // :82 if 0 < y <= w_full
+                    const bool pos = y > 0.0;
+                    const bool fullp = y > s.w_full;                           // :77-79 (tail_drop_threshold)
+                    const double w = pos ? y : 0.0;                            // max(0.0, y)
+                    double qn = fullp ? y : cpos;
+                    qn = pos ? qn : k0;
+                    const bool full = pos ? fullp : full0;
+                    q = rdrop ? q : qn;                                        // :74-82
                     tu = rdrop ? tu : tt;
-                    const bool dropped = rdrop || full;
-                    const double lsigned = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
-                    stage[k] = make_double2(tt + ll, lsigned);                  // :173-175
-                    tt = tt + inv_rate;                                         // :161
+                    pw = w; pt = tt; pd = rdrop || full;
+                    tt = tt + inv_rate;                                        // :161
+                }
+                if (cntk > 0) {
+                    const double pll = s.dl + pw;
+                    const double pls = __longlong_as_double(__double_as_longlong(pll) | (pd ? (long long)PCC_SIGN : 0ll));
+                    stage[cntk] = make_double2(pt + pll, pls);
                 }
                 t = tt; qd = q; t_upd = tu;
             }
@@ -173,7 +206,7 @@ __device__ __forceinline__ void coop_send_chunks(const Grp<G> &g, bool alive, co
         k = packed & 0xff;
         __syncwarp();
         for (int j = (int)g.gl; j < k; j += G) {
-            const double2 v = stage[j];
+            const double2 v = stage[j + 1];          // slot j + 1 holds packet j
             Rec r; r.a = v.x; r.l = v.y;
             ring.store(tail + (uint32_t)j, r);
         }

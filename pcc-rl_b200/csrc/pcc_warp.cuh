@@ -32,8 +32,8 @@ struct LeafScratch {
     int off[PCC_MAX_LEAVES];
     int cnt[PCC_MAX_LEAVES];
 };
-// ... followed by 64 double2 of record staging for the single-env send phase (coop_send_chunks<32>)
-__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch) + 64 * 16; }
+// ... followed by 65 (+1 pad) double2 of record staging for the single-env send phase (coop_send_chunks<32>)
+__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch) + 66 * 16; }
 
 struct ConsumeIn {
     double end, dl, tnext;
@@ -427,12 +427,16 @@ __device__ __forceinline__ void lane_send_one(LaneChain &c, const EnvState &s, R
                                               double inv_rate, double u)
 {
     const bool rdrop = u < s.lr;                                        // :73
-    const long long yb = __double_as_longlong(c.q - (c.t - c.tu));     // :66-67
-    const double w = __longlong_as_double(yb & ~(yb >> 63));            // max(0.0, y)
-    const double cc = s.d_bw + w;                                       // :77-79
-    const bool full = w > s.w_full;                                      // tail_drop_threshold
+    const double y = c.q - (c.t - c.tu);                                // :66-67
+    const double cpos = s.d_bw + y;                                     // :82 if 0 < y <= w_full
+    const bool pos = y > 0.0;
+    const bool fullp = y > s.w_full;                                    // :77-79 (tail_drop_threshold)
+    const double w = pos ? y : 0.0;                                     // max(0.0, y)
     const double ll = s.dl + w;                                         // :69-70
-    c.q = rdrop ? c.q : (full ? w : cc);                                // :74-82
+    double qn = fullp ? y : cpos;
+    qn = pos ? qn : ((0.0 > s.w_full) ? 0.0 : s.d_bw);
+    const bool full = pos ? fullp : (0.0 > s.w_full);
+    c.q = rdrop ? c.q : qn;                                             // :74-82
     c.tu = rdrop ? c.tu : c.t;
     const bool dropped = rdrop || full;
     Rec r;
