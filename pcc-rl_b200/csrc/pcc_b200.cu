@@ -59,6 +59,7 @@ struct DevState {
     uint32_t *mt;              // [n][625] or null
     unsigned long long *meta;  // [0] steps issued (history head), [1] overflow count, [2] first overflowed env + 1
     Rec *rings;                // [n][cap]
+    double *mean_scratch;      // [warps][PCC_GSCRATCH] acked-latency staging of heavy MIs (global), or null
     uint32_t cap;
     int64_t n;
     int32_t H, F;
@@ -319,6 +320,7 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
 // kernels (v4: a warp owns E envs, see pcc_warp.cuh) -- Philox streams only
 // ---------------------------------------------------------------------------------------
 #define PCC_WARP_THREADS 128
+#define PCC_GSCRATCH 4096   // samples of global staging per warp (MIs with more acks than the shared buffer)
 #ifndef PCC_STAGED_STORES
 #define PCC_STAGED_STORES 0   // 1: stage ring records in shared memory, coalesced copy-out (measured: no gain)
 #endif
@@ -331,7 +333,7 @@ template <bool WANT_MEANS, bool DO_SEND>
 __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, bool owner, int cnt, int64_t e, EnvState &s,
                                         PhiloxRng &rng, double dur, double *buf, int wbuf, WarpStage &stage, MiOut &mo,
                                         double &avg_lat, double &lat_inc, int32_t sent_before = 0,
-                                        long long *prof = nullptr)
+                                        long long *prof = nullptr, double *gscratch = nullptr)
 {
     const unsigned lane = g.gl;
     const double end = s.cur_time + dur;            // network_sim.py:124
@@ -400,19 +402,24 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
         in.tail = __shfl_sync(PCC_FULL, c.tail, j);
         in.h1 = __shfl_sync(PCC_FULL, s.h1, j);
         in.h2 = __shfl_sync(PCC_FULL, s.h2, j);
+        // staging of this MI's acked latencies: shared memory, or -- when more than wbuf packets could be acked
+        // (pending hop-2 events bound it) -- the warp's global scratch
+        double *sbuf_j = buf;
         in.wbuf = wbuf;
+        if (gscratch != nullptr && (uint32_t)(in.tail - in.h2) > (uint32_t)wbuf) { sbuf_j = gscratch; in.wbuf = PCC_GSCRATCH; }
 #ifdef PCC_PROFILE
         const long long tc0 = clock64();
 #endif
         const long long ej = __shfl_sync(PCC_FULL, (long long)e, j);
         DevRing rj{p.rings + (size_t)ej * p.cap, p.cap - 1u};
         ConsumeOut co;
-        consume_mi_warp(g, in, rj, buf, co);
+        consume_mi_warp(g, in, rj, sbuf_j, co);
         double a = 0.0, li = 0.0;
 #ifdef PCC_PROFILE
         const long long tc1 = clock64();
 #endif
-        if (WANT_MEANS) mi_means_warp(g, co, rj, in.dl, buf, wbuf, p.need_inc != 0, a, li);
+        if (WANT_MEANS) mi_means_warp(g, co, rj, in.dl, sbuf_j, in.wbuf, reinterpret_cast<LeafScratch *>(buf + wbuf + 32), buf,
+                                      p.need_inc != 0, a, li);
 #ifdef PCC_PROFILE
         if (prof && (int)lane == j) { prof[2] = tc1 - tc0; prof[3] = clock64() - tc1; }
 #endif
@@ -490,7 +497,8 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
 #endif
     warp_mi<true, !SPLIT>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf,
                           sstage[(SPLIT || !PCC_STAGED_STORES) ? 0 : (threadIdx.x >> 5)], o.mi, avg_lat, lat_inc,
-                          SPLIT ? sent_tmp[e] : 0, prof);                        // :416
+                          SPLIT ? sent_tmp[e] : 0, prof,
+                          p.mean_scratch ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : nullptr);   // :416
     if (!owner) return;
     mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
     s.steps += 1;                                                                // :419
@@ -666,7 +674,8 @@ pcc_rollout_kernel(DevState p, WarpPartition part, unsigned long long head0, Rol
         }
         StepOut o;
         double avg_lat, lat_inc;
-        warp_mi<true, true>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf, sstage[0], o.mi, avg_lat, lat_inc);   // :416
+        warp_mi<true, true>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf, sstage[0], o.mi, avg_lat, lat_inc, 0, nullptr,
+                            p.mean_scratch ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : nullptr);   // :416
         bool need_reset = false;
         if (owner) {
             mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
@@ -1113,9 +1122,11 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     if (cfg->rng_kind != PCC_RNG_PHILOX) { h->group = 0; h->epw = 0; }   // MT19937 (fidelity mode): scalar kernels
     {
         const char *wb = getenv("PCC_B200_WBUF");
-        h->wbuf = wb ? atoi(wb) : (small_batch ? 4096 : 2048);
+        h->wbuf = wb ? atoi(wb) : (small_batch ? 4096 : 512);   // big batches: small shared buffer -> 16 warps/SM; heavy MIs stage to global scratch
         if (h->wbuf < 128) h->wbuf = 128;
-        h->warp_threads = (h->wbuf > 1024) ? 64 : PCC_WARP_THREADS;
+        const char *wt = getenv("PCC_B200_WARP_THREADS");
+        h->warp_threads = wt ? atoi(wt) : ((h->wbuf > 1024) ? 64 : PCC_WARP_THREADS);
+        if (h->warp_threads != 32 && h->warp_threads != 64 && h->warp_threads != 128) h->warp_threads = 64;
         if (h->epw) {
             const size_t dyn = (size_t)(h->warp_threads / 32) * warp_smem_bytes(h->wbuf);
             cudaError_t ce = cudaFuncSetAttribute(pcc_step_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -1161,6 +1172,8 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         if (ce == cudaSuccess) ce = cudaMalloc(&h->starts, 4 * (n + 2));
         if (ce == cudaSuccess) ce = cudaMalloc(&h->n_warps, 4);
         if (ce == cudaSuccess) ce = cudaMalloc(&h->sent_tmp, 4 * n);
+        if (ce == cudaSuccess && h->wbuf < PCC_GSCRATCH && !getenv("PCC_B200_NO_GSCRATCH"))
+            ce = cudaMalloc(&h->d.mean_scratch, (size_t)n * PCC_GSCRATCH * 8);   // one row per (possible) warp
         const char *sp = getenv("PCC_B200_SPLIT");
         h->split = sp ? atoi(sp) != 0 : false;   // two-kernel variant: measured slower, kept for experiments
         if (ce != cudaSuccess) { delete h; return fail(PCC_ECUDA, "rebalance scratch: %s", cudaGetErrorString(ce)); }
@@ -1196,7 +1209,7 @@ void pcc_destroy(pcc_handle h)
     cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_reward);
     cudaFree(h->st_done); cudaFree(h->st_counts);
     cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->perm); cudaFree(h->sort_tmp);
-    cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps); cudaFree(h->sent_tmp);
+    cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps); cudaFree(h->sent_tmp); cudaFree(h->d.mean_scratch);
     delete h;
 }
 

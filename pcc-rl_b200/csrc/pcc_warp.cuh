@@ -238,7 +238,7 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
     out.acked = acked; out.lost = lost;
 }
 
-// ---- np.mean for 128 < n <= wbuf: all samples are in shared memory --------------------------------
+// ---- np.mean for 128 < n <= capacity: all samples are staged (shared memory, or the warp's global scratch) ----
 // numpy's pairwise recursion (n > 128: n2 = n/2 rounded down to a multiple of 8; sum(left) + sum(right))
 // bottoms out in leaves of 65..128 elements.  List the leaves left to right ...
 __device__ __forceinline__ int enum_leaves(int base, int n, int *off, int *cnt, int at)
@@ -368,8 +368,8 @@ __device__ __noinline__ void mi_means_stream(ConsumeOut co, Ring ring, double dl
 // avg latency (sender_obs.py:119-122) and latency increase (:138-142) of one env's MI, warp-wide
 template <class Ring>
 __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut &co, Ring &ring, double dl,
-                                              double *buf, int wbuf, bool need_increase, double &avg_lat,
-                                              double &lat_increase)
+                                              double *buf, int wbuf, LeafScratch *ls, double *smem_buf,
+                                              bool need_increase, double &avg_lat, double &lat_increase)
 {
     const int n = co.acked;
     avg_lat = 0.0;
@@ -409,9 +409,9 @@ __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut
         }
         __syncwarp();
     } else if (n <= wbuf) {
-        means_from_smem(buf, reinterpret_cast<LeafScratch *>(buf + wbuf + 32), n, need_increase, avg_lat, lat_increase);
+        means_from_smem(buf, ls, n, need_increase, avg_lat, lat_increase);
     } else {
-        mi_means_stream(co, ring, dl, buf, need_increase, avg_lat, lat_increase);
+        mi_means_stream(co, ring, dl, smem_buf, need_increase, avg_lat, lat_increase);
     }
 }
 
