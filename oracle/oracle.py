@@ -25,7 +25,7 @@ def feature_ids(features=DEFAULT_FEATURES):
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("pcc_oracle.c", "pcc_oracle_batch.c", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("pcc_oracle.c", "pcc_oracle_batch.c", "pcc_oracle_flows.c", "Makefile")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
@@ -257,3 +257,65 @@ class OracleBatch(object):
         self.L.pcco_batch_step(self.b, a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data,
                                self.done.ctypes.data, self.counts.ctypes.data, self.n_threads)
         return self.obs, self.reward, self.done, self.counts
+
+
+class OracleFlows(object):
+    """The MI-sample ingestion path restated (oracle/pcc_oracle_flows.c): per-flow SenderHistory fed by
+    give_sample records (loaded_client.py:111-138, shim_env.py:102-139)."""
+
+    def __init__(self, n_flows, history_len=10, features=DEFAULT_FEATURES):
+        L = self.L = lib()
+        vp, d, i, l, ll = C.c_void_p, C.c_double, C.c_int, C.c_long, C.c_longlong
+        pd = C.POINTER(C.c_double)
+        L.pcco_flows_create.restype = vp
+        L.pcco_flows_create.argtypes = [l, i, C.POINTER(C.c_int), i]
+        L.pcco_flows_destroy.argtypes = [vp]
+        L.pcco_flows_reset.argtypes = [vp, l, i]
+        L.pcco_flows_set_rate.argtypes = [vp, l, d]
+        L.pcco_flows_rate.restype = d
+        L.pcco_flows_rate.argtypes = [vp, l]
+        L.pcco_flows_conn_min.restype = d
+        L.pcco_flows_conn_min.argtypes = [vp, l]
+        L.pcco_flows_n_records.restype = ll
+        L.pcco_flows_n_records.argtypes = [vp, l]
+        L.pcco_flows_give_sample.argtypes = [vp, l, ll, ll, ll, d, d, d, d, pd, l, ll, pd]
+        L.pcco_flows_get_obs.argtypes = [vp, l, pd]
+        L.pcco_flows_apply_rate_delta.restype = d
+        L.pcco_flows_apply_rate_delta.argtypes = [d, d, d, d, d, i]
+        ids = np.asarray(feature_ids(features), dtype=np.int32)
+        self.n_flows, self.history_len, self.n_features = n_flows, history_len, len(ids)
+        self.h = L.pcco_flows_create(n_flows, history_len, _p(ids, C.c_int), len(ids))
+        if not self.h:
+            raise ValueError("bad n_flows / history_len / features")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.pcco_flows_destroy(self.h)
+            self.h = None
+
+    def reset(self, flow, mode=0):
+        self.L.pcco_flows_reset(self.h, flow, mode)
+
+    def give_sample(self, flow, bytes_sent, bytes_acked, bytes_lost, send_start, send_end, recv_start, recv_end,
+                    rtt_samples, packet_size, want_metrics=False):
+        rtt = np.ascontiguousarray(rtt_samples, dtype=np.float64)
+        m = np.zeros(12) if want_metrics else None
+        self.L.pcco_flows_give_sample(self.h, flow, int(bytes_sent), int(bytes_acked), int(bytes_lost),
+                                      float(send_start), float(send_end), float(recv_start), float(recv_end),
+                                      _p(rtt, C.c_double), rtt.size, int(packet_size),
+                                      _p(m, C.c_double) if want_metrics else None)
+        return m
+
+    def obs(self, flow):
+        o = np.zeros(self.history_len * self.n_features)
+        self.L.pcco_flows_get_obs(self.h, flow, _p(o, C.c_double))
+        return o
+
+    def conn_min(self, flow):
+        return self.L.pcco_flows_conn_min(self.h, flow)
+
+    def n_records(self, flow):
+        return self.L.pcco_flows_n_records(self.h, flow)
+
+    def apply_rate_delta(self, rate, delta, delta_scale, min_rate, max_rate, style=0):
+        return self.L.pcco_flows_apply_rate_delta(rate, delta, delta_scale, min_rate, max_rate, style)

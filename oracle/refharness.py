@@ -146,3 +146,92 @@ class StreamShim(object):
         if self.script:
             return self.script.pop(0)
         return a + (b - a) * self.streams[self.cur].random()
+
+
+# ---------------------------------------------------------------------------------------------
+# The MI-sample ingestion path: common/sender_obs.py, the loaded-model
+# client udt-plugins/testing/loaded_client.py and the online shim (gym/online/shim_env.py +
+# udt-plugins/training/shim.py), all imported unmodified.
+# ---------------------------------------------------------------------------------------------
+class StubAgent(object):
+    """Stands in for loaded_agent.LoadedModelAgent (TensorFlow saved model; TF is absent here):
+    a fixed, deterministic function of the observation.  `StubAgent.fn` may be replaced."""
+
+    fn = None
+
+    def __init__(self, model_path=None):
+        self.n_reset = 0
+
+    def reset(self):
+        self.n_reset += 1
+
+    def act(self, ob):
+        return StubAgent.fn(ob)
+
+
+_ref_flows = None
+
+
+def load_reference_flows():
+    """Returns (sender_obs, loaded_client) of the reference.  loaded_client imports `loaded_agent`
+    (TensorFlow); a stub module with the same class name is injected for the import."""
+    global _ref_flows
+    if _ref_flows is not None:
+        return _ref_flows
+    ns = load_reference()                      # makes `common.sender_obs` the reference's module
+    sender_obs = sys.modules["common.sender_obs"]
+    assert ns.sender_obs is sender_obs
+    stub = types.ModuleType("loaded_agent")
+    stub.LoadedModelAgent = StubAgent
+    testing_dir = os.path.join(REFERENCE_ROOT, "src", "udt-plugins", "testing")
+    saved_argv, saved_agent = sys.argv, sys.modules.get("loaded_agent")
+    sys.argv = ["refharness"]
+    sys.modules["loaded_agent"] = stub
+    sys.path.insert(0, testing_dir)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import importlib
+            lc = importlib.import_module("loaded_client")
+    finally:
+        sys.argv = saved_argv
+        sys.path.remove(testing_dir)
+        if saved_agent is None:
+            sys.modules.pop("loaded_agent", None)
+        else:
+            sys.modules["loaded_agent"] = saved_agent
+    sys.modules["pcc_reference_loaded_client"] = sys.modules.pop("loaded_client")
+    assert lc.sender_obs is sender_obs
+    _ref_flows = (sender_obs, lc)
+    return _ref_flows
+
+
+_ref_shim = None
+
+
+def load_reference_shim():
+    """Returns (shim_env, shim): the online training shim, server and client side.  Both use a real TCP
+    socket on localhost:9787 (shim_env.py:62-64, shim.py:24-25); the caller runs them in two threads."""
+    global _ref_shim
+    if _ref_shim is not None:
+        return _ref_shim
+    load_reference()
+    _install_gym_stub()
+    saved_argv = sys.argv
+    sys.argv = ["refharness"]
+    dirs = [os.path.join(REFERENCE_ROOT, "src", "gym", "online"),
+            os.path.join(REFERENCE_ROOT, "src", "udt-plugins", "training")]
+    for d in dirs:
+        sys.path.insert(0, d)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import importlib
+            shim_env = importlib.import_module("shim_env")
+            shim = importlib.import_module("shim")
+    finally:
+        sys.argv = saved_argv
+        for d in dirs:
+            sys.path.remove(d)
+    sys.modules["pcc_reference_shim_env"] = sys.modules.pop("shim_env")
+    sys.modules["pcc_reference_shim"] = sys.modules.pop("shim")
+    _ref_shim = (shim_env, shim)
+    return _ref_shim
