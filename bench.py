@@ -39,6 +39,8 @@ WORKLOADS = {
     "config4": dict(envs=65536, desc="65 536 envs per GPU (524 288 on 8), PPO-style rollout end to end: on-device MLP policy "
                                      "30-32-16-1 + env step fused (pcc_rollout, 64 MIs per launch), NCCL gather of episode returns"),
 }
+WORKLOADS["flows"] = dict(envs=1 << 20, desc="MI-sample ingestion (SURVEY 8f rank 4): 1 Mi live flows per GPU, one MI record per flow "
+                                             "per step (~150 RTT samples each), history_len=10, 3 features")
 ACTION_SIGMA = 1.0   # a ~ N(0,1), BASELINE.md §3
 
 
@@ -213,6 +215,148 @@ def run_config4(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
         torch.distributed.destroy_process_group()
 
 
+def flows_batch(rng, n_flows, mean_samples=150):
+    """One synthetic MI record per flow (flow order shuffled), SoA + CSR -- numpy, host."""
+    n = rng.poisson(mean_samples, n_flows).astype(np.int64)
+    n[rng.random(n_flows) < 0.01] = 0
+    ps = rng.choice(np.array([1500, 1400, 1000], dtype=np.int64), n_flows)
+    lost = rng.integers(0, 6, n_flows)
+    dur = rng.uniform(0.01, 0.5, n_flows)
+    base = rng.uniform(0.01, 0.4, n_flows)
+    off = np.zeros(n_flows + 1, dtype=np.int64)
+    off[1:] = np.cumsum(n)
+    rtt = np.repeat(base, n) * (1.0 + 0.5 * rng.random(int(off[-1])))
+    return dict(flow=rng.permutation(n_flows).astype(np.int32), bytes_sent=(n + lost + 1) * ps, bytes_acked=n * ps,
+                bytes_lost=lost * ps, send_start=np.zeros(n_flows), send_end=dur, recv_start=base, recv_end=dur + base,
+                packet_size=ps, rtt_off=off, rtt=rtt)
+
+
+def flows_algorithmic_bytes(n_records, n_samples, H=10, F=3):
+    """Per record: 76 B of fields (flow 4, 4 x i64, 4 x f64, CSR offset 8) + 8 B per RTT sample (read once) + per-flow
+    state read+write (conn-min entry 16, head/flags 8, record counter 8, batch stamp 8 = 40) + the new history row
+    (8F write) + the observation (8(H-1)F history read + 8HF write)."""
+    return n_records * (76 + 40 + 8 * F + 8 * (H - 1) * F + 8 * H * F) + 8 * n_samples
+
+
+def run_flows(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
+    """--workload flows: steps of one record per flow through pcc_flows_give_samples (unique batch, one launch)."""
+    K, W = args.steps, args.warmup
+    NB = 3                                               # distinct pre-generated batches, cycled (each >> L2)
+    rng = np.random.default_rng(args.seed + 17 * rank)
+    mon = pcc_rl_b200.PccFlowMonitor(n, device=dev)
+    host = [flows_batch(rng, n) for _ in range(NB)]
+    batches = [mon.make_batch(**b) for b in host]
+    n_samples = [int(b["rtt_off"][-1]) for b in host]
+    obs = torch.empty((n, mon.obs_dim), dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for t in range(W):
+        mon.give_samples(batches[t % NB], unique_flows=True, obs_out=obs)
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else dev.index)
+    barrier()
+    launches0 = mon.launches
+    sampler.start()
+    samples_total = 0
+    for t in range(K):
+        ev_s[t].record()
+        mon.give_samples(batches[(W + t) % NB], unique_flows=True, obs_out=obs)
+        ev_e[t].record()
+        samples_total += n_samples[(W + t) % NB]
+    barrier()
+    clocks = sampler.stop()
+    launches = mon.launches - launches0
+    mon.check()
+    dev_ms = D.max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e)), dev)
+    g_samples = D.sum_over_ranks(samples_total, dev)
+    value = n_global * K / (dev_ms * 1e-3)
+
+    # general (non-unique) batches: ingest + cub sort + per-flow apply
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kg = max(1, K // 4)
+    mon.give_samples(batches[0], unique_flows=False, obs_out=obs)
+    barrier()
+    s.record()
+    for t in range(kg):
+        mon.give_samples(batches[t % NB], unique_flows=False, obs_out=obs)
+    e.record()
+    barrier()
+    gen_ms = D.max_over_ranks(s.elapsed_time(e), dev)
+
+    # end to end: pinned HOST batch -> device, ingest, observation back to the host
+    ke = max(1, min(K, 8))
+    pin = [{k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in b.items()} for b in host[:2]]
+    h_obs = torch.empty((n, mon.obs_dim), dtype=torch.float64).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in pin[0].values())
+
+    def e2e_step(t):
+        b = {k: v.to(dev, non_blocking=True) for k, v in pin[t % 2].items()}
+        mon.give_samples(b, unique_flows=True, obs_out=obs)
+        h_obs.copy_(obs, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return float(h_obs[0, -1])
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for t in range(ke):
+        acc += e2e_step(t)
+    barrier()
+    e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    mon.check()
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak_gbs()
+    bytes_total = flows_algorithmic_bytes(n_global * K, g_samples)
+    achieved = bytes_total / (dev_ms * 1e-3) / 1e9 / world
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)["flows"]
+        if n == WORKLOADS["flows"]["envs"]:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/" + tj["source"]
+    except Exception:
+        pass
+    line = {
+        "metric": "MI records/sec (flow-monitor ingestion)", "value": value, "unit": "records/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "flows: " + WORKLOADS["flows"]["desc"], "flows_per_gpu": n, "global_flows": n_global,
+                   "history_len": 10, "features": 3, "samples_per_record": g_samples / (n_global * K),
+                   "l2": "inputs larger than L2 (%.2f GB per batch, %d batches cycled)" % (h2d / 1e9, NB),
+                   "parallelism": "flow sharding x%d, no collective" % world},
+        "general_batches": {"value": n_global * kg / (gen_ms * 1e-3), "ms_per_step": gen_ms / kg,
+                            "note": "unique_flows=0: ingest + cub radix sort by flow + per-flow apply in batch order"},
+        "e2e": {"value": n_global * ke / e2e_s, "unit": "records/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(h_obs.numel() * 8), "ms_per_step": 1e3 * e2e_s / ke, "steps": ke,
+                "api": "PccFlowMonitor.give_samples on pinned host tensors (H2D batch, D2H observations, synchronous)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "pcc_flows_ingest_kernel<true>",
+                     "algorithmic_bytes_per_launch": bytes_total / (K * world)},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        import oracle
+        ns = 200000
+        fl = oracle.OracleFlows(n, 10, oracle.DEFAULT_FEATURES)
+        sub = {k: (v[:ns] if k not in ("rtt", "rtt_off") else v) for k, v in host[0].items()}
+        sub["rtt_off"] = host[0]["rtt_off"][:ns + 1]
+        secs = fl.give_batch(sub)
+        line["cpu_baseline"] = {"value": ns / secs, "unit": "records/s", "cores": 1, "kind": "port",
+                                "sample": "%d records of the same batch, one host thread, C restatement of "
+                                          "sender_obs.py / loaded_client.give_sample (oracle/pcc_oracle_flows.c)" % ns}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,6 +377,9 @@ def main():
 
     if args.workload == "config4":
         run_config4(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global)
+        return
+    if args.workload == "flows":
+        run_flows(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global)
         return
 
     def make_env():

@@ -217,6 +217,89 @@ int pcc_multi_step(pcc_multi_handle h, const double *actions_dev /*[n][S]*/, dou
                    void *stream);
 int pcc_multi_check(pcc_multi_handle h, void *stream);
 
+/* ---- MI-sample ingestion ("flow monitor") -------------------------------------------
+ * The other producer of SenderMonitorIntervals: records measured on REAL flows by the PCC sender, handed to
+ * Python one at a time and turned into the agent's observation:
+ *   pcc_flows_give_samples   give_sample -> SenderMonitorInterval -> SenderHistory.step
+ *                              udt-plugins/testing/loaded_client.py:84-86, 111-138; gym/online/shim_env.py:102-139
+ *                              (wire format udt-plugins/training/shim.py:31-42); common/sender_obs.py:20-73, 110-191
+ *   pcc_flows_get_obs        SenderHistory.as_array                     common/sender_obs.py:68-73
+ *   pcc_flows_reset          PccGymDriver.reset_history / ShimNetworkEnv.reset   loaded_client.py:97-101; shim_env.py:141-149
+ *   pcc_flows_get_rates      PccGymDriver.get_rate -> apply_rate_delta  loaded_client.py:72-76, 147-168
+ *                            ShimNetworkEnv.apply_action / set_rate     shim_env.py:80-95
+ *   pcc_flows_act            LoadedModelAgent.act (the saved MLP policy) loaded_client.py:74; stable_solve.py:30-45
+ * Here a batch carries records of many flows (structure of arrays + CSR sample lists, device pointers); each
+ * record's metrics are evaluated when it is ingested and appended to its flow's history, exactly what the
+ * reference computes when history.as_array() is taken at least once per history_len records of a flow (it
+ * memoises metrics per MI and updates the global _conn_min_latencies dict on first evaluation).  Byte counts
+ * and packet sizes are integers below 2^53.  Records of one flow inside a batch apply in batch order. */
+#define PCC_RATE_CLIENT 0     /* loaded_client.apply_rate_delta: >0 multiply, <0 divide; only flows that have data */
+#define PCC_RATE_SHIM 1       /* ShimNetworkEnv.apply_action:    >=0 multiply, else divide; every selected flow   */
+#define PCC_FLOW_RESET_NEW 0     /* a new flow id: no conn-min dict entry, empty history                          */
+#define PCC_FLOW_RESET_CLIENT 1  /* PccGymDriver.reset_history: entry survives, the new empty MIs see it          */
+#define PCC_FLOW_RESET_SHIM 2    /* ShimNetworkEnv.reset: entry survives, the empty MIs (sender id 0) do not see it */
+
+typedef struct pcc_flows_config {
+    int32_t abi_version;      /* PCC_ABI_VERSION */
+    int32_t device;
+    int64_t n_flows;
+    int32_t history_len;      /* --history-len (default 10) */
+    int32_t n_features;       /* --input-features (default: the three of network_sim.py:348-351) */
+    int32_t feature_ids[PCC_MAX_FEATURES];
+    double delta_scale;       /* DELTA_SCALE  0.05 (loaded_client.py:35)  / 0.025 (shim_env.py:43) */
+    double min_rate;          /* MIN_RATE     0.5  (loaded_client.py:33)  / 0.25  (shim_env.py:40) */
+    double max_rate;          /* MAX_RATE     300  (loaded_client.py:34)  / 1000  (shim_env.py:39) */
+    int32_t rate_style;       /* PCC_RATE_* */
+    int32_t reserved0;
+} pcc_flows_config;
+
+/* One batch of MI records; every pointer is a device pointer, arrays have n_records elements. */
+typedef struct pcc_mi_batch {
+    int64_t n_records;
+    const int32_t *flow;          /* index of the record's flow, 0 .. n_flows-1 */
+    const int64_t *bytes_sent, *bytes_acked, *bytes_lost, *packet_size;
+    const double *send_start, *send_end, *recv_start, *recv_end;   /* seconds */
+    const int64_t *rtt_offsets;   /* [n_records + 1]: record r owns rtt_samples[rtt_offsets[r] .. rtt_offsets[r+1]) */
+    const double *rtt_samples;    /* seconds, in arrival order */
+} pcc_mi_batch;
+
+typedef struct pcc_flows_handle_s *pcc_flows_handle;
+
+/* loaded_client's defaults: history 10, the three default features, rate control 0.05 / 0.5 / 300. */
+void pcc_flows_default_config(pcc_flows_config *cfg);
+int pcc_flows_workspace_bytes(const pcc_flows_config *cfg, uint64_t *bytes);
+/* Caller-owned, 256-byte aligned device workspace; create initialises every flow as PCC_FLOW_RESET_NEW with
+ * rate 0 (synchronous); attach adopts a workspace that already holds state (checkpoint). */
+int pcc_flows_create(pcc_flows_handle *out, const pcc_flows_config *cfg, void *workspace_dev);
+int pcc_flows_attach(pcc_flows_handle *out, const pcc_flows_config *cfg, void *workspace_dev);
+void pcc_flows_destroy(pcc_flows_handle h);
+
+/* Ingests a batch.  unique_flows != 0: the caller guarantees at most one record per flow (one fused kernel;
+ * violations are detected and reported by pcc_flows_check); 0: any batch (records of a flow apply in batch order).
+ *   obs_dev      double[n_records][history_len*n_features]  (optional) the flow's observation right after the record
+ *   metrics_dev  double[n_records][PCC_N_METRICS]           (optional) the record's 12 raw metric values */
+int pcc_flows_give_samples(pcc_flows_handle h, const pcc_mi_batch *batch, int32_t unique_flows, double *obs_dev,
+                           double *metrics_dev, void *stream);
+/* mask_dev: uint8[n_flows] or NULL (= all); mode: PCC_FLOW_RESET_*.  Rates are not touched (the reference's
+ * reset_rate sets an unused attribute, loaded_client.py:94-95); use pcc_flows_set_rates. */
+int pcc_flows_reset(pcc_flows_handle h, const uint8_t *mask_dev, int32_t mode, void *stream);
+/* obs_dev: double[n_flows][history_len*n_features], oldest MI first. */
+int pcc_flows_get_obs(pcc_flows_handle h, double *obs_dev, void *stream);
+/* rate[flow] = rates_dev[flow], or `rate` for every selected flow when rates_dev is NULL. */
+int pcc_flows_set_rates(pcc_flows_handle h, const uint8_t *mask_dev, const double *rates_dev, double rate, void *stream);
+/* Applies actions_dev[flow] (optional) to the selected flows' rates (PCC_RATE_CLIENT: only flows that have
+ * received a record since their last reset) and writes the rates to rates_dev[n_flows] (optional; the
+ * reference's get_rate returns rate * 1e6). */
+int pcc_flows_get_rates(pcc_flows_handle h, const double *actions_dev, const uint8_t *mask_dev, double *rates_dev,
+                        void *stream);
+/* actions_dev[flow] = policy(observation of the flow), deterministic (stochastic = False). */
+int pcc_flows_act(pcc_flows_handle h, const pcc_policy *policy, double *actions_dev, void *stream);
+/* Copies a per-flow column ("conn_min", "rate") to dst_dev[n_flows]. */
+int pcc_flows_get_column(pcc_flows_handle h, const char *name, double *dst_dev, void *stream);
+/* Synchronises and reports sticky errors: out-of-range flow index, duplicate flow in a unique batch. */
+int pcc_flows_check(pcc_flows_handle h, void *stream);
+int64_t pcc_flows_launch_count(pcc_flows_handle h);
+
 const char *pcc_last_error(void);
 int pcc_abi_version(void);
 

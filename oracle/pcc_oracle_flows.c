@@ -246,3 +246,15 @@ double pcco_flows_apply_rate_delta(double rate, double delta, double delta_scale
     }
     return rate;
 }
+
+/* A whole batch in C (the cpu_baseline leg of bench.py --workload flows): records in batch order. */
+void pcco_flows_give_batch(pccf_flows *fs, long n_records, const int *flow, const long long *bytes_sent,
+                           const long long *bytes_acked, const long long *bytes_lost, const double *send_start,
+                           const double *send_end, const double *recv_start, const double *recv_end,
+                           const long long *packet_size, const long long *rtt_off, const double *rtt)
+{
+    for (long r = 0; r < n_records; r++)
+        pcco_flows_give_sample(fs, flow[r], bytes_sent[r], bytes_acked[r], bytes_lost[r], send_start[r], send_end[r],
+                               recv_start[r], recv_end[r], rtt + rtt_off[r], (long)(rtt_off[r + 1] - rtt_off[r]),
+                               packet_size[r], NULL);
+}

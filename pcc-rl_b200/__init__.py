@@ -7,6 +7,8 @@ from . import _lib, sender_obs, params
 from .params import LinkRanges, sample_link_params
 from .batch_env import PccBatchEnv
 from .multi_env import PccMultiSenderEnv, grid_sweep_params
+from .flow_monitor import PccFlowMonitor
+from . import flow_monitor
 
 
 def build(force=False, verbose=False):

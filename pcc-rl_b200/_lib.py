@@ -30,6 +30,26 @@ class PccPolicy(C.Structure):
                 ("h2", C.c_int32), ("stochastic", C.c_int32), ("log_std", C.c_double), ("noise_seed", C.c_uint64)]
 
 
+class PccFlowsConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_flows", C.c_int64),
+                ("history_len", C.c_int32), ("n_features", C.c_int32),
+                ("feature_ids", C.c_int32 * PCC_MAX_FEATURES), ("delta_scale", C.c_double),
+                ("min_rate", C.c_double), ("max_rate", C.c_double), ("rate_style", C.c_int32),
+                ("reserved0", C.c_int32)]
+
+
+class PccMiBatch(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("flow", C.c_void_p), ("bytes_sent", C.c_void_p),
+                ("bytes_acked", C.c_void_p), ("bytes_lost", C.c_void_p), ("packet_size", C.c_void_p),
+                ("send_start", C.c_void_p), ("send_end", C.c_void_p), ("recv_start", C.c_void_p),
+                ("recv_end", C.c_void_p), ("rtt_offsets", C.c_void_p), ("rtt_samples", C.c_void_p)]
+
+
+PCC_RATE_CLIENT, PCC_RATE_SHIM = 0, 1
+PCC_FLOW_RESET_NEW, PCC_FLOW_RESET_CLIENT, PCC_FLOW_RESET_SHIM = 0, 1, 2
+PCC_N_METRICS = 12
+
+
 class PccError(RuntimeError):
     def __init__(self, code, msg):
         RuntimeError.__init__(self, "libpcc_b200 error %d: %s" % (code, msg))
@@ -41,7 +61,10 @@ EXPORTS = ["pcc_default_consts", "pcc_default_config", "pcc_ring_capacity_for", 
            "pcc_create", "pcc_destroy", "pcc_attach", "pcc_seed", "pcc_get_mt_state", "pcc_set_mt_state",
            "pcc_reset", "pcc_step", "pcc_step_host", "pcc_rollout", "pcc_check", "pcc_get_column", "pcc_launch_count",
            "pcc_last_error", "pcc_abi_version", "pcc_multi_workspace_bytes", "pcc_multi_create", "pcc_multi_destroy",
-           "pcc_multi_seed", "pcc_multi_reset", "pcc_multi_step", "pcc_multi_check"]
+           "pcc_multi_seed", "pcc_multi_reset", "pcc_multi_step", "pcc_multi_check",
+           "pcc_flows_default_config", "pcc_flows_workspace_bytes", "pcc_flows_create", "pcc_flows_attach",
+           "pcc_flows_destroy", "pcc_flows_give_samples", "pcc_flows_reset", "pcc_flows_get_obs", "pcc_flows_set_rates",
+           "pcc_flows_get_rates", "pcc_flows_act", "pcc_flows_get_column", "pcc_flows_check", "pcc_flows_launch_count"]
 
 _lib = None
 
@@ -90,6 +113,23 @@ def load(rebuild_if_stale=True):
     L.pcc_multi_reset.argtypes = [vp, u8p, dp, dp, vp, dp, dp, dp, vp]
     L.pcc_multi_step.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
     L.pcc_multi_check.argtypes = [vp, vp]
+    L.pcc_flows_default_config.argtypes = [C.POINTER(PccFlowsConfig)]
+    L.pcc_flows_default_config.restype = None
+    L.pcc_flows_workspace_bytes.argtypes = [C.POINTER(PccFlowsConfig), C.POINTER(C.c_uint64)]
+    L.pcc_flows_create.argtypes = [C.POINTER(vp), C.POINTER(PccFlowsConfig), vp]
+    L.pcc_flows_attach.argtypes = [C.POINTER(vp), C.POINTER(PccFlowsConfig), vp]
+    L.pcc_flows_destroy.argtypes = [vp]
+    L.pcc_flows_destroy.restype = None
+    L.pcc_flows_give_samples.argtypes = [vp, C.POINTER(PccMiBatch), C.c_int32, dp, dp, vp]
+    L.pcc_flows_reset.argtypes = [vp, u8p, C.c_int32, vp]
+    L.pcc_flows_get_obs.argtypes = [vp, dp, vp]
+    L.pcc_flows_set_rates.argtypes = [vp, u8p, dp, C.c_double, vp]
+    L.pcc_flows_get_rates.argtypes = [vp, dp, u8p, dp, vp]
+    L.pcc_flows_act.argtypes = [vp, C.POINTER(PccPolicy), dp, vp]
+    L.pcc_flows_get_column.argtypes = [vp, C.c_char_p, dp, vp]
+    L.pcc_flows_check.argtypes = [vp, vp]
+    L.pcc_flows_launch_count.argtypes = [vp]
+    L.pcc_flows_launch_count.restype = C.c_int64
     L.pcc_get_column.argtypes = [vp, C.c_char_p, dp, vp]
     L.pcc_launch_count.argtypes = [vp]
     L.pcc_launch_count.restype = C.c_int64

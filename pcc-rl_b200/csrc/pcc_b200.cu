@@ -1710,3 +1710,5 @@ int pcc_multi_check(pcc_multi_handle h, void *stream)
 }
 
 }  // extern "C"
+
+#include "pcc_flows.cuh"

@@ -1,0 +1,705 @@
+// pcc_flows.cuh -- CUDA kernels + C ABI of the MI-sample ingestion path ("flow monitor"): batches of
+// monitor-interval records from many live flows -> the 12 MI metrics -> per-flow history -> observation.
+// Included at the end of pcc_b200.cu (one translation unit, one libpcc_b200.so).  Scalar semantics and the
+// reference file:line map are in pcc_flows_core.cuh; the oracle is oracle/pcc_oracle_flows.c.
+//
+// This path is HBM-bound byte work: a record is ~76 B of fields plus 8 B per RTT sample (CSR), and the
+// only arithmetic is numpy's pairwise mean over the samples (three ranges: all, first half, second half),
+// a handful of binary64 divisions, and one history row.  Mapping:
+//   * an 8-lane subgroup owns a record (4 records per warp): the 8 lanes ARE numpy's 8 accumulators
+//     (r[j] += a[8k+j] in numpy's order), three xor-shuffles are its ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+//     tree, so np.mean is bit-exact; every load of a subgroup is a contiguous 64 B run of the sample array;
+//   * the divisions of a record are spread over the subgroup's lanes (two rounds of one DDIV each instead
+//     of twelve in sequence), the result row and the observation are written by the subgroup cooperatively;
+//   * records with more than 128 samples (numpy's recursion kicks in) are handed to the whole warp: the
+//     leaves of the recursion are independent, four at a time (one per subgroup), folded in numpy's order;
+//   * persistent grid (a multiple of the SM count), warps stride over the batch.
+// State per flow (caller-owned workspace): hist[flow][H][F] (a ring over H with a per-flow head), the
+// conn-min dict entry, the sending rate, record counter.
+#pragma once
+#include "pcc_flows_core.cuh"
+
+namespace pccf {
+using namespace pcc;
+
+#define PCCF_THREADS 256
+#define PCCF_FULL 0xffffffffu
+#define PCCF_HEAD_MASK 0xffu
+#define PCCF_HAS_MIN 0x100u
+
+struct FlowsDev {
+    double *hist;               // [n_flows][H*F]; row `slot` at slot*F; head = slot of the OLDEST row
+    double *conn_min;           // [n_flows]
+    double *rate;               // [n_flows]
+    uint32_t *flags;            // [n_flows] bits 0-7 head, bit 8 = dict entry exists
+    uint32_t *n_rec;            // [n_flows] records since the last reset (saturating)
+    uint32_t *stamp;            // [n_flows] batch number of the flow's last record (unique-batch check)
+    unsigned long long *meta;   // [0] duplicate flows in a batch declared unique, [1] flow index out of range
+    int64_t n_flows;
+    int32_t H, F;
+    int32_t ids[PCC_MAX_FEATURES];
+    int32_t touch_conn;         // the feature set reads/updates the conn-min entry
+    double delta_scale, min_rate, max_rate;
+    int32_t rate_style;
+};
+
+struct BatchDev {
+    int64_t R;
+    const int32_t *flow;
+    const long long *bytes_sent, *bytes_acked, *bytes_lost, *packet_size;
+    const double *send_start, *send_end, *recv_start, *recv_end;
+    const long long *off;       // [R + 1]
+    const double *rtt;
+};
+
+// One leaf of numpy's DOUBLE_pairwise_sum (n <= 128) on an 8-lane subgroup; the result is subgroup-uniform.
+__device__ __forceinline__ double sg_leaf(const double *__restrict__ a, int n, int j, unsigned mask)
+{
+    if (n < 8) {
+        double res = 0.;
+        for (int k = 0; k < n; k++) res += __ldg(a + k);
+        return res;
+    }
+    const int nb = n - (n % 8);
+    double r = __ldg(a + j);
+#pragma unroll 8
+    for (int k = 8; k < nb; k += 8) r += __ldg(a + k + j);
+    r += __shfl_xor_sync(mask, r, 1);
+    r += __shfl_xor_sync(mask, r, 2);
+    r += __shfl_xor_sync(mask, r, 4);
+    for (int k = nb; k < n; k++) r += __ldg(a + k);
+    return r;
+}
+
+// numpy's pairwise sum of a[0..n) for any n, by the whole warp (warp-uniform control flow and result).
+// The recursion (n > 128: n2 = n/2 rounded down to a multiple of 8; sum(left n2) + sum(right n - n2)) is
+// walked twice in lock step: a structure-only walk runs ahead and names the next four leaves -- leaves
+// tile [0, n) left to right -- the subgroups sum them, and the value walk folds the sums in post-order.
+struct PwWalk {
+    int right_n[32];
+    unsigned have_left;
+    int sp, cur;
+    __device__ __forceinline__ void init(int n) { sp = 0; cur = n; have_left = 0u; }
+    __device__ __forceinline__ int next_leaf()     // descend to the next leaf, return its size
+    {
+        while (cur > 128) {
+            int n2 = cur / 2;
+            n2 -= n2 % 8;
+            right_n[sp] = cur - n2; have_left &= ~(1u << sp); sp++;
+            cur = n2;
+        }
+        return cur;
+    }
+    // after a leaf (or a completed subtree): climb; returns true when the whole sum is complete
+    template <class OnLeft, class OnJoin>
+    __device__ __forceinline__ bool climb(OnLeft on_left, OnJoin on_join)
+    {
+        for (;;) {
+            if (sp == 0) return true;
+            if (!(have_left & (1u << (sp - 1)))) {
+                on_left(sp - 1);
+                have_left |= 1u << (sp - 1);
+                cur = right_n[sp - 1];
+                return false;
+            }
+            on_join(sp - 1);
+            sp--;
+        }
+    }
+};
+
+__device__ __noinline__ double warp_pw_sum(const double *__restrict__ a, long long n)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int sg = (int)(lane >> 3), j = (int)(lane & 7u);
+    PwWalk ahead, fold;
+    ahead.init((int)n);
+    fold.init((int)n);
+    double left_sum[32];
+    long long off = 0;
+    bool ahead_done = (n <= 0), done = (n <= 0);
+    double result = 0.0;
+    while (!done) {
+        long long lo[4]; int lc[4]; int cnt = 0;
+        while (cnt < 4 && !ahead_done) {
+            const int c = ahead.next_leaf();
+            lo[cnt] = off; lc[cnt] = c; cnt++;
+            off += c;
+            ahead_done = ahead.climb([](int) {}, [](int) {});
+        }
+        double mine = 0.0;
+        {
+            long long o = 0; int c = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (k == sg && k < cnt) { o = lo[k]; c = lc[k]; }
+            mine = sg_leaf(a + o, c, j, 0xffu << (sg * 8));   // subgroups diverge (idle ones have c == 0)
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double leaf = __shfl_sync(PCCF_FULL, mine, k * 8);
+            if (k < cnt && !done) {
+                fold.next_leaf();
+                double res = leaf;
+                done = fold.climb([&](int s) { left_sum[s] = res; },
+                                  [&](int s) { res = left_sum[s] + res; });
+                if (done) result = res;
+            }
+        }
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ingest kernel.  UNIQUE: every flow appears at most once in the batch (checked): metrics, conn-min entry,
+// history row and observation in this one kernel.  !UNIQUE: the per-record part only; rows[R][F] (scaled
+// feature values) and avg[R] are handed to pcc_flows_apply_kernel, which walks each flow's records in batch
+// order.
+// ---------------------------------------------------------------------------------------------------------
+template <bool UNIQUE>
+__global__ void __launch_bounds__(PCCF_THREADS, 2)
+pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__restrict__ obs, double *__restrict__ metrics,
+                        double *__restrict__ rows, double *__restrict__ avg_out)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int sg = (int)(lane >> 3), j = (int)(lane & 7u);
+    const unsigned sgmask = 0xffu << (sg * 8);
+    const int sg0 = sg * 8;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int H = p.H, F = p.F, HF = H * F;
+
+    for (long long base = warp * 4; base < b.R; base += nwarps * 4) {      // warp-uniform
+        const long long r = base + sg;
+        const bool valid = r < b.R;
+        long long n = 0, bs = 0, ba = 0, bl = 0, ps = 0;
+        double ss = 0., se = 0., rs = 0., re = 0.;
+        const double *a = b.rtt;
+        int flow = 0;
+        if (valid) {
+            const long long o0 = __ldg(b.off + r), o1 = __ldg(b.off + r + 1);
+            n = o1 - o0; a = b.rtt + o0;
+            bs = __ldg(b.bytes_sent + r); ba = __ldg(b.bytes_acked + r); bl = __ldg(b.bytes_lost + r);
+            ps = __ldg(b.packet_size + r);
+            ss = __ldg(b.send_start + r); se = __ldg(b.send_end + r);
+            rs = __ldg(b.recv_start + r); re = __ldg(b.recv_end + r);
+            flow = __ldg(b.flow + r);
+        }
+        bool good = valid && flow >= 0 && (long long)flow < p.n_flows && n >= 0;
+        if (valid && !good && j == 0) atomicAdd(&p.meta[1], 1ull);
+        if (!good) n = 0;
+        const long long half = n / 2;
+
+        // ---- the three pairwise sums -------------------------------------------------------------------
+        double sum = 0.0, s1 = 0.0, s2 = 0.0;
+        if (good && n > 0 && n <= 128) {
+            sum = sg_leaf(a, (int)n, j, sgmask);
+            if (half >= 1) {
+                s1 = sg_leaf(a, (int)half, j, sgmask);
+                s2 = sg_leaf(a + half, (int)(n - half), j, sgmask);
+            }
+        }
+        unsigned bigmask = __ballot_sync(PCCF_FULL, good && n > 128 && j == 0);
+        while (bigmask) {                                                   // warp-uniform
+            const int src = __ffs(bigmask) - 1;
+            bigmask &= bigmask - 1;
+            const double *aa = (const double *)__shfl_sync(PCCF_FULL, (unsigned long long)a, src);
+            const long long nn = __shfl_sync(PCCF_FULL, n, src);
+            const double t0 = warp_pw_sum(aa, nn);
+            const double t1 = warp_pw_sum(aa, nn / 2);
+            const double t2 = warp_pw_sum(aa + nn / 2, nn - nn / 2);
+            if (sg0 == src) { sum = t0; s1 = t1; s2 = t2; }
+        }
+
+        // ---- round 1 of divisions: one per lane (sender_obs.py:110-142) ---------------------------------
+        const double sdur = se - ss, rdur = re - rs;
+        double num = 0.0, den = 1.0;
+        bool ok = false;
+        if (j == 0) { num = 8.0 * (double)bs; den = sdur; ok = sdur > 0.0; }                    // send rate
+        else if (j == 1) { num = 8.0 * (double)(ba - ps); den = rdur; ok = rdur > 0.0; }        // recv rate
+        else if (j == 2) { num = 0.0 + sum; den = (double)n; ok = n > 0; }                      // np.mean(all)
+        else if (j == 3) { num = 0.0 + s1; den = (double)half; ok = half >= 1; }                // np.mean(first half)
+        else if (j == 4) { num = 0.0 + s2; den = (double)(n - half); ok = half >= 1; }          // np.mean(second half)
+        else if (j == 5) { num = (double)bl; den = (double)(bl + ba); ok = (bl + ba) > 0; }     // loss ratio
+        double q = num / (ok ? den : 1.0);
+        if (!ok) q = 0.0;
+        const double send_rate = __shfl_sync(sgmask, q, sg0 + 0);
+        const double recv_rate = __shfl_sync(sgmask, q, sg0 + 1);
+        const double avg = __shfl_sync(sgmask, q, sg0 + 2);
+        const double m1 = __shfl_sync(sgmask, q, sg0 + 3);
+        const double m2 = __shfl_sync(sgmask, q, sg0 + 4);
+        const double loss = __shfl_sync(sgmask, q, sg0 + 5);
+        const double inc = (half >= 1) ? m2 - m1 : 0.0;
+
+        // ---- conn-min dict entry (:158-176) -----------------------------------------------------------------
+        uint32_t fl = 0; double cmin = 0.0, cm = 0.0;
+        bool has_min = false;
+        if (UNIQUE && good) {
+            fl = p.flags[flow]; cmin = p.conn_min[flow];
+            has_min = (fl & PCCF_HAS_MIN) != 0;
+            cm = flow_conn_min(avg, has_min, cmin, p.touch_conn != 0);
+        }
+
+        // ---- round 2 --------------------------------------------------------------------------------------
+        double dflt = 0.0;
+        num = 0.0; den = 1.0; ok = false;
+        if (j == 0) { num = inc; den = rdur; ok = rdur > 0.0; }                                  // ack latency inflation
+        else if (j == 1) { num = inc; den = sdur; ok = sdur > 0.0; }                             // sent latency inflation
+        else if (j == 2) { num = avg; den = cm; ok = cm > 0.0; dflt = 1.0; }                     // latency ratio
+        else if (j == 3) { num = send_rate; den = recv_rate; dflt = 1.0;
+                           ok = recv_rate > 0.0 && send_rate < 1000.0 * recv_rate; }             // send ratio
+        else if (j == 4) { num = send_rate; den = 1e7; ok = true; }                              // scaled rates
+        else if (j == 5) { num = recv_rate; den = 1e7; ok = true; }
+        q = num / (ok ? den : 1.0);
+        if (!ok) q = dflt;
+        const double ack_infl = __shfl_sync(sgmask, q, sg0 + 0);
+        const double sent_infl = __shfl_sync(sgmask, q, sg0 + 1);
+        const double lat_ratio = __shfl_sync(sgmask, q, sg0 + 2);
+        const double send_ratio = __shfl_sync(sgmask, q, sg0 + 3);
+        const double send_rate_s = __shfl_sync(sgmask, q, sg0 + 4);
+        const double recv_rate_s = __shfl_sync(sgmask, q, sg0 + 5);
+
+        auto raw = [&](int id) -> double {
+            switch (id) {
+            case M_SEND_RATE: return send_rate;
+            case M_RECV_RATE: return recv_rate;
+            case M_RECV_DUR: return rdur;
+            case M_SEND_DUR: return sdur;
+            case M_AVG_LATENCY: return avg;
+            case M_LOSS_RATIO: return loss;
+            case M_ACK_LAT_INFL: return ack_infl;
+            case M_SENT_LAT_INFL: return sent_infl;
+            case M_CONN_MIN_LAT: return cm;
+            case M_LAT_INCREASE: return inc;
+            case M_LAT_RATIO: return lat_ratio;
+            default: return send_ratio;
+            }
+        };
+        if (!good) continue;                                                // (no warp-wide sync below this line)
+
+        if (metrics) {
+            metrics[r * N_METRICS + j] = raw(j);
+            if (j + 8 < N_METRICS) metrics[r * N_METRICS + j + 8] = raw(j + 8);
+        }
+        if (UNIQUE) {
+            const uint32_t head = fl & PCCF_HEAD_MASK;
+            double *hrow = p.hist + (size_t)flow * HF;
+            for (int f = j; f < F; f += 8) {                                // SenderHistory.step (:64-66)
+                const int id = p.ids[f];
+                const double v = (id == M_SEND_RATE) ? send_rate_s : (id == M_RECV_RATE) ? recv_rate_s : raw(id);
+                hrow[head * F + f] = v;
+            }
+            const uint32_t nhead = (head + 1 == (uint32_t)H) ? 0u : head + 1;
+            if (j == 0) {
+                if (atomicExch(&p.stamp[flow], batch_no) == batch_no) atomicAdd(&p.meta[0], 1ull);
+                p.flags[flow] = nhead | (has_min ? PCCF_HAS_MIN : 0u);
+                if (p.touch_conn) p.conn_min[flow] = cmin;
+                const uint32_t c = p.n_rec[flow];
+                if (c != 0xffffffffu) p.n_rec[flow] = c + 1;
+            }
+            if (obs) {                                                      // as_array (:68-73): oldest row first
+                __syncwarp(sgmask);
+                double *ob = obs + (size_t)r * HF;
+                const int rot = (int)nhead * F;
+                for (int k = j; k < HF; k += 8) {
+                    int src = k + rot;
+                    if (src >= HF) src -= HF;
+                    ob[k] = hrow[src];
+                }
+            }
+        } else {
+            for (int f = j; f < F; f += 8) {
+                const int id = p.ids[f];
+                rows[(size_t)r * F + f] = (id == M_SEND_RATE) ? send_rate_s : (id == M_RECV_RATE) ? recv_rate_s : raw(id);
+            }
+            if (j == 0) avg_out[r] = avg;
+        }
+    }
+}
+
+// General batches: position i of the flow-sorted (stable) record list; the first record of each flow's run
+// applies the whole run in batch order.
+__global__ void pcc_flows_apply_kernel(FlowsDev p, int64_t R, const int32_t *__restrict__ sorted_flow,
+                                       const int32_t *__restrict__ sorted_rec, const double *__restrict__ rows,
+                                       const double *__restrict__ avg, double *__restrict__ obs,
+                                       double *__restrict__ metrics)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const int flow = sorted_flow[i];
+    if (flow < 0 || (int64_t)flow >= p.n_flows) return;
+    if (i > 0 && sorted_flow[i - 1] == flow) return;
+    const int H = p.H, F = p.F, HF = H * F;
+    uint32_t fl = p.flags[flow];
+    double cmin = p.conn_min[flow];
+    bool has_min = (fl & PCCF_HAS_MIN) != 0;
+    uint32_t head = fl & PCCF_HEAD_MASK;
+    double *hrow = p.hist + (size_t)flow * HF;
+    uint32_t cnt = p.n_rec[flow];
+    for (int64_t k = i; k < R && sorted_flow[k] == flow; k++) {
+        const int64_t r = sorted_rec[k];
+        const double a = avg[r];
+        const double cm = flow_conn_min(a, has_min, cmin, p.touch_conn != 0);
+        const double lat_ratio = (cm > 0.0) ? a / cm : 1.0;
+        for (int f = 0; f < F; f++) {
+            const int id = p.ids[f];
+            double v = rows[(size_t)r * F + f];
+            if (id == M_CONN_MIN_LAT) v = cm;
+            else if (id == M_LAT_RATIO) v = lat_ratio;
+            hrow[head * F + f] = v;
+        }
+        if (metrics) { metrics[r * N_METRICS + M_CONN_MIN_LAT] = cm; metrics[r * N_METRICS + M_LAT_RATIO] = lat_ratio; }
+        head = (head + 1 == (uint32_t)H) ? 0u : head + 1;
+        if (cnt != 0xffffffffu) cnt++;
+        if (obs) {
+            double *ob = obs + (size_t)r * HF;
+            const int rot = (int)head * F;
+            for (int q = 0; q < HF; q++) { int src = q + rot; if (src >= HF) src -= HF; ob[q] = hrow[src]; }
+        }
+    }
+    p.flags[flow] = head | (has_min ? PCCF_HAS_MIN : 0u);
+    if (p.touch_conn) p.conn_min[flow] = cmin;
+    p.n_rec[flow] = cnt;
+}
+
+__global__ void pcc_flows_iota_kernel(int32_t *__restrict__ v, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+
+// History reset (mode: FLOW_RESET_*), one thread per flow.
+__global__ void pcc_flows_reset_kernel(FlowsDev p, const uint8_t *__restrict__ mask, int mode)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_flows || (mask && !mask[e])) return;
+    uint32_t fl = p.flags[e];
+    double cmin = p.conn_min[e];
+    if (mode == FLOW_RESET_NEW) { fl &= ~PCCF_HAS_MIN; cmin = 0.0; p.conn_min[e] = 0.0; }
+    const bool seen = (mode == FLOW_RESET_CLIENT) && (fl & PCCF_HAS_MIN);
+    double *hrow = p.hist + (size_t)e * p.H * p.F;
+    for (int h = 0; h < p.H; h++)
+        for (int f = 0; f < p.F; f++) {
+            const int id = p.ids[f];
+            hrow[h * p.F + f] = flow_metric_empty(id, seen, cmin) / flow_metric_scale(id);
+        }
+    p.flags[e] = fl & PCCF_HAS_MIN;     // head = 0
+    p.n_rec[e] = 0u;
+}
+
+// history.as_array() of every flow: obs[flow][H*F], oldest row first
+__global__ void pcc_flows_obs_kernel(FlowsDev p, double *__restrict__ obs)
+{
+    const int HF = p.H * p.F;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_flows * HF) return;
+    const int64_t e = i / HF;
+    const int k = (int)(i - e * HF);
+    int src = k + (int)(p.flags[e] & PCCF_HEAD_MASK) * p.F;
+    if (src >= HF) src -= HF;
+    obs[i] = p.hist[(size_t)e * HF + src];
+}
+
+// PccGymDriver.get_rate (loaded_client.py:72-76): flows that have data apply the agent's action; shim style
+// (ShimNetworkEnv.step, shim_env.py:107): every selected flow applies it.
+__global__ void pcc_flows_rate_kernel(FlowsDev p, const double *__restrict__ actions, const uint8_t *__restrict__ mask,
+                                      double *__restrict__ rates_out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_flows) return;
+    double rate = p.rate[e];
+    const bool sel = !mask || mask[e];
+    if (actions && sel && (p.rate_style == RATE_STYLE_SHIM || p.n_rec[e] != 0u)) {
+        rate = flow_apply_rate_delta(rate, actions[e], p.delta_scale, p.min_rate, p.max_rate, p.rate_style);
+        p.rate[e] = rate;
+    }
+    if (rates_out) rates_out[e] = rate;
+}
+
+__global__ void pcc_flows_set_rate_kernel(FlowsDev p, const uint8_t *__restrict__ mask, const double *__restrict__ rates,
+                                          double scalar)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_flows || (mask && !mask[e])) return;
+    p.rate[e] = rates ? rates[e] : scalar;
+}
+
+}  // namespace pccf
+
+// =========================================================================================================
+// C ABI (include/pcc_b200.h, "MI-sample ingestion")
+// =========================================================================================================
+using namespace pccf;
+
+// the agent on the device: action[flow] = MLP(history.as_array()) (loaded_agent.LoadedModelAgent.act with
+// stochastic=False, loaded_client.py:72-75), the network of stable_solve.py:30-45
+__global__ void pcc_flows_act_kernel(FlowsDev p, PolicyDev pol, double *__restrict__ actions)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_flows) return;
+    const int head = (int)(p.flags[e] & PCCF_HEAD_MASK);
+    actions[e] = policy_action(pol, p.hist + (size_t)e * p.H * p.F, head, p.H, p.F, e, 0ull);
+}
+
+struct pcc_flows_handle_s {
+    pcc_flows_config cfg;
+    FlowsDev d;
+    uint32_t batch_no;
+    int64_t launches;
+    int sm_count;
+};
+
+static void flows_layout(const pcc_flows_config *c, size_t off[8], size_t &total)
+{
+    const size_t n = (size_t)c->n_flows, HF = (size_t)c->history_len * c->n_features;
+    size_t o = 0;
+    off[0] = o; o = align_up(o + n * HF * 8);     // hist
+    off[1] = o; o = align_up(o + n * 8);          // conn_min
+    off[2] = o; o = align_up(o + n * 8);          // rate
+    off[3] = o; o = align_up(o + n * 4);          // flags
+    off[4] = o; o = align_up(o + n * 4);          // n_rec
+    off[5] = o; o = align_up(o + n * 4);          // stamp
+    off[6] = o; o = align_up(o + 64);             // meta
+    total = o;
+}
+
+static int flows_validate(const pcc_flows_config *c)
+{
+    if (!c) return fail(PCC_EINVAL, "null config");
+    if (c->abi_version != PCC_ABI_VERSION) return fail(PCC_EINVAL, "ABI version mismatch");
+    if (c->n_flows < 1 || c->n_flows > 0x7fffffffLL) return fail(PCC_EINVAL, "n_flows out of range");
+    if (c->history_len < 1 || c->history_len > PCC_MAX_HISTORY) return fail(PCC_EINVAL, "history_len out of range");
+    if (c->n_features < 1 || c->n_features > PCC_MAX_FEATURES) return fail(PCC_EINVAL, "n_features out of range");
+    for (int i = 0; i < c->n_features; i++)
+        if (c->feature_ids[i] < 0 || c->feature_ids[i] >= PCC_N_METRICS) return fail(PCC_EINVAL, "unknown feature id");
+    if (c->rate_style != PCC_RATE_CLIENT && c->rate_style != PCC_RATE_SHIM) return fail(PCC_EINVAL, "bad rate_style");
+    return PCC_OK;
+}
+
+extern "C" {
+
+void pcc_flows_default_config(pcc_flows_config *c)
+{
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->abi_version = PCC_ABI_VERSION;
+    c->history_len = 10;
+    c->n_features = 3;
+    c->feature_ids[0] = PCC_M_SENT_LATENCY_INFLATION;
+    c->feature_ids[1] = PCC_M_LATENCY_RATIO;
+    c->feature_ids[2] = PCC_M_SEND_RATIO;
+    c->delta_scale = 0.05;      /* loaded_client.py:33-35 */
+    c->min_rate = 0.5;
+    c->max_rate = 300.0;
+    c->rate_style = PCC_RATE_CLIENT;
+}
+
+int pcc_flows_workspace_bytes(const pcc_flows_config *cfg, uint64_t *bytes)
+{
+    int rc = flows_validate(cfg);
+    if (rc) return rc;
+    size_t off[8], total;
+    flows_layout(cfg, off, total);
+    if (bytes) *bytes = total;
+    return PCC_OK;
+}
+
+static int flows_build(pcc_flows_handle *out, const pcc_flows_config *cfg, void *workspace_dev, bool init)
+{
+    int rc = flows_validate(cfg);
+    if (rc) return rc;
+    if (!out || !workspace_dev || ((uintptr_t)workspace_dev & 255)) return fail(PCC_EINVAL, "bad workspace pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(PCC_ENODEV, "no CUDA device: libpcc_b200 has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    pcc_flows_handle h = new (std::nothrow) pcc_flows_handle_s();
+    if (!h) return fail(PCC_EINVAL, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    size_t off[8], total;
+    flows_layout(cfg, off, total);
+    char *b = (char *)workspace_dev;
+    FlowsDev &d = h->d;
+    d.hist = (double *)(b + off[0]); d.conn_min = (double *)(b + off[1]); d.rate = (double *)(b + off[2]);
+    d.flags = (uint32_t *)(b + off[3]); d.n_rec = (uint32_t *)(b + off[4]); d.stamp = (uint32_t *)(b + off[5]);
+    d.meta = (unsigned long long *)(b + off[6]);
+    d.n_flows = cfg->n_flows; d.H = cfg->history_len; d.F = cfg->n_features;
+    for (int i = 0; i < PCC_MAX_FEATURES; i++) d.ids[i] = i < cfg->n_features ? cfg->feature_ids[i] : 0;
+    d.touch_conn = features_touch_conn_min(d.ids, d.F) ? 1 : 0;
+    d.delta_scale = cfg->delta_scale; d.min_rate = cfg->min_rate; d.max_rate = cfg->max_rate;
+    d.rate_style = cfg->rate_style;
+    h->batch_no = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete h; return fail(PCC_ECUDA, "cudaGetDeviceProperties failed"); }
+    h->sm_count = prop.multiProcessorCount;
+    if (init) {
+        cudaError_t e = cudaMemset(b, 0, total);
+        if (e == cudaSuccess) {
+            pcc_flows_reset_kernel<<<(unsigned)((d.n_flows + 127) / 128), 128>>>(d, nullptr, FLOW_RESET_NEW);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "flows init: %s", cudaGetErrorString(e)); }
+        h->launches++;
+    }
+    *out = h;
+    return PCC_OK;
+}
+
+int pcc_flows_create(pcc_flows_handle *out, const pcc_flows_config *cfg, void *workspace_dev)
+{
+    return flows_build(out, cfg, workspace_dev, true);
+}
+int pcc_flows_attach(pcc_flows_handle *out, const pcc_flows_config *cfg, void *workspace_dev)
+{
+    return flows_build(out, cfg, workspace_dev, false);
+}
+void pcc_flows_destroy(pcc_flows_handle h) { delete h; }
+
+int pcc_flows_give_samples(pcc_flows_handle h, const pcc_mi_batch *batch, int32_t unique_flows, double *obs_dev,
+                           double *metrics_dev, void *stream)
+{
+    if (!h || !batch) return fail(PCC_EINVAL, "null pointer");
+    if (batch->n_records < 0 || batch->n_records > 0x7fffffffLL) return fail(PCC_EINVAL, "n_records out of range");
+    if (batch->n_records == 0) return PCC_OK;
+    if (!batch->flow || !batch->bytes_sent || !batch->bytes_acked || !batch->bytes_lost || !batch->packet_size ||
+        !batch->send_start || !batch->send_end || !batch->recv_start || !batch->recv_end || !batch->rtt_offsets)
+        return fail(PCC_EINVAL, "null field array in the batch");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    BatchDev b;
+    b.R = batch->n_records; b.flow = batch->flow;
+    b.bytes_sent = (const long long *)batch->bytes_sent; b.bytes_acked = (const long long *)batch->bytes_acked;
+    b.bytes_lost = (const long long *)batch->bytes_lost; b.packet_size = (const long long *)batch->packet_size;
+    b.send_start = batch->send_start; b.send_end = batch->send_end; b.recv_start = batch->recv_start;
+    b.recv_end = batch->recv_end; b.off = (const long long *)batch->rtt_offsets; b.rtt = batch->rtt_samples;
+    const int64_t R = b.R;
+    // persistent grid: 32 records per block pass, at most 8 blocks per SM
+    int64_t blocks = (R + 31) / 32;
+    const int64_t cap = (int64_t)h->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    h->batch_no++;
+    if (h->batch_no == 0) h->batch_no = 1;
+    if (unique_flows) {
+        pcc_flows_ingest_kernel<true><<<(unsigned)blocks, PCCF_THREADS, 0, st>>>(h->d, b, h->batch_no, obs_dev, metrics_dev,
+                                                                                   nullptr, nullptr);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        return PCC_OK;
+    }
+    // general batch: per-record part, stable sort of record indices by flow, per-flow sequential apply
+    const size_t F = (size_t)h->d.F;
+    const size_t rows_b = align_up((size_t)R * F * 8), avg_b = align_up((size_t)R * 8), idx_b = align_up((size_t)R * 4);
+    size_t tmp_b = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_b, (const int32_t *)nullptr, (int32_t *)nullptr,
+                                             (const int32_t *)nullptr, (int32_t *)nullptr, (int)R, 0, 32, st));
+    tmp_b = align_up(tmp_b);
+    char *scratch = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&scratch, rows_b + avg_b + 3 * idx_b + tmp_b, st));
+    double *rows = (double *)scratch;
+    double *avg = (double *)(scratch + rows_b);
+    int32_t *iota = (int32_t *)(scratch + rows_b + avg_b);
+    int32_t *sflow = (int32_t *)(scratch + rows_b + avg_b + idx_b);
+    int32_t *srec = (int32_t *)(scratch + rows_b + avg_b + 2 * idx_b);
+    void *tmp = scratch + rows_b + avg_b + 3 * idx_b;
+    pcc_flows_ingest_kernel<false><<<(unsigned)blocks, PCCF_THREADS, 0, st>>>(h->d, b, h->batch_no, nullptr, metrics_dev,
+                                                                                rows, avg);
+    pcc_flows_iota_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(iota, R);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_b, b.flow, sflow, (const int32_t *)iota, srec, (int)R, 0, 32, st);
+    if (e == cudaSuccess) {
+        pcc_flows_apply_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(h->d, R, sflow, srec, rows, avg, obs_dev, metrics_dev);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(PCC_ECUDA, "give_samples: %s", cudaGetErrorString(e));
+    h->launches += 3;   // ingest, iota, apply (+ cub's sort passes, not ours)
+    return PCC_OK;
+}
+
+int pcc_flows_reset(pcc_flows_handle h, const uint8_t *mask_dev, int32_t mode, void *stream)
+{
+    if (!h) return fail(PCC_EINVAL, "null handle");
+    if (mode < PCC_FLOW_RESET_NEW || mode > PCC_FLOW_RESET_SHIM) return fail(PCC_EINVAL, "bad reset mode");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    pcc_flows_reset_kernel<<<(unsigned)((h->d.n_flows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d, mask_dev, mode);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return PCC_OK;
+}
+
+int pcc_flows_get_obs(pcc_flows_handle h, double *obs_dev, void *stream)
+{
+    if (!h || !obs_dev) return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int64_t tot = h->d.n_flows * h->d.H * h->d.F;
+    pcc_flows_obs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d, obs_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return PCC_OK;
+}
+
+int pcc_flows_set_rates(pcc_flows_handle h, const uint8_t *mask_dev, const double *rates_dev, double rate, void *stream)
+{
+    if (!h) return fail(PCC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    pcc_flows_set_rate_kernel<<<(unsigned)((h->d.n_flows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d, mask_dev, rates_dev, rate);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return PCC_OK;
+}
+
+int pcc_flows_get_rates(pcc_flows_handle h, const double *actions_dev, const uint8_t *mask_dev, double *rates_dev,
+                        void *stream)
+{
+    if (!h) return fail(PCC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    pcc_flows_rate_kernel<<<(unsigned)((h->d.n_flows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d, actions_dev, mask_dev, rates_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return PCC_OK;
+}
+
+int pcc_flows_act(pcc_flows_handle h, const pcc_policy *policy, double *actions_dev, void *stream)
+{
+    if (!h || !policy || !policy->w1 || !actions_dev) return fail(PCC_EINVAL, "null pointer");
+    if (policy->n_in != h->d.H * h->d.F || policy->n_in > 128 || policy->h1 < 1 || policy->h1 > PCC_POLICY_MAXH ||
+        policy->h2 < 1 || policy->h2 > PCC_POLICY_MAXH)
+        return fail(PCC_EINVAL, "policy shape does not fit (n_in = history_len * n_features <= 128, hidden <= 64)");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    PolicyDev pol;
+    pol.w1 = policy->w1; pol.b1 = policy->b1; pol.w2 = policy->w2; pol.b2 = policy->b2; pol.w3 = policy->w3; pol.b3 = policy->b3;
+    pol.n_in = policy->n_in; pol.h1 = policy->h1; pol.h2 = policy->h2;
+    pol.log_std = 0.0; pol.noise_seed = 0ull; pol.stochastic = 0;      /* act(..., stochastic=False) */
+    pcc_flows_act_kernel<<<(unsigned)((h->d.n_flows + 63) / 64), 64, 0, (cudaStream_t)stream>>>(h->d, pol, actions_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return PCC_OK;
+}
+
+int pcc_flows_get_column(pcc_flows_handle h, const char *name, double *dst_dev, void *stream)
+{
+    if (!h || !name || !dst_dev) return fail(PCC_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const double *src = nullptr;
+    if (!strcmp(name, "conn_min")) src = h->d.conn_min;
+    else if (!strcmp(name, "rate")) src = h->d.rate;
+    else return fail(PCC_EINVAL, "unknown column %s", name);
+    CUDA_TRY(cudaMemcpyAsync(dst_dev, src, (size_t)h->d.n_flows * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PCC_OK;
+}
+
+int pcc_flows_check(pcc_flows_handle h, void *stream)
+{
+    if (!h) return fail(PCC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned long long meta[2];
+    CUDA_TRY(cudaMemcpy(meta, h->d.meta, sizeof(meta), cudaMemcpyDeviceToHost));
+    if (meta[1]) return fail(PCC_EINVAL, "a record named a flow index outside [0, n_flows) or a negative sample count (record ignored)");
+    if (meta[0]) return fail(PCC_EINVAL, "a batch declared unique_flows held two records of one flow (that flow's history is undefined)");
+    return PCC_OK;
+}
+
+int64_t pcc_flows_launch_count(pcc_flows_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

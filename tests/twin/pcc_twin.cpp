@@ -157,3 +157,52 @@ double twin_multi_cur_time(TwinMulti *t) { return t->net.cur_time; }
 double twin_multi_run_dur(TwinMulti *t) { return t->net.run_dur; }
 int twin_multi_ok(TwinMulti *t) { return t->ok; }
 }
+
+// ---- MI-sample ingestion (pcc_flows_core.cuh), host build: one flow, scalar ------------------------------------
+#include "../../pcc-rl_b200/csrc/pcc_flows_core.cuh"
+
+struct TwinFlow {
+    int H, F; int ids[PCC_MAX_FEATURES]; bool touch;
+    bool has_min; double conn_min;
+    std::vector<double> hist;   // [H][F], oldest first
+};
+extern "C" {
+TwinFlow *twin_flow_create(int history_len, const int *feature_ids, int n_features)
+{
+    TwinFlow *t = new TwinFlow();
+    t->H = history_len; t->F = n_features;
+    for (int i = 0; i < n_features; i++) t->ids[i] = feature_ids[i];
+    t->touch = features_touch_conn_min(t->ids, t->F);
+    t->has_min = false; t->conn_min = 0.0;
+    t->hist.assign((size_t)history_len * n_features, 0.0);
+    for (int h = 0; h < t->H; h++)
+        for (int f = 0; f < t->F; f++) t->hist[h * t->F + f] = flow_metric_empty(t->ids[f], false, 0.0) / flow_metric_scale(t->ids[f]);
+    return t;
+}
+void twin_flow_destroy(TwinFlow *t) { delete t; }
+void twin_flow_reset(TwinFlow *t, int mode)
+{
+    if (mode == FLOW_RESET_NEW) { t->has_min = false; t->conn_min = 0.0; }
+    const bool seen = (mode == FLOW_RESET_CLIENT) && t->has_min;
+    for (int h = 0; h < t->H; h++)
+        for (int f = 0; f < t->F; f++)
+            t->hist[h * t->F + f] = flow_metric_empty(t->ids[f], seen, t->conn_min) / flow_metric_scale(t->ids[f]);
+}
+void twin_flow_give_sample(TwinFlow *t, int64_t bytes_sent, int64_t bytes_acked, int64_t bytes_lost, double send_start,
+                           double send_end, double recv_start, double recv_end, const double *rtt, int64_t n,
+                           int64_t packet_size, double *metrics12)
+{
+    FlowRecord r{bytes_sent, bytes_acked, bytes_lost, packet_size, send_start, send_end, recv_start, recv_end};
+    FlowStats st;
+    flow_record_stats(r, rtt, n, t->has_min, t->conn_min, t->touch, st);
+    for (int h = 0; h + 1 < t->H; h++)
+        for (int f = 0; f < t->F; f++) t->hist[h * t->F + f] = t->hist[(h + 1) * t->F + f];
+    for (int f = 0; f < t->F; f++) t->hist[(t->H - 1) * t->F + f] = st.v[t->ids[f]] / flow_metric_scale(t->ids[f]);
+    if (metrics12) memcpy(metrics12, st.v, sizeof(st.v));
+}
+void twin_flow_get_obs(TwinFlow *t, double *obs) { memcpy(obs, t->hist.data(), sizeof(double) * t->hist.size()); }
+double twin_flow_apply_rate_delta(double rate, double action, double scale, double mn, double mx, int style)
+{
+    return flow_apply_rate_delta(rate, action, scale, mn, mx, style);
+}
+}

@@ -10,13 +10,15 @@ import oracle
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "twin", "pcc_twin.cpp")
-_CORE = os.path.join(os.path.dirname(_HERE), "pcc-rl_b200", "csrc", "pcc_core.cuh")
+_CSRC = os.path.join(os.path.dirname(_HERE), "pcc-rl_b200", "csrc")
+_CORE = os.path.join(_CSRC, "pcc_core.cuh")
+_DEPS = [os.path.join(_CSRC, f) for f in ("pcc_core.cuh", "pcc_multi_core.cuh", "pcc_flows_core.cuh")]
 _LIB = os.path.join(_HERE, "twin", "libpcc_twin.so")
 
 
 def build(force=False):
     if (not force and os.path.exists(_LIB)
-            and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in (_SRC, _CORE))):
+            and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in [_SRC] + _DEPS)):
         return _LIB
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall",
                            "-Wno-unknown-pragmas", "-o", _LIB, _SRC])
@@ -101,3 +103,48 @@ class TwinEnv(object):
     rate = property(lambda self: self.L.twin_rate(self.h))
     overflow = property(lambda self: bool(self.L.twin_overflow(self.h)))
     inflight = property(lambda self: self.L.twin_inflight(self.h))
+
+
+class TwinFlow(object):
+    """One flow of the MI-sample ingestion path: pcc_flows_core.cuh compiled for the host."""
+
+    def __init__(self, history_len=10, features=oracle.DEFAULT_FEATURES):
+        L = self.L = lib()
+        vp, d, i, q = C.c_void_p, C.c_double, C.c_int, C.c_int64
+        L.twin_flow_create.restype = vp
+        L.twin_flow_create.argtypes = [i, C.POINTER(C.c_int), i]
+        L.twin_flow_destroy.argtypes = [vp]
+        L.twin_flow_reset.argtypes = [vp, i]
+        L.twin_flow_give_sample.argtypes = [vp, q, q, q, d, d, d, d, C.POINTER(d), q, q, C.POINTER(d)]
+        L.twin_flow_get_obs.argtypes = [vp, C.POINTER(d)]
+        L.twin_flow_apply_rate_delta.restype = d
+        L.twin_flow_apply_rate_delta.argtypes = [d, d, d, d, d, i]
+        ids = np.asarray(oracle.feature_ids(features), dtype=np.int32)
+        self.hf = history_len * len(ids)
+        self.h = L.twin_flow_create(history_len, ids.ctypes.data_as(C.POINTER(C.c_int)), len(ids))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.twin_flow_destroy(self.h)
+            self.h = None
+
+    def reset(self, mode):
+        self.L.twin_flow_reset(self.h, mode)
+
+    def give_sample(self, r):
+        rtt = np.ascontiguousarray(r["rtt"], dtype=np.float64)
+        m = np.zeros(12)
+        self.L.twin_flow_give_sample(self.h, r["bytes_sent"], r["bytes_acked"], r["bytes_lost"], r["send_start"],
+                                     r["send_end"], r["recv_start"], r["recv_end"],
+                                     rtt.ctypes.data_as(C.POINTER(C.c_double)), rtt.size, r["packet_size"],
+                                     m.ctypes.data_as(C.POINTER(C.c_double)))
+        return m
+
+    def obs(self):
+        o = np.zeros(self.hf)
+        self.L.twin_flow_get_obs(self.h, o.ctypes.data_as(C.POINTER(C.c_double)))
+        return o
+
+    def apply_rate_delta(self, rate, action, cfg):
+        return self.L.twin_flow_apply_rate_delta(rate, action, cfg["delta_scale"], cfg["min_rate"], cfg["max_rate"],
+                                                 cfg["style"])
