@@ -217,6 +217,28 @@ int pcc_multi_step(pcc_multi_handle h, const double *actions_dev /*[n][S]*/, dou
                    void *stream);
 int pcc_multi_check(pcc_multi_handle h, void *stream);
 
+/* The two variants of the event loop that the reference compiles out behind module switches:
+ *   use_cwnd           USE_CWND = True  (network_sim.py:54): congestion window, Sender.can_send_packet :251-255,
+ *                      apply_cwnd_delta / set_cwnd :243-249, 283-289, second action component :413-414
+ *   use_latency_noise  USE_LATENCY_NOISE = True (:51-52): every hop's latency times random.uniform(1.0, 1.1), :150-151, 171-172
+ * They run on the generic heap path (n_senders = 1 is the reference's own single-sender env with the switch on).
+ * Set before pcc_multi_reset. */
+typedef struct pcc_variant {
+    int32_t use_cwnd;
+    int32_t use_latency_noise;
+    double max_latency_noise;   /* MAX_LATENCY_NOISE 1.1 (:52) */
+    int32_t initial_cwnd;       /* 25   (Sender.__init__, :209) */
+    int32_t min_cwnd;           /* MIN_CWND 4    (:34) */
+    int32_t max_cwnd;           /* MAX_CWND 5000 (:33) */
+    int32_t reserved0;
+} pcc_variant;
+void pcc_default_variant(pcc_variant *v);   /* both switches off, the reference's constants */
+int pcc_multi_set_variant(pcc_multi_handle h, const pcc_variant *v);
+/* pcc_multi_step with the window action: cwnd_actions_dev double[n][S] (NULL = leave the windows alone),
+ * cwnd_dev int32[n][S] (optional) = the windows after the update. */
+int pcc_multi_step_cwnd(pcc_multi_handle h, const double *actions_dev, const double *cwnd_actions_dev, double *obs_dev,
+                        double *reward_dev, uint8_t *done_dev, int32_t *counts_dev, int32_t *cwnd_dev, void *stream);
+
 /* ---- MI-sample ingestion ("flow monitor") -------------------------------------------
  * The other producer of SenderMonitorIntervals: records measured on REAL flows by the PCC sender, handed to
  * Python one at a time and turned into the agent's observation:

@@ -70,6 +70,11 @@ def lib():
     L.pcco_total_events.argtypes = [vp]
     L.pcco_reset_multi.argtypes = [vp, i, d, d, l, d, pd]
     L.pcco_step_multi.argtypes = [vp, pd, pd, pd, pi, pl]
+    L.pcco_set_variant.argtypes = [vp, i, i]
+    L.pcco_cwnd.restype = l
+    L.pcco_cwnd.argtypes = [vp, i]
+    L.pcco_step_cwnd.argtypes = [vp, d, d, pd, pd, pi, pl, pd]
+    L.pcco_step_multi_cwnd.argtypes = [vp, pd, pd, pd, pd, pi, pl]
     L.pcco_np_mean.restype = d
     L.pcco_np_mean.argtypes = [pd, l]
     L.pcco_batch_run.restype = d
@@ -132,6 +137,19 @@ class OracleEnv(object):
     def set_max_steps(self, n):
         self.L.pcco_set_max_steps(self.h, n)
 
+    def set_variant(self, use_cwnd=False, use_latency_noise=False):
+        """The reference's module switches USE_CWND / USE_LATENCY_NOISE (network_sim.py:51-54)."""
+        self.L.pcco_set_variant(self.h, int(use_cwnd), int(use_latency_noise))
+
+    def cwnd(self, sender=0):
+        return self.L.pcco_cwnd(self.h, sender)
+
+    def step_cwnd(self, action, cwnd_action):
+        r, dn = C.c_double(), C.c_int()
+        self.L.pcco_step_cwnd(self.h, float(action), float(cwnd_action), _p(self._obs, C.c_double), C.byref(r),
+                              C.byref(dn), _p(self._counts, C.c_long), _p(self._info, C.c_double))
+        return self._obs.copy(), r.value, bool(dn.value), self._counts.copy(), self._info.copy()
+
     def sample_params(self, bw=(100, 500), lat=(0.05, 0.5), queue=(0, 8), loss=(0.0, 0.05)):
         """The five draws of create_new_links_and_senders (network_sim.py:455-466), taken from
         this env's own stream, in the reference's order."""
@@ -159,9 +177,18 @@ class OracleEnv(object):
         self.n_senders = len(r)
         self.L.pcco_reset_multi(self.h, len(r), bw, lat, int(queue), loss, _p(r, C.c_double))
 
-    def step_multi(self, actions):
+    def step_multi(self, actions, cwnd_actions=None):
         S = self.n_senders
         a = np.ascontiguousarray(actions, dtype=np.float64)
+        if cwnd_actions is not None:
+            ca = np.ascontiguousarray(cwnd_actions, dtype=np.float64)
+            obs = np.zeros((S, self.history_len * self.n_features))
+            rew = np.zeros(S)
+            cnt = np.zeros((S, 3), dtype=np.int64)
+            dn = C.c_int()
+            self.L.pcco_step_multi_cwnd(self.h, _p(a, C.c_double), _p(ca, C.c_double), _p(obs, C.c_double),
+                                        _p(rew, C.c_double), C.byref(dn), _p(cnt, C.c_long))
+            return obs, rew, bool(dn.value), cnt
         obs = np.zeros((S, self.history_len * self.n_features))
         rew = np.zeros(S)
         cnt = np.zeros((S, 3), dtype=np.int64)

@@ -47,6 +47,11 @@
 #define BYTES_PER_PACKET 1500
 /* common/config.py:17 */
 #define DELTA_SCALE 0.025
+/* the compiled-out variants of the same loop (network_sim.py:33-34, 51-54): congestion window and latency noise */
+#define MAX_CWND 5000
+#define MIN_CWND 4
+#define MAX_LATENCY_NOISE 1.1
+#define INITIAL_CWND 25      /* Sender.__init__ default, network_sim.py:209 */
 
 /* ------------------------------------------------------------------------------------ */
 /* RNG streams                                                                          */
@@ -247,6 +252,8 @@ typedef struct {
     /* _conn_min_latencies[sender_id] (sender_obs.py:158): has_min == key present */
     int has_min; double conn_min;
     pcco_mi_row hist[PCCO_MAX_HISTORY];
+    long cwnd;               /* :225, int after set_cwnd (:283-289) */
+    long bytes_in_flight;    /* :215, +-BYTES_PER_PACKET on sent / acked / lost (:260-273) */
 } pcco_sender;
 
 /* metric ids = position in SENDER_MI_METRICS (sender_obs.py:193-206) */
@@ -418,6 +425,8 @@ typedef struct pcco_env {
     long steps_taken;
     long max_steps;
     long long total_events; /* heap pops, for events/s reporting */
+    int use_cwnd;           /* USE_CWND (:54); the reference ships False */
+    int use_latency_noise;  /* USE_LATENCY_NOISE (:51); the reference ships False */
 } pcco_env;
 
 pcco_env *pcco_create(int history_len, const int *feature_ids, int n_features)
@@ -447,6 +456,14 @@ void pcco_destroy(pcco_env *e)
 }
 
 void pcco_set_max_steps(pcco_env *e, long n) { e->max_steps = n; }
+
+/* The module-level switches USE_CWND / USE_LATENCY_NOISE of network_sim.py:51-54 (both False as shipped). */
+void pcco_set_variant(pcco_env *e, int use_cwnd, int use_latency_noise)
+{
+    e->use_cwnd = use_cwnd;
+    e->use_latency_noise = use_latency_noise;
+}
+long pcco_cwnd(const pcco_env *e, int sender) { return e->senders[sender].cwnd; }
 
 /* random.seed(int) of CPython: init_by_array over the 32-bit little-endian limbs of |seed| */
 void pcco_seed_mt(pcco_env *e, uint64_t seed)
@@ -511,6 +528,32 @@ static void sender_apply_rate_delta(pcco_sender *s, double delta) /* :235-241 */
     else sender_set_rate(s, s->rate / (1.0 - delta));
 }
 
+static void sender_set_cwnd(pcco_sender *s, double new_cwnd) /* :283-289 */
+{
+    s->cwnd = (long)new_cwnd;                /* int(): truncation toward zero */
+    if (s->cwnd > MAX_CWND) s->cwnd = MAX_CWND;
+    if (s->cwnd < MIN_CWND) s->cwnd = MIN_CWND;
+}
+
+static void sender_apply_cwnd_delta(pcco_sender *s, double delta) /* :243-249 */
+{
+    delta *= DELTA_SCALE;
+    if (delta >= 0.0) sender_set_cwnd(s, (double)s->cwnd * (1.0 + delta));
+    else sender_set_cwnd(s, (double)s->cwnd / (1.0 - delta));
+}
+
+static int sender_can_send_packet(const pcco_env *e, const pcco_sender *s) /* :251-255 */
+{
+    if (e->use_cwnd) return (double)s->bytes_in_flight / (double)BYTES_PER_PACKET < (double)s->cwnd;
+    return 1;
+}
+
+/* random.uniform(1.0, MAX_LATENCY_NOISE) = a + (b - a) * random() (CPython Lib/random.py) */
+static double latency_noise(pcco_env *e)
+{
+    return 1.0 + (MAX_LATENCY_NOISE - 1.0) * rng_random(&e->rng);
+}
+
 static pcco_mi sender_get_run_data(const pcco_env *e, const pcco_sender *s) /* :298-317 */
 {
     pcco_mi m;
@@ -545,9 +588,11 @@ static double run_for_dur(pcco_env *e, double dur)
                     sender->acked += 1;
                     sender_append_rtt(sender, ev.cur_latency);
                 }
+                sender->bytes_in_flight -= BYTES_PER_PACKET;   /* :269, :273 */
             } else {                                /* :147-154 */
                 nw.next_hop = ev.next_hop + 1;
                 double link_latency = link_cur_latency(&e->links[ev.next_hop], e->cur_time);
+                if (e->use_latency_noise) link_latency *= latency_noise(e);   /* :150-151 */
                 nw.cur_latency += link_latency;
                 nw.time += link_latency;
                 push_new_event = 1;
@@ -555,9 +600,11 @@ static double run_for_dur(pcco_env *e, double dur)
         }
         if (ev.type == 1) { /* SEND :155 */
             if (ev.next_hop == 0) {                 /* :156 */
-                /* can_send_packet() is True with USE_CWND = False (:243-247) */
-                sender->sent += 1;                  /* :159-160, :260-262 */
-                push_new_event = 1;
+                if (sender_can_send_packet(e, sender)) {   /* :158; always True as shipped */
+                    sender->sent += 1;              /* :159-160, :260-262 */
+                    sender->bytes_in_flight += BYTES_PER_PACKET;
+                    push_new_event = 1;
+                }
                 pcco_event timer = {e->cur_time + (1.0 / sender->rate), ev.sender, 1, 0, 0.0, 0};
                 heap_push(&e->q, timer);            /* :161 */
             } else {
@@ -566,6 +613,7 @@ static double run_for_dur(pcco_env *e, double dur)
             if (ev.next_hop == 0) nw.type = 0;      /* next_hop == sender.dest (== 0) :166-167 */
             nw.next_hop = ev.next_hop + 1;          /* :168 */
             double link_latency = link_cur_latency(&e->links[ev.next_hop], e->cur_time); /* :170 */
+            if (e->use_latency_noise) link_latency *= latency_noise(e);                  /* :171-172 */
             nw.cur_latency += link_latency;         /* :173 */
             nw.time += link_latency;                /* :174 */
             nw.dropped = !link_packet_enters(&e->links[ev.next_hop], e->cur_time, &e->rng); /* :175 */
@@ -590,6 +638,7 @@ void pcco_reset(pcco_env *e, double bw, double lat, long queue_size, double loss
     e->n_senders = 1;
     pcco_sender *s = &e->senders[0];                      /* :466 */
     s->rate = start_rate; s->starting_rate = start_rate;
+    s->cwnd = INITIAL_CWND; s->bytes_in_flight = 0;       /* a fresh Sender (:209-226) */
     s->has_min = 0; s->conn_min = 0.0;                    /* fresh sender id => no dict entry */
     for (int h = 0; h < e->history_len; h++)              /* SenderHistory.__init__ sender_obs.py:57-62 */
         for (int f = 0; f < e->n_features; f++) {
@@ -619,11 +668,28 @@ void pcco_get_obs(const pcco_env *e, double *obs) /* _get_all_sender_obs :400-40
  * counts[3] = sent, acked, lost of this MI; info[8] = reward's three inputs and the event-log
  * fields: send rate, throughput (recv rate), avg latency, loss ratio, latency inflation,
  * latency ratio, send ratio, MI duration. */
+static void step_impl(pcco_env *e, double action, double cwnd_action, double *obs, double *reward, int *done,
+                      long *counts, double *info);
+
 void pcco_step(pcco_env *e, double action, double *obs, double *reward, int *done,
                long *counts, double *info)
 {
+    step_impl(e, action, 0.0, obs, reward, done, counts, info);
+}
+
+/* step([rate_action, cwnd_action]) of the USE_CWND variant (:409-414) */
+void pcco_step_cwnd(pcco_env *e, double action, double cwnd_action, double *obs, double *reward, int *done,
+                    long *counts, double *info)
+{
+    step_impl(e, action, cwnd_action, obs, reward, done, counts, info);
+}
+
+static void step_impl(pcco_env *e, double action, double cwnd_action, double *obs, double *reward, int *done,
+                      long *counts, double *info)
+{
     pcco_sender *s = &e->senders[0];
     sender_apply_rate_delta(s, action);                   /* :412 */
+    if (e->use_cwnd) sender_apply_cwnd_delta(s, cwnd_action);   /* :413-414 */
     double r = run_for_dur(e, e->run_dur);                /* :416 */
     /* record_run (:418 -> :291-293): features are memoised per MI object the first time the
      * history is turned into an array (sender_obs.py:44-54, 68-73). */
@@ -693,6 +759,7 @@ void pcco_reset_multi(pcco_env *e, int n_senders, double bw, double lat, long qu
     for (int i = 0; i < n_senders; i++) {
         pcco_sender *s = &e->senders[i];
         s->rate = start_rates[i]; s->starting_rate = start_rates[i];
+        s->cwnd = INITIAL_CWND; s->bytes_in_flight = 0;
         s->has_min = 0; s->conn_min = 0.0;
         for (int h = 0; h < e->history_len; h++)
             for (int f = 0; f < e->n_features; f++) {
@@ -709,10 +776,25 @@ void pcco_reset_multi(pcco_env *e, int n_senders, double bw, double lat, long qu
 }
 
 /* obs [S][H*F], rewards [S], counts [S][3] */
+static void step_multi_impl(pcco_env *e, const double *actions, const double *cwnd_actions, double *obs, double *rewards,
+                            int *done, long *counts);
 void pcco_step_multi(pcco_env *e, const double *actions, double *obs, double *rewards, int *done, long *counts)
 {
+    step_multi_impl(e, actions, NULL, obs, rewards, done, counts);
+}
+void pcco_step_multi_cwnd(pcco_env *e, const double *actions, const double *cwnd_actions, double *obs, double *rewards,
+                          int *done, long *counts)
+{
+    step_multi_impl(e, actions, cwnd_actions, obs, rewards, done, counts);
+}
+static void step_multi_impl(pcco_env *e, const double *actions, const double *cwnd_actions, double *obs, double *rewards,
+                            int *done, long *counts)
+{
     const int hf = e->history_len * e->n_features;
-    for (int i = 0; i < e->n_senders; i++) sender_apply_rate_delta(&e->senders[i], actions[i]);
+    for (int i = 0; i < e->n_senders; i++) {
+        sender_apply_rate_delta(&e->senders[i], actions[i]);
+        if (e->use_cwnd && cwnd_actions) sender_apply_cwnd_delta(&e->senders[i], cwnd_actions[i]);
+    }
     run_for_dur(e, e->run_dur);
     double avg0 = 0.0;
     for (int i = 0; i < e->n_senders; i++) {

@@ -30,6 +30,11 @@ class PccPolicy(C.Structure):
                 ("h2", C.c_int32), ("stochastic", C.c_int32), ("log_std", C.c_double), ("noise_seed", C.c_uint64)]
 
 
+class PccVariant(C.Structure):
+    _fields_ = [("use_cwnd", C.c_int32), ("use_latency_noise", C.c_int32), ("max_latency_noise", C.c_double),
+                ("initial_cwnd", C.c_int32), ("min_cwnd", C.c_int32), ("max_cwnd", C.c_int32), ("reserved0", C.c_int32)]
+
+
 class PccFlowsConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_flows", C.c_int64),
                 ("history_len", C.c_int32), ("n_features", C.c_int32),
@@ -62,6 +67,7 @@ EXPORTS = ["pcc_default_consts", "pcc_default_config", "pcc_ring_capacity_for", 
            "pcc_reset", "pcc_step", "pcc_step_host", "pcc_rollout", "pcc_check", "pcc_get_column", "pcc_launch_count",
            "pcc_last_error", "pcc_abi_version", "pcc_multi_workspace_bytes", "pcc_multi_create", "pcc_multi_destroy",
            "pcc_multi_seed", "pcc_multi_reset", "pcc_multi_step", "pcc_multi_check",
+           "pcc_default_variant", "pcc_multi_set_variant", "pcc_multi_step_cwnd",
            "pcc_flows_default_config", "pcc_flows_workspace_bytes", "pcc_flows_create", "pcc_flows_attach",
            "pcc_flows_destroy", "pcc_flows_give_samples", "pcc_flows_reset", "pcc_flows_get_obs", "pcc_flows_set_rates",
            "pcc_flows_get_rates", "pcc_flows_act", "pcc_flows_get_column", "pcc_flows_check", "pcc_flows_launch_count"]
@@ -113,6 +119,10 @@ def load(rebuild_if_stale=True):
     L.pcc_multi_reset.argtypes = [vp, u8p, dp, dp, vp, dp, dp, dp, vp]
     L.pcc_multi_step.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
     L.pcc_multi_check.argtypes = [vp, vp]
+    L.pcc_default_variant.argtypes = [C.POINTER(PccVariant)]
+    L.pcc_default_variant.restype = None
+    L.pcc_multi_set_variant.argtypes = [vp, C.POINTER(PccVariant)]
+    L.pcc_multi_step_cwnd.argtypes = [vp, dp, dp, dp, dp, u8p, vp, vp, vp]
     L.pcc_flows_default_config.argtypes = [C.POINTER(PccFlowsConfig)]
     L.pcc_flows_default_config.restype = None
     L.pcc_flows_workspace_bytes.argtypes = [C.POINTER(PccFlowsConfig), C.POINTER(C.c_uint64)]

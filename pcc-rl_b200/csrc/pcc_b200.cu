@@ -1510,6 +1510,7 @@ struct MultiDev {
     int32_t ids[PCC_MAX_FEATURES];
     int32_t need_inc;
     Consts c;
+    Variant v;
 };
 struct DevHeap {
     MEvent *base; int cap;
@@ -1534,7 +1535,7 @@ __global__ void pcc_multi_reset_kernel(MultiDev p, const uint8_t *__restrict__ m
     double r[PCC_MAX_SENDERS];
     for (int i = 0; i < p.S; i++) r[i] = rates[(size_t)e * p.S + i];
     const bool ok = multi_reset(net, snd, p.S, heap, p.samples + (size_t)e * p.S * p.cap_s, p.cap_s, rng, bw[e], delay[e],
-                                (int64_t)queue[e], loss[e], r);
+                                (int64_t)queue[e], loss[e], r, p.v);
     me.net = net;
     for (int i = 0; i < p.S; i++) me.snd[i] = snd[i];
     me.draws = rng.draws;
@@ -1549,8 +1550,9 @@ __global__ void pcc_multi_reset_kernel(MultiDev p, const uint8_t *__restrict__ m
 }
 
 __global__ void pcc_multi_step_kernel(MultiDev p, unsigned long long head_step, const double *__restrict__ actions,
+                                      const double *__restrict__ cwnd_actions,
                                       double *__restrict__ obs, double *__restrict__ reward, uint8_t *__restrict__ done,
-                                      int32_t *__restrict__ counts)
+                                      int32_t *__restrict__ counts, int32_t *__restrict__ cwnd_out)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n) return;
@@ -1561,12 +1563,16 @@ __global__ void pcc_multi_step_kernel(MultiDev p, unsigned long long head_step, 
     PhiloxRng rng;
     rng.init(me.seed, me.draws);
     DevHeap heap{p.heaps + (size_t)e * p.heap_cap, p.heap_cap};
-    double acts[PCC_MAX_SENDERS], rows[PCC_MAX_SENDERS * PCC_MAX_FEATURES], rew[PCC_MAX_SENDERS];
+    double acts[PCC_MAX_SENDERS], cacts[PCC_MAX_SENDERS], rows[PCC_MAX_SENDERS * PCC_MAX_FEATURES], rew[PCC_MAX_SENDERS];
     int32_t cnt[PCC_MAX_SENDERS * 3];
-    for (int i = 0; i < p.S; i++) acts[i] = actions[(size_t)e * p.S + i];
+    for (int i = 0; i < p.S; i++) {
+        acts[i] = actions[(size_t)e * p.S + i];
+        cacts[i] = cwnd_actions ? cwnd_actions[(size_t)e * p.S + i] : 0.0;
+    }
     bool dn;
-    const bool ok = multi_step(net, snd, p.S, heap, p.samples + (size_t)e * p.S * p.cap_s, p.cap_s, rng, acts, p.c, p.ids,
-                               p.F, p.need_inc != 0, rows, rew, cnt, dn);
+    const bool ok = multi_step(net, snd, p.S, heap, p.samples + (size_t)e * p.S * p.cap_s, p.cap_s, rng, acts,
+                               cwnd_actions ? cacts : nullptr, p.c, p.v, p.ids, p.F, p.need_inc != 0, rows, rew, cnt, dn);
+    if (cwnd_out) for (int i = 0; i < p.S; i++) cwnd_out[(size_t)e * p.S + i] = snd[i].cwnd;
     me.net = net;
     for (int i = 0; i < p.S; i++) me.snd[i] = snd[i];
     me.draws = rng.draws;
@@ -1655,6 +1661,7 @@ int pcc_multi_create(pcc_multi_handle *out, const pcc_config *cfg, int32_t n_sen
     d.c.max_rate = cfg->consts.max_rate; d.c.min_rate = cfg->consts.min_rate; d.c.delta_scale = cfg->consts.delta_scale;
     d.c.reward_scale = cfg->consts.reward_scale; d.c.max_steps = cfg->consts.max_steps;
     d.c.bytes_per_packet = cfg->consts.bytes_per_packet;
+    d.v = default_variant();
     cudaError_t e = cudaMemset(b + off[0], 0, off[1] - off[0]);
     if (e == cudaSuccess) e = cudaMemset(b + off[4], 0, 64);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1686,15 +1693,41 @@ int pcc_multi_reset(pcc_multi_handle h, const uint8_t *mask_dev, const double *b
     return PCC_OK;
 }
 
+int pcc_multi_step_cwnd(pcc_multi_handle h, const double *actions_dev, const double *cwnd_actions_dev, double *obs_dev,
+                        double *reward_dev, uint8_t *done_dev, int32_t *counts_dev, int32_t *cwnd_dev, void *stream)
+{
+    if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(PCC_EINVAL, "null pointer");
+    if (cwnd_actions_dev && !h->d.v.use_cwnd) return fail(PCC_EINVAL, "cwnd actions given but use_cwnd is off (pcc_multi_set_variant)");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    pcc_multi_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
+        h->d, h->head, actions_dev, cwnd_actions_dev, obs_dev, reward_dev, done_dev, counts_dev, cwnd_dev);
+    h->head++;
+    CUDA_TRY(cudaGetLastError());
+    return PCC_OK;
+}
+
 int pcc_multi_step(pcc_multi_handle h, const double *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev,
                    int32_t *counts_dev, void *stream)
 {
-    if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(PCC_EINVAL, "null pointer");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    pcc_multi_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
-        h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev);
-    h->head++;
-    CUDA_TRY(cudaGetLastError());
+    return pcc_multi_step_cwnd(h, actions_dev, nullptr, obs_dev, reward_dev, done_dev, counts_dev, nullptr, stream);
+}
+
+void pcc_default_variant(pcc_variant *v)
+{
+    if (!v) return;
+    memset(v, 0, sizeof(*v));
+    v->max_latency_noise = 1.1; v->initial_cwnd = 25; v->min_cwnd = 4; v->max_cwnd = 5000;
+}
+
+int pcc_multi_set_variant(pcc_multi_handle h, const pcc_variant *v)
+{
+    if (!h || !v) return fail(PCC_EINVAL, "null pointer");
+    if (v->min_cwnd < 1 || v->max_cwnd < v->min_cwnd || v->max_cwnd > (1 << 30) || v->initial_cwnd < 1 ||
+        !(v->max_latency_noise >= 1.0))
+        return fail(PCC_EINVAL, "bad variant constants");
+    h->d.v.use_cwnd = v->use_cwnd ? 1 : 0; h->d.v.use_noise = v->use_latency_noise ? 1 : 0;
+    h->d.v.max_noise = v->max_latency_noise; h->d.v.initial_cwnd = v->initial_cwnd;
+    h->d.v.min_cwnd = v->min_cwnd; h->d.v.max_cwnd = v->max_cwnd;
     return PCC_OK;
 }
 

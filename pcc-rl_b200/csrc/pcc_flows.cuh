@@ -23,6 +23,9 @@ namespace pccf {
 using namespace pcc;
 
 #define PCCF_THREADS 256
+#ifndef PCCF_MINBLOCKS
+#define PCCF_MINBLOCKS 3      // 80 registers, no spills (64 registers spill in the hot loop)
+#endif
 #define PCCF_FULL 0xffffffffu
 #define PCCF_HEAD_MASK 0xffu
 #define PCCF_HAS_MIN 0x100u
@@ -69,6 +72,47 @@ __device__ __forceinline__ double sg_leaf(const double *__restrict__ a, int n, i
     r += __shfl_xor_sync(mask, r, 4);
     for (int k = nb; k < n; k++) r += __ldg(a + k);
     return r;
+}
+
+// numpy's pairwise sum of a[0..n), n <= PCCF_SG_MAX_N, by ONE subgroup (subgroup-uniform control flow and result).
+// Iterative post-order walk of the recursion (n > 128: n2 = n/2 rounded down to a multiple of 8; sum(left n2) +
+// sum(right n - n2)); leaves tile [0, n) left to right.  A node at depth d holds at most n/2^d + 15 elements, so
+// for n <= 1800 the walk is at most 4 frames deep: the frames live in registers (selected by compare chains),
+// not in local memory.  Longer lists go to warp_pw_sum.
+#define PCCF_SG_MAX_N 1800
+__device__ __forceinline__ double sg_pw_sum(const double *__restrict__ a, int n, int j, unsigned mask)
+{
+    if (n <= 128) return sg_leaf(a, n, j, mask);
+    int rn0 = 0, rn1 = 0, rn2 = 0, rn3 = 0;          // right-child sizes of the open frames
+    double ls0 = 0., ls1 = 0., ls2 = 0., ls3 = 0.;   // left-child sums of the open frames
+    unsigned have_left = 0u;
+    int sp = 0, cur = n;
+    const double *p = a;
+    for (;;) {
+        while (cur > 128) {
+            int n2 = cur >> 1;
+            n2 -= n2 & 7;
+            const int rn = cur - n2;
+            if (sp == 0) rn0 = rn; else if (sp == 1) rn1 = rn; else if (sp == 2) rn2 = rn; else rn3 = rn;
+            have_left &= ~(1u << sp);
+            sp++;
+            cur = n2;
+        }
+        double res = sg_leaf(p, cur, j, mask);
+        p += cur;
+        for (;;) {
+            if (sp == 0) return res;
+            const int t = sp - 1;
+            if (!((have_left >> t) & 1u)) {
+                if (t == 0) ls0 = res; else if (t == 1) ls1 = res; else if (t == 2) ls2 = res; else ls3 = res;
+                have_left |= 1u << t;
+                cur = (t == 0) ? rn0 : (t == 1) ? rn1 : (t == 2) ? rn2 : rn3;
+                break;
+            }
+            res = ((t == 0) ? ls0 : (t == 1) ? ls1 : (t == 2) ? ls2 : ls3) + res;
+            sp--;
+        }
+    }
 }
 
 // numpy's pairwise sum of a[0..n) for any n, by the whole warp (warp-uniform control flow and result).
@@ -156,7 +200,7 @@ __device__ __noinline__ double warp_pw_sum(const double *__restrict__ a, long lo
 // order.
 // ---------------------------------------------------------------------------------------------------------
 template <bool UNIQUE>
-__global__ void __launch_bounds__(PCCF_THREADS, 2)
+__global__ void __launch_bounds__(PCCF_THREADS, PCCF_MINBLOCKS)
 pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__restrict__ obs, double *__restrict__ metrics,
                         double *__restrict__ rows, double *__restrict__ avg_out)
 {
@@ -171,17 +215,12 @@ pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__res
     for (long long base = warp * 4; base < b.R; base += nwarps * 4) {      // warp-uniform
         const long long r = base + sg;
         const bool valid = r < b.R;
-        long long n = 0, bs = 0, ba = 0, bl = 0, ps = 0;
-        double ss = 0., se = 0., rs = 0., re = 0.;
+        long long n = 0;
         const double *a = b.rtt;
         int flow = 0;
         if (valid) {
             const long long o0 = __ldg(b.off + r), o1 = __ldg(b.off + r + 1);
             n = o1 - o0; a = b.rtt + o0;
-            bs = __ldg(b.bytes_sent + r); ba = __ldg(b.bytes_acked + r); bl = __ldg(b.bytes_lost + r);
-            ps = __ldg(b.packet_size + r);
-            ss = __ldg(b.send_start + r); se = __ldg(b.send_end + r);
-            rs = __ldg(b.recv_start + r); re = __ldg(b.recv_end + r);
             flow = __ldg(b.flow + r);
         }
         bool good = valid && flow >= 0 && (long long)flow < p.n_flows && n >= 0;
@@ -189,25 +228,29 @@ pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__res
         if (!good) n = 0;
         const long long half = n / 2;
 
-        // ---- the three pairwise sums -------------------------------------------------------------------
+        // ---- the three pairwise sums (all, first half, second half): one code site, three passes ------------
+        // Passes 2 and 3 re-read the samples the first pass pulled from HBM (L1/L2 hits; numpy's summation trees
+        // of the three ranges share nothing, so the sums cannot be shared either).
         double sum = 0.0, s1 = 0.0, s2 = 0.0;
-        if (good && n > 0 && n <= 128) {
-            sum = sg_leaf(a, (int)n, j, sgmask);
-            if (half >= 1) {
-                s1 = sg_leaf(a, (int)half, j, sgmask);
-                s2 = sg_leaf(a + half, (int)(n - half), j, sgmask);
+        if (n > PCCF_SG_MAX_N) good = false;      // a very long sample list: left to pcc_flows_long_kernel
+        const bool in_sg = good && n > 0;
+#pragma unroll 1
+        for (int q = 0; q < 3; q++) {
+            const long long lo = (q == 2) ? half : 0;
+            const long long len = (q == 0) ? n : (q == 1) ? half : n - half;
+            if (in_sg && (q == 0 || half >= 1)) {
+                const double v = sg_pw_sum(a + lo, (int)len, j, sgmask);
+                if (q == 0) sum = v; else if (q == 1) s1 = v; else s2 = v;
             }
         }
-        unsigned bigmask = __ballot_sync(PCCF_FULL, good && n > 128 && j == 0);
-        while (bigmask) {                                                   // warp-uniform
-            const int src = __ffs(bigmask) - 1;
-            bigmask &= bigmask - 1;
-            const double *aa = (const double *)__shfl_sync(PCCF_FULL, (unsigned long long)a, src);
-            const long long nn = __shfl_sync(PCCF_FULL, n, src);
-            const double t0 = warp_pw_sum(aa, nn);
-            const double t1 = warp_pw_sum(aa, nn / 2);
-            const double t2 = warp_pw_sum(aa + nn / 2, nn - nn / 2);
-            if (sg0 == src) { sum = t0; s1 = t1; s2 = t2; }
+        // ---- the record's scalar fields (loaded after the sums: they are not live across the sample passes) --
+        long long bs = 0, ba = 0, bl = 0, ps = 0;
+        double ss = 0., se = 0., rs = 0., re = 0.;
+        if (good) {
+            bs = __ldg(b.bytes_sent + r); ba = __ldg(b.bytes_acked + r); bl = __ldg(b.bytes_lost + r);
+            ps = __ldg(b.packet_size + r);
+            ss = __ldg(b.send_start + r); se = __ldg(b.send_end + r);
+            rs = __ldg(b.recv_start + r); re = __ldg(b.recv_end + r);
         }
 
         // ---- round 1 of divisions: one per lane (sender_obs.py:110-142) ---------------------------------
@@ -312,6 +355,80 @@ pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__res
                 rows[(size_t)r * F + f] = (id == M_SEND_RATE) ? send_rate_s : (id == M_RECV_RATE) ? recv_rate_s : raw(id);
             }
             if (j == 0) avg_out[r] = avg;
+        }
+    }
+}
+
+// Records with more than PCCF_SG_MAX_N samples (rare): one warp per record, numpy's recursion walked by the whole
+// warp (warp_pw_sum), the scalar part by the core's flow_stats_finish on every lane redundantly.  Launched after
+// the ingest kernel on the same stream; a warp looks at 32 consecutive records and usually finds nothing.
+template <bool UNIQUE>
+__global__ void __launch_bounds__(128)
+pcc_flows_long_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__restrict__ obs, double *__restrict__ metrics,
+                      double *__restrict__ rows, double *__restrict__ avg_out)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int H = p.H, F = p.F, HF = H * F;
+    for (long long base = warp * 32; base < b.R; base += nwarps * 32) {
+        const long long mine = base + lane;
+        bool is_long = false;
+        if (mine < b.R) {
+            const long long nn = __ldg(b.off + mine + 1) - __ldg(b.off + mine);
+            const int fl = __ldg(b.flow + mine);
+            is_long = nn > PCCF_SG_MAX_N && fl >= 0 && (long long)fl < p.n_flows;
+        }
+        unsigned m = __ballot_sync(PCCF_FULL, is_long);
+        while (m) {                                                          // warp-uniform
+            const long long r = base + (__ffs(m) - 1);
+            m &= m - 1;
+            const long long o0 = __ldg(b.off + r), n = __ldg(b.off + r + 1) - o0;
+            const double *a = b.rtt + o0;
+            const long long half = n / 2;
+            const double sum = warp_pw_sum(a, n), s1 = warp_pw_sum(a, half), s2 = warp_pw_sum(a + half, n - half);
+            const double avg = (0.0 + sum) / (double)n;
+            const double m1 = (0.0 + s1) / (double)half, m2 = (0.0 + s2) / (double)(n - half);
+            FlowRecord rec;
+            rec.bytes_sent = __ldg(b.bytes_sent + r); rec.bytes_acked = __ldg(b.bytes_acked + r);
+            rec.bytes_lost = __ldg(b.bytes_lost + r); rec.packet_size = __ldg(b.packet_size + r);
+            rec.send_start = __ldg(b.send_start + r); rec.send_end = __ldg(b.send_end + r);
+            rec.recv_start = __ldg(b.recv_start + r); rec.recv_end = __ldg(b.recv_end + r);
+            const int flow = __ldg(b.flow + r);
+            uint32_t fl = 0; double cmin = 0.0;
+            bool has_min = false;
+            if (UNIQUE) { fl = p.flags[flow]; cmin = p.conn_min[flow]; has_min = (fl & PCCF_HAS_MIN) != 0; }
+            FlowStats st;
+            flow_stats_finish(rec, n, avg, m1, m2, has_min, cmin, UNIQUE && p.touch_conn != 0, st);
+            __syncwarp();
+            if (metrics && lane < N_METRICS) metrics[r * N_METRICS + lane] = st.v[lane];
+            if (UNIQUE) {
+                const uint32_t head = fl & PCCF_HEAD_MASK;
+                double *hrow = p.hist + (size_t)flow * HF;
+                if ((int)lane < F) hrow[head * F + lane] = st.v[p.ids[lane]] / flow_metric_scale(p.ids[lane]);
+                const uint32_t nhead = (head + 1 == (uint32_t)H) ? 0u : head + 1;
+                if (lane == 0) {
+                    if (atomicExch(&p.stamp[flow], batch_no) == batch_no) atomicAdd(&p.meta[0], 1ull);
+                    p.flags[flow] = nhead | (has_min ? PCCF_HAS_MIN : 0u);
+                    if (p.touch_conn) p.conn_min[flow] = cmin;
+                    const uint32_t c = p.n_rec[flow];
+                    if (c != 0xffffffffu) p.n_rec[flow] = c + 1;
+                }
+                if (obs) {
+                    __syncwarp();
+                    double *ob = obs + (size_t)r * HF;
+                    const int rot = (int)nhead * F;
+                    for (int k = (int)lane; k < HF; k += 32) {
+                        int src = k + rot;
+                        if (src >= HF) src -= HF;
+                        ob[k] = hrow[src];
+                    }
+                }
+            } else {
+                if ((int)lane < F) rows[(size_t)r * F + lane] = st.v[p.ids[lane]] / flow_metric_scale(p.ids[lane]);
+                if (lane == 0) avg_out[r] = avg;
+            }
+            __syncwarp();
         }
     }
 }
@@ -578,13 +695,16 @@ int pcc_flows_give_samples(pcc_flows_handle h, const pcc_mi_batch *batch, int32_
     int64_t blocks = (R + 31) / 32;
     const int64_t cap = (int64_t)h->sm_count * 8;
     if (blocks > cap) blocks = cap;
+    int64_t lblocks = (R + 127) / 128;          // the long-list pass: 4 warps x 32 records per block pass
+    if (lblocks > cap) lblocks = cap;
     h->batch_no++;
     if (h->batch_no == 0) h->batch_no = 1;
     if (unique_flows) {
         pcc_flows_ingest_kernel<true><<<(unsigned)blocks, PCCF_THREADS, 0, st>>>(h->d, b, h->batch_no, obs_dev, metrics_dev,
                                                                                    nullptr, nullptr);
+        pcc_flows_long_kernel<true><<<(unsigned)lblocks, 128, 0, st>>>(h->d, b, h->batch_no, obs_dev, metrics_dev, nullptr, nullptr);
         CUDA_TRY(cudaGetLastError());
-        h->launches++;
+        h->launches += 2;
         return PCC_OK;
     }
     // general batch: per-record part, stable sort of record indices by flow, per-flow sequential apply
@@ -604,6 +724,7 @@ int pcc_flows_give_samples(pcc_flows_handle h, const pcc_mi_batch *batch, int32_
     void *tmp = scratch + rows_b + avg_b + 3 * idx_b;
     pcc_flows_ingest_kernel<false><<<(unsigned)blocks, PCCF_THREADS, 0, st>>>(h->d, b, h->batch_no, nullptr, metrics_dev,
                                                                                 rows, avg);
+    pcc_flows_long_kernel<false><<<(unsigned)lblocks, 128, 0, st>>>(h->d, b, h->batch_no, nullptr, metrics_dev, rows, avg);
     pcc_flows_iota_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(iota, R);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_b, b.flow, sflow, (const int32_t *)iota, srec, (int)R, 0, 32, st);
     if (e == cudaSuccess) {
@@ -612,7 +733,7 @@ int pcc_flows_give_samples(pcc_flows_handle h, const pcc_mi_batch *batch, int32_
     }
     cudaFreeAsync(scratch, st);
     if (e != cudaSuccess) return fail(PCC_ECUDA, "give_samples: %s", cudaGetErrorString(e));
-    h->launches += 3;   // ingest, iota, apply (+ cub's sort passes, not ours)
+    h->launches += 4;   // ingest, long-list pass, iota, apply (+ cub's sort passes, not ours)
     return PCC_OK;
 }
 

@@ -1,7 +1,12 @@
 """PccMultiSenderEnv: N independent links, each shared by S senders (BASELINE config 5: the bw x delay grid
 sweep with 2 senders per link).  Batched counterpart of driving the reference's Network with several Sender
 objects (gym/network_sim.py:100-178); semantics in include/pcc_b200.h / DESIGN.md.  Exact, not fast: one env
-per thread with a per-env event heap."""
+per thread with a per-env event heap.
+
+The same path carries the two variants the reference hides behind module switches (network_sim.py:51-54):
+`use_cwnd=True` (USE_CWND: congestion window, a second action component per sender) and
+`use_latency_noise=True` (USE_LATENCY_NOISE: per-hop latency jitter).  With n_senders=1 this is the reference's
+own SimulatedNetworkEnv with the switch turned on (tests/golden/variant_*.npz)."""
 import ctypes as C
 
 import numpy as np
@@ -22,7 +27,7 @@ def grid_sweep_params(bw_mbps=(1.0, 1000.0), lat_ms=(1.0, 500.0), n_bw=32, n_lat
 
 class PccMultiSenderEnv(object):
     def __init__(self, n_envs, n_senders=2, history_len=10, features=sender_obs.DEFAULT_FEATURES, device=None, seed=0,
-                 ring_capacity=8192, max_steps=None):
+                 ring_capacity=8192, max_steps=None, use_cwnd=False, use_latency_noise=False):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("pcc_rl_b200 needs a CUDA device; there is no CPU fallback")
@@ -47,6 +52,13 @@ class PccMultiSenderEnv(object):
             self.ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
             self.h = C.c_void_p()
             _lib.check(self.L.pcc_multi_create(C.byref(self.h), C.byref(cfg), self.S, self.ws.data_ptr()))
+            self.use_cwnd, self.use_latency_noise = bool(use_cwnd), bool(use_latency_noise)
+            if use_cwnd or use_latency_noise:
+                v = _lib.PccVariant()
+                self.L.pcc_default_variant(C.byref(v))
+                v.use_cwnd, v.use_latency_noise = int(self.use_cwnd), int(self.use_latency_noise)
+                _lib.check(self.L.pcc_multi_set_variant(self.h, C.byref(v)))
+            self.cwnd = torch.empty((self.n_envs, self.S), dtype=torch.int32, device=self.device)
             f64 = dict(dtype=torch.float64, device=self.device)
             self.obs = torch.empty((self.n_envs, self.S, self.obs_dim), **f64)
             self.reward = torch.empty((self.n_envs, self.S), **f64)
@@ -87,13 +99,24 @@ class PccMultiSenderEnv(object):
         self._keep = (bw, lat, loss, q, r)
         return self.obs
 
-    def step(self, actions):
+    def step(self, actions, cwnd_actions=None):
+        """actions [n_envs, n_senders] (rate); with use_cwnd also cwnd_actions [n_envs, n_senders], or actions of
+        shape [n_envs, n_senders, 2] = the reference's 2-dim action (network_sim.py:380-381, 412-414)."""
         torch = self.torch
-        a = torch.as_tensor(actions).to(self.device, torch.float64).reshape(self.n_envs, self.S).contiguous()
-        _lib.check(self.L.pcc_multi_step(self.h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
-                                         self.done.data_ptr(), self.counts.data_ptr(), self._stream()))
-        self._keep_a = a
-        return self.obs, self.reward, self.done.bool(), {"counts": self.counts}
+        a = torch.as_tensor(actions).to(self.device, torch.float64)
+        if self.use_cwnd and cwnd_actions is None and a.dim() >= 2 and a.shape[-1] == 2 and a.numel() == 2 * self.n_envs * self.S:
+            a, cwnd_actions = a.reshape(self.n_envs, self.S, 2)[..., 0], a.reshape(self.n_envs, self.S, 2)[..., 1]
+        a = a.reshape(self.n_envs, self.S).contiguous()
+        ca = None
+        if self.use_cwnd:
+            if cwnd_actions is None:
+                raise ValueError("use_cwnd: step needs the window actions too")
+            ca = torch.as_tensor(cwnd_actions).to(self.device, torch.float64).reshape(self.n_envs, self.S).contiguous()
+        _lib.check(self.L.pcc_multi_step_cwnd(self.h, a.data_ptr(), ca.data_ptr() if ca is not None else None,
+                                              self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                              self.counts.data_ptr(), self.cwnd.data_ptr(), self._stream()))
+        self._keep_a = (a, ca)
+        return self.obs, self.reward, self.done.bool(), {"counts": self.counts, "cwnd": self.cwnd}
 
     def check(self):
         _lib.check(self.L.pcc_multi_check(self.h, self._stream()))

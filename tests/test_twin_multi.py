@@ -96,3 +96,114 @@ def test_twin_multi_equals_oracle_on_grid_points(seed):
             assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2], (seed, trial, k)
             assert o.cur_time == t.cur_time and o.run_dur == t.run_dur
         assert t.ok
+
+
+# ---- the cwnd / latency-noise variants of the loop on the same heap path ---------------
+def _variant_lib():
+    L = _lib()
+    pd = C.POINTER(C.c_double)
+    L.twin_multi_set_variant.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.twin_multi_cwnd.argtypes = [C.c_void_p, C.c_int]
+    L.twin_multi_step_cwnd.argtypes = [C.c_void_p, pd, pd, pd, pd, C.POINTER(C.c_int), C.POINTER(C.c_int32)]
+    return L
+
+
+class TwinVariant(TwinMulti):
+    def __init__(self, S, use_cwnd, use_noise, n_obs=30, features=None):
+        self.L = _variant_lib()
+        ids = np.asarray(oracle.feature_ids(features) if features else oracle.feature_ids(), dtype=np.int32)
+        self.S, self.hf = S, 10 * len(ids)
+        self.h = self.L.twin_multi_create(S, 10, ids.ctypes.data_as(C.POINTER(C.c_int)), len(ids), 1 << 15)
+        self.L.twin_multi_set_variant(self.h, int(use_cwnd), int(use_noise))
+        self.use_cwnd = use_cwnd
+
+    def step2(self, actions, cwnd_actions):
+        pd = C.POINTER(C.c_double)
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        ca = np.ascontiguousarray(cwnd_actions, dtype=np.float64)
+        obs = np.zeros((self.S, self.hf)); rew = np.zeros(self.S); cnt = np.zeros((self.S, 3), dtype=np.int32)
+        dn = C.c_int()
+        self.L.twin_multi_step_cwnd(self.h, a.ctypes.data_as(pd), ca.ctypes.data_as(pd) if self.use_cwnd else None,
+                                    obs.ctypes.data_as(pd), rew.ctypes.data_as(pd), C.byref(dn),
+                                    cnt.ctypes.data_as(C.POINTER(C.c_int32)))
+        return obs, rew, bool(dn.value), cnt
+
+    def cwnd(self, i=0):
+        return self.L.twin_multi_cwnd(self.h, i)
+
+
+SINGLE_VARIANTS = [n for n in golden_names("variant_") if not n.startswith("variant_multi_")]
+
+
+@pytest.mark.parametrize("name", SINGLE_VARIANTS)
+def test_twin_variant_single_sender_golden(name):
+    """USE_CWND / USE_LATENCY_NOISE on the reference's own single-sender env = this path with one sender."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    use_cwnd, use_noise = bool(z["use_cwnd"]), bool(z["use_noise"])
+    n_steps = int(z["steps_per_episode"])
+    k = 0
+    for ep in range(len(z["ep_params"])):
+        bw, lat, q, loss, rate = z["ep_params"][ep]
+        t = TwinVariant(1, use_cwnd, use_noise, features=str(z["features"]))
+        # one Philox stream runs through all episodes of the file: continue it by replaying the draw count
+        if ep == 0:
+            t.reset(int(z["seed"]), bw, lat, int(q), loss, [rate])
+            keep = t
+        else:
+            t = keep
+            t.L.twin_multi_reset(t.h, bw, lat, int(q), loss, np.array([rate]).ctypes.data_as(C.POINTER(C.c_double)))
+        assert t.cur_time == z["ep_cur_time0"][ep]
+        for _ in range(n_steps):
+            obs, rew, done, cnt = t.step2([z["action"][k]], [z["cwnd_action"][k]])
+            assert tuple(cnt[0]) == tuple(z["counts"][k]), (name, k)
+            assert np.array_equal(obs[0], z["obs"][k]) and rew[0] == z["reward"][k], (name, k)
+            assert t.cur_time == z["cur_time"][k] and t.run_dur == z["run_dur"][k]
+            assert t.cwnd() == z["cwnd"][k]
+            k += 1
+        assert t.ok
+
+
+@pytest.mark.parametrize("name", golden_names("variant_multi_"))
+def test_twin_variant_multi_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    bw, lat, queue, loss = z["params"]
+    S = len(z["rates"])
+    t = TwinVariant(S, bool(z["use_cwnd"]), bool(z["use_noise"]))
+    t.reset(int(z["seed"]), bw, lat, int(queue), loss, z["rates"])
+    assert t.cur_time == float(z["cur_time0"])
+    for k in range(len(z["action"])):
+        obs, rew, done, cnt = t.step2(z["action"][k], z["cwnd_action"][k])
+        assert np.array_equal(cnt, z["counts"][k]), (name, k)
+        assert np.array_equal(obs, z["obs"][k]) and np.array_equal(rew, z["reward"][k]), (name, k)
+        assert t.cur_time == z["cur_time"][k] and t.run_dur == z["run_dur"][k]
+        assert [t.cwnd(i) for i in range(S)] == list(z["cwnd"][k])
+    assert t.ok
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_twin_variant_equals_oracle_random(seed):
+    g = np.random.default_rng(900 + seed)
+    for trial in range(3):
+        S = int(g.choice([1, 1, 2, 3]))
+        use_cwnd, use_noise = bool(g.integers(0, 2)), bool(g.integers(0, 2))
+        if not (use_cwnd or use_noise):
+            use_cwnd = True
+        bw = float(g.uniform(100, 2000)); lat = float(g.uniform(0.005, 0.4))
+        queue = 1 + int(np.exp(g.uniform(0, 6))); loss = float(g.choice([0.0, 0.02, 0.2]))
+        rates = g.uniform(40, 1000, S)
+        o = oracle.OracleEnv()
+        o.set_variant(use_cwnd, use_noise)
+        o.seed_philox(seed)
+        o.reset_multi(bw, lat, queue, loss, rates)
+        t = TwinVariant(S, use_cwnd, use_noise)
+        t.reset(seed, bw, lat, queue, loss, rates)
+        assert o.cur_time == t.cur_time
+        for k in range(120):
+            a, ca = g.normal(0, 2.5, S), g.normal(0, 6.0, S)
+            x = o.step_multi(a, ca)
+            y = t.step2(a, ca)
+            assert np.array_equal(x[3], y[3]), (seed, trial, k)
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2], (seed, trial, k)
+            assert o.cur_time == t.cur_time and o.run_dur == t.run_dur
+            assert [o.cwnd(i) for i in range(S)] == [t.cwnd(i) for i in range(S)]
+        assert t.ok

@@ -108,7 +108,7 @@ struct HostHeap {
 };
 struct TwinMulti {
     int S, H, F, cap_s; int ids[PCC_MAX_FEATURES]; bool need_inc;
-    Consts c; MNet net; MSender snd[PCC_MAX_SENDERS];
+    Consts c; Variant v; MNet net; MSender snd[PCC_MAX_SENDERS];
     std::vector<MEvent> heap; std::vector<double> samples, hist;   // hist [S][H][F], oldest first
     PhiloxRng ph; bool ok;
 };
@@ -125,25 +125,35 @@ TwinMulti *twin_multi_create(int n_senders, int history_len, const int *feature_
     t->samples.resize((size_t)capacity * n_senders);
     t->hist.assign((size_t)n_senders * history_len * n_features, 0.0);
     t->ph.init(0, 0); t->ok = true;
+    t->v = default_variant();
     return t;
 }
 void twin_multi_destroy(TwinMulti *t) { delete t; }
+void twin_multi_set_variant(TwinMulti *t, int use_cwnd, int use_noise) { t->v.use_cwnd = use_cwnd; t->v.use_noise = use_noise; }
+int twin_multi_cwnd(TwinMulti *t, int i) { return t->snd[i].cwnd; }
+void twin_multi_step_cwnd(TwinMulti *t, const double *actions, const double *cwnd_actions, double *obs, double *rewards,
+                          int *done, int32_t *counts);
 void twin_multi_seed(TwinMulti *t, uint64_t seed) { t->ph.init(seed, 0); }
 void twin_multi_reset(TwinMulti *t, double bw, double dl, int64_t queue, double lr, const double *rates)
 {
     HostHeap hp{&t->heap};
-    t->ok = multi_reset(t->net, t->snd, t->S, hp, t->samples.data(), t->cap_s, t->ph, bw, dl, queue, lr, rates) && t->ok;
+    t->ok = multi_reset(t->net, t->snd, t->S, hp, t->samples.data(), t->cap_s, t->ph, bw, dl, queue, lr, rates, t->v) && t->ok;
     for (int i = 0; i < t->S; i++)
         for (int h = 0; h < t->H; h++)
             for (int f = 0; f < t->F; f++) t->hist[((size_t)i * t->H + h) * t->F + f] = metric_empty(t->ids[f]);
 }
 void twin_multi_step(TwinMulti *t, const double *actions, double *obs, double *rewards, int *done, int32_t *counts)
 {
+    twin_multi_step_cwnd(t, actions, nullptr, obs, rewards, done, counts);
+}
+void twin_multi_step_cwnd(TwinMulti *t, const double *actions, const double *cwnd_actions, double *obs, double *rewards,
+                          int *done, int32_t *counts)
+{
     HostHeap hp{&t->heap};
     double rows[PCC_MAX_SENDERS * PCC_MAX_FEATURES];
     bool dn;
-    t->ok = multi_step(t->net, t->snd, t->S, hp, t->samples.data(), t->cap_s, t->ph, actions, t->c, t->ids, t->F,
-                       t->need_inc, rows, rewards, counts, dn) && t->ok;
+    t->ok = multi_step(t->net, t->snd, t->S, hp, t->samples.data(), t->cap_s, t->ph, actions, cwnd_actions, t->c, t->v,
+                       t->ids, t->F, t->need_inc, rows, rewards, counts, dn) && t->ok;
     const size_t hf = (size_t)t->H * t->F;
     for (int i = 0; i < t->S; i++) {
         double *hs = t->hist.data() + i * hf;
