@@ -24,19 +24,25 @@ using namespace pcc;
 
 #define PCCF_THREADS 256
 #ifndef PCCF_MINBLOCKS
-#define PCCF_MINBLOCKS 3      // 80 registers, no spills (64 registers spill in the hot loop)
+#define PCCF_MINBLOCKS 4      // 64 registers, 32 warps per SM (measured: 3 -> 1.12 ms, 4 -> 1.04, 5 -> 1.01, 6 -> 1.01 per 1 Mi records)
 #endif
 #define PCCF_FULL 0xffffffffu
 #define PCCF_HEAD_MASK 0xffu
 #define PCCF_HAS_MIN 0x100u
 
+// Per-flow scalars, one 32-byte sector per flow (flows arrive in arbitrary order: one random sector per record).
+struct __align__(32) FlowState {
+    double conn_min;            // _conn_min_latencies[flow] (valid when PCCF_HAS_MIN is set)
+    double rate;                // the sending rate (PccGymDriver.rate / ShimNetworkEnv.rate)
+    uint32_t flags;             // bits 0-7 head (slot of the OLDEST history row), bit 8 = dict entry exists
+    uint32_t n_rec;             // records since the last reset (saturating); got_data = n_rec != 0
+    uint32_t stamp;             // batch number of the flow's last record (unique-batch check)
+    uint32_t pad;
+};
+
 struct FlowsDev {
     double *hist;               // [n_flows][H*F]; row `slot` at slot*F; head = slot of the OLDEST row
-    double *conn_min;           // [n_flows]
-    double *rate;               // [n_flows]
-    uint32_t *flags;            // [n_flows] bits 0-7 head, bit 8 = dict entry exists
-    uint32_t *n_rec;            // [n_flows] records since the last reset (saturating)
-    uint32_t *stamp;            // [n_flows] batch number of the flow's last record (unique-batch check)
+    FlowState *st;              // [n_flows]
     unsigned long long *meta;   // [0] duplicate flows in a batch declared unique, [1] flow index out of range
     int64_t n_flows;
     int32_t H, F;
@@ -56,21 +62,27 @@ struct BatchDev {
 };
 
 // One leaf of numpy's DOUBLE_pairwise_sum (n <= 128) on an 8-lane subgroup; the result is subgroup-uniform.
+// LDG: the samples are read from global memory through the read-only path; !LDG: `a` is a generic pointer (the
+// TMA-staged copy in shared memory, or global memory when a span did not fit the stage).
+template <bool LDG>
+__device__ __forceinline__ double ld_sample(const double *a) { return LDG ? __ldg(a) : *a; }
+
+template <bool LDG>
 __device__ __forceinline__ double sg_leaf(const double *__restrict__ a, int n, int j, unsigned mask)
 {
     if (n < 8) {
         double res = 0.;
-        for (int k = 0; k < n; k++) res += __ldg(a + k);
+        for (int k = 0; k < n; k++) res += ld_sample<LDG>(a + k);
         return res;
     }
     const int nb = n - (n % 8);
-    double r = __ldg(a + j);
+    double r = ld_sample<LDG>(a + j);
 #pragma unroll 8
-    for (int k = 8; k < nb; k += 8) r += __ldg(a + k + j);
+    for (int k = 8; k < nb; k += 8) r += ld_sample<LDG>(a + k + j);
     r += __shfl_xor_sync(mask, r, 1);
     r += __shfl_xor_sync(mask, r, 2);
     r += __shfl_xor_sync(mask, r, 4);
-    for (int k = nb; k < n; k++) r += __ldg(a + k);
+    for (int k = nb; k < n; k++) r += ld_sample<LDG>(a + k);
     return r;
 }
 
@@ -80,9 +92,10 @@ __device__ __forceinline__ double sg_leaf(const double *__restrict__ a, int n, i
 // for n <= 1800 the walk is at most 4 frames deep: the frames live in registers (selected by compare chains),
 // not in local memory.  Longer lists go to warp_pw_sum.
 #define PCCF_SG_MAX_N 1800
+template <bool LDG>
 __device__ __forceinline__ double sg_pw_sum(const double *__restrict__ a, int n, int j, unsigned mask)
 {
-    if (n <= 128) return sg_leaf(a, n, j, mask);
+    if (n <= 128) return sg_leaf<LDG>(a, n, j, mask);
     int rn0 = 0, rn1 = 0, rn2 = 0, rn3 = 0;          // right-child sizes of the open frames
     double ls0 = 0., ls1 = 0., ls2 = 0., ls3 = 0.;   // left-child sums of the open frames
     unsigned have_left = 0u;
@@ -98,7 +111,7 @@ __device__ __forceinline__ double sg_pw_sum(const double *__restrict__ a, int n,
             sp++;
             cur = n2;
         }
-        double res = sg_leaf(p, cur, j, mask);
+        double res = sg_leaf<LDG>(p, cur, j, mask);
         p += cur;
         for (;;) {
             if (sp == 0) return res;
@@ -176,7 +189,7 @@ __device__ __noinline__ double warp_pw_sum(const double *__restrict__ a, long lo
             long long o = 0; int c = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) if (k == sg && k < cnt) { o = lo[k]; c = lc[k]; }
-            mine = sg_leaf(a + o, c, j, 0xffu << (sg * 8));   // subgroups diverge (idle ones have c == 0)
+            mine = sg_leaf<true>(a + o, c, j, 0xffu << (sg * 8));   // subgroups diverge (idle ones have c == 0)
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -199,6 +212,135 @@ __device__ __noinline__ double warp_pw_sum(const double *__restrict__ a, long lo
 // feature values) and avg[R] are handed to pcc_flows_apply_kernel, which walks each flow's records in batch
 // order.
 // ---------------------------------------------------------------------------------------------------------
+// Everything of a record after its three pairwise sums: fields, the two rounds of lane-parallel divisions, the
+// conn-min dict entry, the history row, the observation (UNIQUE) or the hand-over to the apply kernel (!UNIQUE).
+// Called with the four subgroups of a warp converged; `good` is subgroup-uniform.
+template <bool UNIQUE>
+__device__ __forceinline__ void flows_finish_record(const FlowsDev &p, const BatchDev &b, long long r, int flow, long long n,
+                                                    double sum, double s1, double s2, bool good, int j, int sg0,
+                                                    unsigned sgmask, uint32_t batch_no, double *__restrict__ obs,
+                                                    double *__restrict__ metrics, double *__restrict__ rows,
+                                                    double *__restrict__ avg_out)
+{
+    const int H = p.H, F = p.F, HF = H * F;
+    const long long half = n / 2;
+    // ---- the record's scalar fields (loaded after the sums: they are not live across the sample passes) --
+    long long bs = 0, ba = 0, bl = 0, ps = 0;
+    double ss = 0., se = 0., rs = 0., re = 0.;
+    if (good) {
+        bs = __ldg(b.bytes_sent + r); ba = __ldg(b.bytes_acked + r); bl = __ldg(b.bytes_lost + r);
+        ps = __ldg(b.packet_size + r);
+        ss = __ldg(b.send_start + r); se = __ldg(b.send_end + r);
+        rs = __ldg(b.recv_start + r); re = __ldg(b.recv_end + r);
+    }
+
+    // ---- round 1 of divisions: one per lane (sender_obs.py:110-142) ---------------------------------
+    const double sdur = se - ss, rdur = re - rs;
+    double num = 0.0, den = 1.0;
+    bool ok = false;
+    if (j == 0) { num = 8.0 * (double)bs; den = sdur; ok = sdur > 0.0; }                    // send rate
+    else if (j == 1) { num = 8.0 * (double)(ba - ps); den = rdur; ok = rdur > 0.0; }        // recv rate
+    else if (j == 2) { num = 0.0 + sum; den = (double)n; ok = n > 0; }                      // np.mean(all)
+    else if (j == 3) { num = 0.0 + s1; den = (double)half; ok = half >= 1; }                // np.mean(first half)
+    else if (j == 4) { num = 0.0 + s2; den = (double)(n - half); ok = half >= 1; }          // np.mean(second half)
+    else if (j == 5) { num = (double)bl; den = (double)(bl + ba); ok = (bl + ba) > 0; }     // loss ratio
+    double q = num / (ok ? den : 1.0);
+    if (!ok) q = 0.0;
+    const double send_rate = __shfl_sync(sgmask, q, sg0 + 0);
+    const double recv_rate = __shfl_sync(sgmask, q, sg0 + 1);
+    const double avg = __shfl_sync(sgmask, q, sg0 + 2);
+    const double m1 = __shfl_sync(sgmask, q, sg0 + 3);
+    const double m2 = __shfl_sync(sgmask, q, sg0 + 4);
+    const double loss = __shfl_sync(sgmask, q, sg0 + 5);
+    const double inc = (half >= 1) ? m2 - m1 : 0.0;
+
+    // ---- conn-min dict entry (:158-176) -----------------------------------------------------------------
+    uint32_t fl = 0; double cmin = 0.0, cm = 0.0;
+    bool has_min = false;
+    uint32_t n_rec = 0;
+    if (UNIQUE && good) {
+        const FlowState fs = p.st[flow];          // one 32-byte sector
+        fl = fs.flags; cmin = fs.conn_min; n_rec = fs.n_rec;
+        has_min = (fl & PCCF_HAS_MIN) != 0;
+        cm = flow_conn_min(avg, has_min, cmin, p.touch_conn != 0);
+    }
+
+    // ---- round 2 --------------------------------------------------------------------------------------
+    double dflt = 0.0;
+    num = 0.0; den = 1.0; ok = false;
+    if (j == 0) { num = inc; den = rdur; ok = rdur > 0.0; }                                  // ack latency inflation
+    else if (j == 1) { num = inc; den = sdur; ok = sdur > 0.0; }                             // sent latency inflation
+    else if (j == 2) { num = avg; den = cm; ok = cm > 0.0; dflt = 1.0; }                     // latency ratio
+    else if (j == 3) { num = send_rate; den = recv_rate; dflt = 1.0;
+                       ok = recv_rate > 0.0 && send_rate < 1000.0 * recv_rate; }             // send ratio
+    else if (j == 4) { num = send_rate; den = 1e7; ok = true; }                              // scaled rates
+    else if (j == 5) { num = recv_rate; den = 1e7; ok = true; }
+    q = num / (ok ? den : 1.0);
+    if (!ok) q = dflt;
+    const double ack_infl = __shfl_sync(sgmask, q, sg0 + 0);
+    const double sent_infl = __shfl_sync(sgmask, q, sg0 + 1);
+    const double lat_ratio = __shfl_sync(sgmask, q, sg0 + 2);
+    const double send_ratio = __shfl_sync(sgmask, q, sg0 + 3);
+    const double send_rate_s = __shfl_sync(sgmask, q, sg0 + 4);
+    const double recv_rate_s = __shfl_sync(sgmask, q, sg0 + 5);
+
+    auto raw = [&](int id) -> double {
+        switch (id) {
+        case M_SEND_RATE: return send_rate;
+        case M_RECV_RATE: return recv_rate;
+        case M_RECV_DUR: return rdur;
+        case M_SEND_DUR: return sdur;
+        case M_AVG_LATENCY: return avg;
+        case M_LOSS_RATIO: return loss;
+        case M_ACK_LAT_INFL: return ack_infl;
+        case M_SENT_LAT_INFL: return sent_infl;
+        case M_CONN_MIN_LAT: return cm;
+        case M_LAT_INCREASE: return inc;
+        case M_LAT_RATIO: return lat_ratio;
+        default: return send_ratio;
+        }
+    };
+    if (!good) return;                                                  // (no warp-wide sync below this line)
+
+    if (metrics) {
+        metrics[r * N_METRICS + j] = raw(j);
+        if (j + 8 < N_METRICS) metrics[r * N_METRICS + j + 8] = raw(j + 8);
+    }
+    if (UNIQUE) {
+        const uint32_t head = fl & PCCF_HEAD_MASK;
+        double *hrow = p.hist + (size_t)flow * HF;
+        for (int f = j; f < F; f += 8) {                                // SenderHistory.step (:64-66)
+            const int id = p.ids[f];
+            const double v = (id == M_SEND_RATE) ? send_rate_s : (id == M_RECV_RATE) ? recv_rate_s : raw(id);
+            hrow[head * F + f] = v;
+        }
+        const uint32_t nhead = (head + 1 == (uint32_t)H) ? 0u : head + 1;
+        if (j == 0) {
+            FlowState *fs = p.st + flow;
+            if (atomicExch(&fs->stamp, batch_no) == batch_no) atomicAdd(&p.meta[0], 1ull);
+            fs->flags = nhead | (has_min ? PCCF_HAS_MIN : 0u);
+            if (p.touch_conn) fs->conn_min = cmin;
+            if (n_rec != 0xffffffffu) fs->n_rec = n_rec + 1;
+        }
+        if (obs) {                                                      // as_array (:68-73): oldest row first
+            __syncwarp(sgmask);
+            double *ob = obs + (size_t)r * HF;
+            const int rot = (int)nhead * F;
+            for (int k = j; k < HF; k += 8) {
+                int src = k + rot;
+                if (src >= HF) src -= HF;
+                ob[k] = hrow[src];
+            }
+        }
+    } else {
+        for (int f = j; f < F; f += 8) {
+            const int id = p.ids[f];
+            rows[(size_t)r * F + f] = (id == M_SEND_RATE) ? send_rate_s : (id == M_RECV_RATE) ? recv_rate_s : raw(id);
+        }
+        if (j == 0) avg_out[r] = avg;
+    }
+}
+
 template <bool UNIQUE>
 __global__ void __launch_bounds__(PCCF_THREADS, PCCF_MINBLOCKS)
 pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__restrict__ obs, double *__restrict__ metrics,
@@ -210,18 +352,33 @@ pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__res
     const int sg0 = sg * 8;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int H = p.H, F = p.F, HF = H * F;
 
-    for (long long base = warp * 4; base < b.R; base += nwarps * 4) {      // warp-uniform
+    // A warp owns a contiguous run of records (4 per pass, one per subgroup): its offsets, fields and samples are
+    // one sequential stream; the next pass's offsets and flow id are loaded a pass ahead.  (Measured: an additional
+    // prefetch.global.L2 of the next pass's sample span bought nothing and cost 35 % more DRAM reads.)
+    long long chunk = (b.R + nwarps - 1) / nwarps;
+    chunk = (chunk + 3) & ~3ll;
+    const long long wbeg = warp * chunk;
+    const long long wend = (wbeg + chunk < b.R) ? wbeg + chunk : b.R;
+    long long o0n = 0, o1n = 0;
+    int flown = 0;
+    if (wbeg + sg < wend) {
+        o0n = __ldg(b.off + wbeg + sg); o1n = __ldg(b.off + wbeg + sg + 1);
+        flown = __ldg(b.flow + wbeg + sg);
+    }
+    for (long long base = wbeg; base < wend; base += 4) {                  // warp-uniform
         const long long r = base + sg;
-        const bool valid = r < b.R;
-        long long n = 0;
-        const double *a = b.rtt;
-        int flow = 0;
-        if (valid) {
-            const long long o0 = __ldg(b.off + r), o1 = __ldg(b.off + r + 1);
-            n = o1 - o0; a = b.rtt + o0;
-            flow = __ldg(b.flow + r);
+        const bool valid = r < wend;
+        const long long n0 = o1n - o0n;
+        long long n = valid ? n0 : 0;
+        const double *a = b.rtt + (valid ? o0n : 0);
+        const int flow = valid ? flown : 0;
+        {   // the next pass: load its offsets / flow id now, prefetch what it will touch
+            const long long rn = r + 4;
+            if (rn < wend) {
+                o0n = __ldg(b.off + rn); o1n = __ldg(b.off + rn + 1);
+                flown = __ldg(b.flow + rn);
+            }
         }
         bool good = valid && flow >= 0 && (long long)flow < p.n_flows && n >= 0;
         if (valid && !good && j == 0) atomicAdd(&p.meta[1], 1ull);
@@ -239,123 +396,163 @@ pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__res
             const long long lo = (q == 2) ? half : 0;
             const long long len = (q == 0) ? n : (q == 1) ? half : n - half;
             if (in_sg && (q == 0 || half >= 1)) {
-                const double v = sg_pw_sum(a + lo, (int)len, j, sgmask);
+                const double v = sg_pw_sum<true>(a + lo, (int)len, j, sgmask);
                 if (q == 0) sum = v; else if (q == 1) s1 = v; else s2 = v;
             }
         }
-        // ---- the record's scalar fields (loaded after the sums: they are not live across the sample passes) --
-        long long bs = 0, ba = 0, bl = 0, ps = 0;
-        double ss = 0., se = 0., rs = 0., re = 0.;
-        if (good) {
-            bs = __ldg(b.bytes_sent + r); ba = __ldg(b.bytes_acked + r); bl = __ldg(b.bytes_lost + r);
-            ps = __ldg(b.packet_size + r);
-            ss = __ldg(b.send_start + r); se = __ldg(b.send_end + r);
-            rs = __ldg(b.recv_start + r); re = __ldg(b.recv_end + r);
+        flows_finish_record<UNIQUE>(p, b, r, flow, n, sum, s1, s2, good, j, sg0, sgmask, batch_no, obs, metrics, rows, avg_out);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same ingest with the sample stream staged by TMA.  The four records of a pass are consecutive, so their
+// samples are ONE contiguous span of the CSR array: lane 0 issues a single cp.async.bulk (global -> shared,
+// completion counted in bytes on an mbarrier) per pass.  One stage per warp: as soon as the three summation
+// passes have read the stage, the copy of the NEXT pass is started, and it lands while the warp does the part of
+// the current pass that needs no samples (fields, divisions, history row, observation -- 60 % of the
+// instructions).  No registers are tied up by loads in flight and the summation passes read shared memory.
+// cp.async.bulk moves 16-byte granules from a 16-byte aligned address: an odd first element index starts the
+// copy one element early, an odd element count copies one element more (the last element of the whole array is
+// fetched by hand instead of reading past it).  A span that does not fit the stage is read from global memory
+// by the same code (generic pointers).
+// ---------------------------------------------------------------------------------------------------------
+#ifndef PCCF_TMA_WARPS
+#define PCCF_TMA_WARPS 4         // warps per block
+#endif
+#ifndef PCCF_TMA_SLOT
+#define PCCF_TMA_SLOT 768        // doubles per warp stage (6 KB): span of a pass + 1 must fit
+#endif
+#ifndef PCCF_TMA_MINBLOCKS
+#define PCCF_TMA_MINBLOCKS 8     // 8 blocks x 4 warps per SM: 64 registers, 8 x 24.1 KB of shared memory
+#endif
+#define PCCF_TMA_SMEM ((size_t)PCCF_TMA_WARPS * PCCF_TMA_SLOT * 8 + (size_t)PCCF_TMA_WARPS * 8)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool UNIQUE>
+__global__ void __launch_bounds__(PCCF_TMA_WARPS * 32, PCCF_TMA_MINBLOCKS)
+pcc_flows_ingest_tma_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__restrict__ obs, double *__restrict__ metrics,
+                            double *__restrict__ rows, double *__restrict__ avg_out)
+{
+    extern __shared__ __align__(128) unsigned char pccf_smem[];
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const int sg = (int)(lane >> 3), j = (int)(lane & 7u);
+    const unsigned sgmask = 0xffu << (sg * 8);
+    const int sg0 = sg * 8;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    double *stage = reinterpret_cast<double *>(pccf_smem) + (size_t)wib * PCCF_TMA_SLOT;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(pccf_smem + (size_t)PCCF_TMA_WARPS * PCCF_TMA_SLOT * 8) + wib;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
+    }
+    __syncwarp();
+
+    long long chunk = (b.R + nwarps - 1) / nwarps;
+    chunk = (chunk + 3) & ~3ll;
+    const long long wbeg = warp * chunk;
+    const long long wend = (wbeg + chunk < b.R) ? wbeg + chunk : b.R;
+    if (wbeg >= wend) return;                                              // warp-uniform
+    const long long total = __ldg(b.off + b.R);                           // elements in the sample array
+
+    // Starts the copy of the pass beginning at record `base` (offsets of its records in o0x / o1x of the subgroups).
+    // Returns the element index the stage then starts at, or -1 when the pass has to read global memory.
+    auto issue = [&](long long base, long long o0x, long long o1x) -> long long {
+        const int nvalid = (wend - base >= 4) ? 4 : (int)(wend - base);
+        const long long e0 = __shfl_sync(PCCF_FULL, o0x, 0);
+        const long long e1 = __shfl_sync(PCCF_FULL, o1x, (nvalid - 1) * 8);
+        const long long e0a = e0 & ~1ll;
+        const long long nel = e1 - e0a;
+        const bool ok = e0 >= 0 && nel >= 0 && nel + 1 <= PCCF_TMA_SLOT && e1 <= total;
+        if (lane == 0) {
+            long long ncopy = ok ? ((nel + 1) & ~1ll) : 0;
+            if (ncopy > 0 && e0a + ncopy > total) {                        // never read past the end of the array
+                ncopy -= 2;
+                stage[nel - 1] = __ldg(b.rtt + e0a + nel - 1);
+            }
+            if (ncopy > 0) {
+                mbar_expect_tx(bar, (uint32_t)(ncopy * 8));
+                tma_load_1d(stage, b.rtt + e0a, (uint32_t)(ncopy * 8), bar);
+            } else {
+                mbar_arrive(bar);
+            }
         }
+        __syncwarp();
+        return ok ? e0a : -1;
+    };
 
-        // ---- round 1 of divisions: one per lane (sender_obs.py:110-142) ---------------------------------
-        const double sdur = se - ss, rdur = re - rs;
-        double num = 0.0, den = 1.0;
-        bool ok = false;
-        if (j == 0) { num = 8.0 * (double)bs; den = sdur; ok = sdur > 0.0; }                    // send rate
-        else if (j == 1) { num = 8.0 * (double)(ba - ps); den = rdur; ok = rdur > 0.0; }        // recv rate
-        else if (j == 2) { num = 0.0 + sum; den = (double)n; ok = n > 0; }                      // np.mean(all)
-        else if (j == 3) { num = 0.0 + s1; den = (double)half; ok = half >= 1; }                // np.mean(first half)
-        else if (j == 4) { num = 0.0 + s2; den = (double)(n - half); ok = half >= 1; }          // np.mean(second half)
-        else if (j == 5) { num = (double)bl; den = (double)(bl + ba); ok = (bl + ba) > 0; }     // loss ratio
-        double q = num / (ok ? den : 1.0);
-        if (!ok) q = 0.0;
-        const double send_rate = __shfl_sync(sgmask, q, sg0 + 0);
-        const double recv_rate = __shfl_sync(sgmask, q, sg0 + 1);
-        const double avg = __shfl_sync(sgmask, q, sg0 + 2);
-        const double m1 = __shfl_sync(sgmask, q, sg0 + 3);
-        const double m2 = __shfl_sync(sgmask, q, sg0 + 4);
-        const double loss = __shfl_sync(sgmask, q, sg0 + 5);
-        const double inc = (half >= 1) ? m2 - m1 : 0.0;
+    // offsets / flow id of this pass (c) and of the next one (n), per subgroup
+    long long o0c = 0, o1c = 0, o0n = 0, o1n = 0;
+    int flowc = 0, flown = 0;
+    if (wbeg + sg < wend) { o0c = __ldg(b.off + wbeg + sg); o1c = __ldg(b.off + wbeg + sg + 1); flowc = __ldg(b.flow + wbeg + sg); }
+    if (wbeg + 4 + sg < wend) { o0n = __ldg(b.off + wbeg + 4 + sg); o1n = __ldg(b.off + wbeg + 4 + sg + 1); flown = __ldg(b.flow + wbeg + 4 + sg); }
+    long long e0a_c = issue(wbeg, o0c, o1c);
 
-        // ---- conn-min dict entry (:158-176) -----------------------------------------------------------------
-        uint32_t fl = 0; double cmin = 0.0, cm = 0.0;
-        bool has_min = false;
-        if (UNIQUE && good) {
-            fl = p.flags[flow]; cmin = p.conn_min[flow];
-            has_min = (fl & PCCF_HAS_MIN) != 0;
-            cm = flow_conn_min(avg, has_min, cmin, p.touch_conn != 0);
+    int pass = 0;
+    for (long long base = wbeg; base < wend; base += 4, pass++) {          // warp-uniform
+        const long long r = base + sg;
+        const bool valid = r < wend;
+        // the pass after the next: offsets / flow id into registers (consumed two passes from now)
+        long long o0f = 0, o1f = 0;
+        int flowf = 0;
+        if (r + 8 < wend) { o0f = __ldg(b.off + r + 8); o1f = __ldg(b.off + r + 9); flowf = __ldg(b.flow + r + 8); }
+        long long n = valid ? o1c - o0c : 0;
+        const int flow = valid ? flowc : 0;
+        bool good = valid && flow >= 0 && (long long)flow < p.n_flows && n >= 0;
+        if (valid && !good && j == 0) atomicAdd(&p.meta[1], 1ull);
+        if (!good) n = 0;
+        if (n > PCCF_SG_MAX_N) good = false;                               // left to pcc_flows_long_kernel
+        const long long half = n / 2;
+        mbar_wait(bar, (uint32_t)(pass & 1));
+        const double *a = (e0a_c >= 0) ? stage + (o0c - e0a_c) : b.rtt + o0c;
+        double sum = 0.0, s1 = 0.0, s2 = 0.0;
+        const bool in_sg = good && n > 0;
+#pragma unroll 1
+        for (int q = 0; q < 3; q++) {
+            const long long lo = (q == 2) ? half : 0;
+            const long long len = (q == 0) ? n : (q == 1) ? half : n - half;
+            if (in_sg && (q == 0 || half >= 1)) {
+                const double v = sg_pw_sum<false>(a + lo, (int)len, j, sgmask);
+                if (q == 0) sum = v; else if (q == 1) s1 = v; else s2 = v;
+            }
         }
-
-        // ---- round 2 --------------------------------------------------------------------------------------
-        double dflt = 0.0;
-        num = 0.0; den = 1.0; ok = false;
-        if (j == 0) { num = inc; den = rdur; ok = rdur > 0.0; }                                  // ack latency inflation
-        else if (j == 1) { num = inc; den = sdur; ok = sdur > 0.0; }                             // sent latency inflation
-        else if (j == 2) { num = avg; den = cm; ok = cm > 0.0; dflt = 1.0; }                     // latency ratio
-        else if (j == 3) { num = send_rate; den = recv_rate; dflt = 1.0;
-                           ok = recv_rate > 0.0 && send_rate < 1000.0 * recv_rate; }             // send ratio
-        else if (j == 4) { num = send_rate; den = 1e7; ok = true; }                              // scaled rates
-        else if (j == 5) { num = recv_rate; den = 1e7; ok = true; }
-        q = num / (ok ? den : 1.0);
-        if (!ok) q = dflt;
-        const double ack_infl = __shfl_sync(sgmask, q, sg0 + 0);
-        const double sent_infl = __shfl_sync(sgmask, q, sg0 + 1);
-        const double lat_ratio = __shfl_sync(sgmask, q, sg0 + 2);
-        const double send_ratio = __shfl_sync(sgmask, q, sg0 + 3);
-        const double send_rate_s = __shfl_sync(sgmask, q, sg0 + 4);
-        const double recv_rate_s = __shfl_sync(sgmask, q, sg0 + 5);
-
-        auto raw = [&](int id) -> double {
-            switch (id) {
-            case M_SEND_RATE: return send_rate;
-            case M_RECV_RATE: return recv_rate;
-            case M_RECV_DUR: return rdur;
-            case M_SEND_DUR: return sdur;
-            case M_AVG_LATENCY: return avg;
-            case M_LOSS_RATIO: return loss;
-            case M_ACK_LAT_INFL: return ack_infl;
-            case M_SENT_LAT_INFL: return sent_infl;
-            case M_CONN_MIN_LAT: return cm;
-            case M_LAT_INCREASE: return inc;
-            case M_LAT_RATIO: return lat_ratio;
-            default: return send_ratio;
-            }
-        };
-        if (!good) continue;                                                // (no warp-wide sync below this line)
-
-        if (metrics) {
-            metrics[r * N_METRICS + j] = raw(j);
-            if (j + 8 < N_METRICS) metrics[r * N_METRICS + j + 8] = raw(j + 8);
-        }
-        if (UNIQUE) {
-            const uint32_t head = fl & PCCF_HEAD_MASK;
-            double *hrow = p.hist + (size_t)flow * HF;
-            for (int f = j; f < F; f += 8) {                                // SenderHistory.step (:64-66)
-                const int id = p.ids[f];
-                const double v = (id == M_SEND_RATE) ? send_rate_s : (id == M_RECV_RATE) ? recv_rate_s : raw(id);
-                hrow[head * F + f] = v;
-            }
-            const uint32_t nhead = (head + 1 == (uint32_t)H) ? 0u : head + 1;
-            if (j == 0) {
-                if (atomicExch(&p.stamp[flow], batch_no) == batch_no) atomicAdd(&p.meta[0], 1ull);
-                p.flags[flow] = nhead | (has_min ? PCCF_HAS_MIN : 0u);
-                if (p.touch_conn) p.conn_min[flow] = cmin;
-                const uint32_t c = p.n_rec[flow];
-                if (c != 0xffffffffu) p.n_rec[flow] = c + 1;
-            }
-            if (obs) {                                                      // as_array (:68-73): oldest row first
-                __syncwarp(sgmask);
-                double *ob = obs + (size_t)r * HF;
-                const int rot = (int)nhead * F;
-                for (int k = j; k < HF; k += 8) {
-                    int src = k + rot;
-                    if (src >= HF) src -= HF;
-                    ob[k] = hrow[src];
-                }
-            }
-        } else {
-            for (int f = j; f < F; f += 8) {
-                const int id = p.ids[f];
-                rows[(size_t)r * F + f] = (id == M_SEND_RATE) ? send_rate_s : (id == M_RECV_RATE) ? recv_rate_s : raw(id);
-            }
-            if (j == 0) avg_out[r] = avg;
-        }
+        __syncwarp();                                                      // the stage has been read: refill it ...
+        long long e0a_n = -1;
+        if (base + 4 < wend) e0a_n = issue(base + 4, o0n, o1n);
+        // ... while this pass's records are finished
+        flows_finish_record<UNIQUE>(p, b, r, flow, n, sum, s1, s2, good, j, sg0, sgmask, batch_no, obs, metrics, rows, avg_out);
+        o0c = o0n; o1c = o1n; flowc = flown; e0a_c = e0a_n;
+        o0n = o0f; o1n = o1f; flown = flowf;
     }
 }
 
@@ -397,7 +594,8 @@ pcc_flows_long_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__restr
             const int flow = __ldg(b.flow + r);
             uint32_t fl = 0; double cmin = 0.0;
             bool has_min = false;
-            if (UNIQUE) { fl = p.flags[flow]; cmin = p.conn_min[flow]; has_min = (fl & PCCF_HAS_MIN) != 0; }
+            uint32_t n_rec = 0;
+            if (UNIQUE) { const FlowState fs = p.st[flow]; fl = fs.flags; cmin = fs.conn_min; n_rec = fs.n_rec; has_min = (fl & PCCF_HAS_MIN) != 0; }
             FlowStats st;
             flow_stats_finish(rec, n, avg, m1, m2, has_min, cmin, UNIQUE && p.touch_conn != 0, st);
             __syncwarp();
@@ -408,11 +606,11 @@ pcc_flows_long_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__restr
                 if ((int)lane < F) hrow[head * F + lane] = st.v[p.ids[lane]] / flow_metric_scale(p.ids[lane]);
                 const uint32_t nhead = (head + 1 == (uint32_t)H) ? 0u : head + 1;
                 if (lane == 0) {
-                    if (atomicExch(&p.stamp[flow], batch_no) == batch_no) atomicAdd(&p.meta[0], 1ull);
-                    p.flags[flow] = nhead | (has_min ? PCCF_HAS_MIN : 0u);
-                    if (p.touch_conn) p.conn_min[flow] = cmin;
-                    const uint32_t c = p.n_rec[flow];
-                    if (c != 0xffffffffu) p.n_rec[flow] = c + 1;
+                    FlowState *fs = p.st + flow;
+                    if (atomicExch(&fs->stamp, batch_no) == batch_no) atomicAdd(&p.meta[0], 1ull);
+                    fs->flags = nhead | (has_min ? PCCF_HAS_MIN : 0u);
+                    if (p.touch_conn) fs->conn_min = cmin;
+                    if (n_rec != 0xffffffffu) fs->n_rec = n_rec + 1;
                 }
                 if (obs) {
                     __syncwarp();
@@ -446,12 +644,13 @@ __global__ void pcc_flows_apply_kernel(FlowsDev p, int64_t R, const int32_t *__r
     if (flow < 0 || (int64_t)flow >= p.n_flows) return;
     if (i > 0 && sorted_flow[i - 1] == flow) return;
     const int H = p.H, F = p.F, HF = H * F;
-    uint32_t fl = p.flags[flow];
-    double cmin = p.conn_min[flow];
+    FlowState *fs = p.st + flow;
+    uint32_t fl = fs->flags;
+    double cmin = fs->conn_min;
     bool has_min = (fl & PCCF_HAS_MIN) != 0;
     uint32_t head = fl & PCCF_HEAD_MASK;
     double *hrow = p.hist + (size_t)flow * HF;
-    uint32_t cnt = p.n_rec[flow];
+    uint32_t cnt = fs->n_rec;
     for (int64_t k = i; k < R && sorted_flow[k] == flow; k++) {
         const int64_t r = sorted_rec[k];
         const double a = avg[r];
@@ -473,9 +672,9 @@ __global__ void pcc_flows_apply_kernel(FlowsDev p, int64_t R, const int32_t *__r
             for (int q = 0; q < HF; q++) { int src = q + rot; if (src >= HF) src -= HF; ob[q] = hrow[src]; }
         }
     }
-    p.flags[flow] = head | (has_min ? PCCF_HAS_MIN : 0u);
-    if (p.touch_conn) p.conn_min[flow] = cmin;
-    p.n_rec[flow] = cnt;
+    fs->flags = head | (has_min ? PCCF_HAS_MIN : 0u);
+    if (p.touch_conn) fs->conn_min = cmin;
+    fs->n_rec = cnt;
 }
 
 __global__ void pcc_flows_iota_kernel(int32_t *__restrict__ v, int64_t n)
@@ -489,9 +688,9 @@ __global__ void pcc_flows_reset_kernel(FlowsDev p, const uint8_t *__restrict__ m
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n_flows || (mask && !mask[e])) return;
-    uint32_t fl = p.flags[e];
-    double cmin = p.conn_min[e];
-    if (mode == FLOW_RESET_NEW) { fl &= ~PCCF_HAS_MIN; cmin = 0.0; p.conn_min[e] = 0.0; }
+    uint32_t fl = p.st[e].flags;
+    double cmin = p.st[e].conn_min;
+    if (mode == FLOW_RESET_NEW) { fl &= ~PCCF_HAS_MIN; cmin = 0.0; p.st[e].conn_min = 0.0; }
     const bool seen = (mode == FLOW_RESET_CLIENT) && (fl & PCCF_HAS_MIN);
     double *hrow = p.hist + (size_t)e * p.H * p.F;
     for (int h = 0; h < p.H; h++)
@@ -499,8 +698,8 @@ __global__ void pcc_flows_reset_kernel(FlowsDev p, const uint8_t *__restrict__ m
             const int id = p.ids[f];
             hrow[h * p.F + f] = flow_metric_empty(id, seen, cmin) / flow_metric_scale(id);
         }
-    p.flags[e] = fl & PCCF_HAS_MIN;     // head = 0
-    p.n_rec[e] = 0u;
+    p.st[e].flags = fl & PCCF_HAS_MIN;     // head = 0
+    p.st[e].n_rec = 0u;
 }
 
 // history.as_array() of every flow: obs[flow][H*F], oldest row first
@@ -511,7 +710,7 @@ __global__ void pcc_flows_obs_kernel(FlowsDev p, double *__restrict__ obs)
     if (i >= p.n_flows * HF) return;
     const int64_t e = i / HF;
     const int k = (int)(i - e * HF);
-    int src = k + (int)(p.flags[e] & PCCF_HEAD_MASK) * p.F;
+    int src = k + (int)(p.st[e].flags & PCCF_HEAD_MASK) * p.F;
     if (src >= HF) src -= HF;
     obs[i] = p.hist[(size_t)e * HF + src];
 }
@@ -523,11 +722,11 @@ __global__ void pcc_flows_rate_kernel(FlowsDev p, const double *__restrict__ act
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n_flows) return;
-    double rate = p.rate[e];
+    double rate = p.st[e].rate;
     const bool sel = !mask || mask[e];
-    if (actions && sel && (p.rate_style == RATE_STYLE_SHIM || p.n_rec[e] != 0u)) {
+    if (actions && sel && (p.rate_style == RATE_STYLE_SHIM || p.st[e].n_rec != 0u)) {
         rate = flow_apply_rate_delta(rate, actions[e], p.delta_scale, p.min_rate, p.max_rate, p.rate_style);
-        p.rate[e] = rate;
+        p.st[e].rate = rate;
     }
     if (rates_out) rates_out[e] = rate;
 }
@@ -537,7 +736,15 @@ __global__ void pcc_flows_set_rate_kernel(FlowsDev p, const uint8_t *__restrict_
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n_flows || (mask && !mask[e])) return;
-    p.rate[e] = rates ? rates[e] : scalar;
+    p.st[e].rate = rates ? rates[e] : scalar;
+}
+
+// one column of the per-flow state: 0 = conn_min (0.0 when there is no dict entry), 1 = rate
+__global__ void pcc_flows_column_kernel(FlowsDev p, int which, double *__restrict__ dst)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_flows) return;
+    dst[e] = (which == 0) ? ((p.st[e].flags & PCCF_HAS_MIN) ? p.st[e].conn_min : 0.0) : p.st[e].rate;
 }
 
 }  // namespace pccf
@@ -553,7 +760,7 @@ __global__ void pcc_flows_act_kernel(FlowsDev p, PolicyDev pol, double *__restri
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n_flows) return;
-    const int head = (int)(p.flags[e] & PCCF_HEAD_MASK);
+    const int head = (int)(p.st[e].flags & PCCF_HEAD_MASK);
     actions[e] = policy_action(pol, p.hist + (size_t)e * p.H * p.F, head, p.H, p.F, e, 0ull);
 }
 
@@ -563,19 +770,17 @@ struct pcc_flows_handle_s {
     uint32_t batch_no;
     int64_t launches;
     int sm_count;
+    int use_tma;          // 1: TMA-staged ingest kernel (default); 0: read-only-path loads (PCC_FLOWS_KERNEL=ldg)
+    int tma_blocks_per_sm;
 };
 
 static void flows_layout(const pcc_flows_config *c, size_t off[8], size_t &total)
 {
     const size_t n = (size_t)c->n_flows, HF = (size_t)c->history_len * c->n_features;
     size_t o = 0;
-    off[0] = o; o = align_up(o + n * HF * 8);     // hist
-    off[1] = o; o = align_up(o + n * 8);          // conn_min
-    off[2] = o; o = align_up(o + n * 8);          // rate
-    off[3] = o; o = align_up(o + n * 4);          // flags
-    off[4] = o; o = align_up(o + n * 4);          // n_rec
-    off[5] = o; o = align_up(o + n * 4);          // stamp
-    off[6] = o; o = align_up(o + 64);             // meta
+    off[0] = o; o = align_up(o + n * HF * 8);              // hist
+    off[1] = o; o = align_up(o + n * sizeof(FlowState));   // per-flow state
+    off[6] = o; o = align_up(o + 64);                      // meta
     total = o;
 }
 
@@ -637,8 +842,7 @@ static int flows_build(pcc_flows_handle *out, const pcc_flows_config *cfg, void 
     flows_layout(cfg, off, total);
     char *b = (char *)workspace_dev;
     FlowsDev &d = h->d;
-    d.hist = (double *)(b + off[0]); d.conn_min = (double *)(b + off[1]); d.rate = (double *)(b + off[2]);
-    d.flags = (uint32_t *)(b + off[3]); d.n_rec = (uint32_t *)(b + off[4]); d.stamp = (uint32_t *)(b + off[5]);
+    d.hist = (double *)(b + off[0]); d.st = (FlowState *)(b + off[1]);
     d.meta = (unsigned long long *)(b + off[6]);
     d.n_flows = cfg->n_flows; d.H = cfg->history_len; d.F = cfg->n_features;
     for (int i = 0; i < PCC_MAX_FEATURES; i++) d.ids[i] = i < cfg->n_features ? cfg->feature_ids[i] : 0;
@@ -649,6 +853,16 @@ static int flows_build(pcc_flows_handle *out, const pcc_flows_config *cfg, void 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete h; return fail(PCC_ECUDA, "cudaGetDeviceProperties failed"); }
     h->sm_count = prop.multiProcessorCount;
+    {
+        const char *fk = getenv("PCC_FLOWS_KERNEL");
+        h->use_tma = !(fk && !strcmp(fk, "ldg"));
+        cudaError_t ce = cudaFuncSetAttribute(pcc_flows_ingest_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCCF_TMA_SMEM);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(pcc_flows_ingest_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCCF_TMA_SMEM);
+        int nb = 0;
+        if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcc_flows_ingest_tma_kernel<true>, PCCF_TMA_WARPS * 32, PCCF_TMA_SMEM);
+        if (ce != cudaSuccess || nb < 1) { delete h; return fail(PCC_ECUDA, "flows: TMA kernel configuration: %s", cudaGetErrorString(ce)); }
+        h->tma_blocks_per_sm = nb;
+    }
     if (init) {
         cudaError_t e = cudaMemset(b, 0, total);
         if (e == cudaSuccess) {
@@ -691,17 +905,25 @@ int pcc_flows_give_samples(pcc_flows_handle h, const pcc_mi_batch *batch, int32_
     b.send_start = batch->send_start; b.send_end = batch->send_end; b.recv_start = batch->recv_start;
     b.recv_end = batch->recv_end; b.off = (const long long *)batch->rtt_offsets; b.rtt = batch->rtt_samples;
     const int64_t R = b.R;
-    // persistent grid: 32 records per block pass, at most 8 blocks per SM
+    // persistent grid: one resident wave (SM count x blocks per SM); every warp streams a contiguous run of records
     int64_t blocks = (R + 31) / 32;
-    const int64_t cap = (int64_t)h->sm_count * 8;
+    const int64_t cap = (int64_t)h->sm_count * PCCF_MINBLOCKS;
     if (blocks > cap) blocks = cap;
     int64_t lblocks = (R + 127) / 128;          // the long-list pass: 4 warps x 32 records per block pass
     if (lblocks > cap) lblocks = cap;
     h->batch_no++;
     if (h->batch_no == 0) h->batch_no = 1;
+    // cp.async.bulk needs a 16-byte aligned source: any other sample array goes through the read-only-path kernel
+    const bool tma = h->use_tma && (((uintptr_t)b.rtt) & 15) == 0;
+    int64_t tblocks = (R + 4 * PCCF_TMA_WARPS - 1) / (4 * PCCF_TMA_WARPS);
+    if (tblocks > (int64_t)h->sm_count * h->tma_blocks_per_sm) tblocks = (int64_t)h->sm_count * h->tma_blocks_per_sm;
     if (unique_flows) {
-        pcc_flows_ingest_kernel<true><<<(unsigned)blocks, PCCF_THREADS, 0, st>>>(h->d, b, h->batch_no, obs_dev, metrics_dev,
-                                                                                   nullptr, nullptr);
+        if (tma)
+            pcc_flows_ingest_tma_kernel<true><<<(unsigned)tblocks, PCCF_TMA_WARPS * 32, PCCF_TMA_SMEM, st>>>(
+                h->d, b, h->batch_no, obs_dev, metrics_dev, nullptr, nullptr);
+        else
+            pcc_flows_ingest_kernel<true><<<(unsigned)blocks, PCCF_THREADS, 0, st>>>(h->d, b, h->batch_no, obs_dev, metrics_dev,
+                                                                                       nullptr, nullptr);
         pcc_flows_long_kernel<true><<<(unsigned)lblocks, 128, 0, st>>>(h->d, b, h->batch_no, obs_dev, metrics_dev, nullptr, nullptr);
         CUDA_TRY(cudaGetLastError());
         h->launches += 2;
@@ -722,8 +944,12 @@ int pcc_flows_give_samples(pcc_flows_handle h, const pcc_mi_batch *batch, int32_
     int32_t *sflow = (int32_t *)(scratch + rows_b + avg_b + idx_b);
     int32_t *srec = (int32_t *)(scratch + rows_b + avg_b + 2 * idx_b);
     void *tmp = scratch + rows_b + avg_b + 3 * idx_b;
-    pcc_flows_ingest_kernel<false><<<(unsigned)blocks, PCCF_THREADS, 0, st>>>(h->d, b, h->batch_no, nullptr, metrics_dev,
-                                                                                rows, avg);
+    if (tma)
+        pcc_flows_ingest_tma_kernel<false><<<(unsigned)tblocks, PCCF_TMA_WARPS * 32, PCCF_TMA_SMEM, st>>>(
+            h->d, b, h->batch_no, nullptr, metrics_dev, rows, avg);
+    else
+        pcc_flows_ingest_kernel<false><<<(unsigned)blocks, PCCF_THREADS, 0, st>>>(h->d, b, h->batch_no, nullptr, metrics_dev,
+                                                                                    rows, avg);
     pcc_flows_long_kernel<false><<<(unsigned)lblocks, 128, 0, st>>>(h->d, b, h->batch_no, nullptr, metrics_dev, rows, avg);
     pcc_flows_iota_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(iota, R);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_b, b.flow, sflow, (const int32_t *)iota, srec, (int)R, 0, 32, st);
@@ -801,11 +1027,13 @@ int pcc_flows_get_column(pcc_flows_handle h, const char *name, double *dst_dev, 
 {
     if (!h || !name || !dst_dev) return fail(PCC_EINVAL, "null pointer");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const double *src = nullptr;
-    if (!strcmp(name, "conn_min")) src = h->d.conn_min;
-    else if (!strcmp(name, "rate")) src = h->d.rate;
+    int which;
+    if (!strcmp(name, "conn_min")) which = 0;
+    else if (!strcmp(name, "rate")) which = 1;
     else return fail(PCC_EINVAL, "unknown column %s", name);
-    CUDA_TRY(cudaMemcpyAsync(dst_dev, src, (size_t)h->d.n_flows * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    pcc_flows_column_kernel<<<(unsigned)((h->d.n_flows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d, which, dst_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
     return PCC_OK;
 }
 

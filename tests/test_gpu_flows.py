@@ -256,3 +256,35 @@ def test_flows_device_policy_matches_torch():
     r0 = mon.get_rates().clone()
     r1 = mon.get_rates(actions=a.numpy())
     assert (r0 == 0).all() and r1.shape == (n_flows,)
+
+
+@pytest.mark.parametrize("kernel", ["tma", "ldg"])
+def test_flows_both_ingest_kernels_and_misaligned_samples(kernel, monkeypatch):
+    """The TMA-staged kernel (default) and the read-only-path kernel give identical histories; a sample array that
+    is not 16-byte aligned (cp.async.bulk cannot take it) silently uses the latter."""
+    import pcc_rl_b200
+    import torch
+    monkeypatch.setenv("PCC_FLOWS_KERNEL", kernel)
+    n_flows = 20000
+    rng = np.random.default_rng(123)
+    feats = "send rate,avg latency,latency increase,ack latency inflation,latency ratio"
+    import oracle
+    fl = oracle.OracleFlows(n_flows, 10, feats)
+    mon = pcc_rl_b200.PccFlowMonitor(n_flows, 10, feats)
+    for it in range(3):
+        b = synth_batch(rng, n_flows - 3, n_flows, mean_samples=[3, 140, 400][it], unique=True, t0=float(it))
+        dev = mon.make_batch(**b)
+        if it == 1:     # shift the sample array by one element: 8-byte aligned only
+            pad = torch.empty(dev["rtt"].numel() + 1, dtype=torch.float64, device=dev["rtt"].device)
+            pad[1:] = dev["rtt"]
+            dev["rtt"] = pad[1:]
+            assert dev["rtt"].data_ptr() % 16 == 8
+        o, _ = mon.give_samples(dev, unique_flows=True)
+        fl.give_batch(b)
+        o = o.cpu().numpy()
+        for r in list(range(0, len(b["flow"]), 37)) + [len(b["flow"]) - 1, len(b["flow"]) - 2]:
+            assert np.array_equal(o[r], fl.obs(int(b["flow"][r]))), "batch %d record %d" % (it, r)   # unique batch
+    final = mon.obs().cpu().numpy()
+    for i in range(0, n_flows, 7):
+        assert np.array_equal(final[i], fl.obs(i)), "flow %d" % i
+    mon.check()
