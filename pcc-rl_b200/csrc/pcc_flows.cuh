@@ -86,6 +86,28 @@ __device__ __forceinline__ double sg_leaf(const double *__restrict__ a, int n, i
     return r;
 }
 
+// The same leaf for code that all 32 lanes execute together (the four subgroups sum four different leaves of
+// possibly different lengths, n == 0 included): no branch around the shuffles, which can then use the full-warp
+// mask (a subgroup mask held in a register costs a WARPSYNC.COLLECTIVE bracket per shuffle).  n < 8 is numpy's
+// sequential case: the accumulator part is skipped by nb = 0 and the "tail" adds all n elements to 0.0.
+template <bool LDG>
+__device__ __forceinline__ double sg_leaf_uniform(const double *__restrict__ a, int n, int j)
+{
+    const int nb = (n >= 8) ? n - (n & 7) : 0;
+    double r = 0.0;
+    if (nb) r = ld_sample<LDG>(a + j);
+#pragma unroll 8
+    for (int k = 8; k < nb; k += 8) r += ld_sample<LDG>(a + k + j);
+    r += __shfl_xor_sync(PCCF_FULL, r, 1);
+    r += __shfl_xor_sync(PCCF_FULL, r, 2);
+    r += __shfl_xor_sync(PCCF_FULL, r, 4);
+    const int nt = n - nb;                       // 0..7 elements, added in order
+    const double *t = a + nb;
+#pragma unroll
+    for (int k = 0; k < 7; k++) if (k < nt) r += ld_sample<LDG>(t + k);
+    return r;
+}
+
 // numpy's pairwise sum of a[0..n), n <= PCCF_SG_MAX_N, by ONE subgroup (subgroup-uniform control flow and result).
 // Iterative post-order walk of the recursion (n > 128: n2 = n/2 rounded down to a multiple of 8; sum(left n2) +
 // sum(right n - n2)); leaves tile [0, n) left to right.  A node at depth d holds at most n/2^d + 15 elements, so
@@ -206,6 +228,36 @@ __device__ __noinline__ double warp_pw_sum(const double *__restrict__ a, long lo
     return result;
 }
 
+// The three pairwise sums of a record (all, first half, second half) for the four subgroups of a warp together.
+// Called by all 32 lanes.  A record whose ranges are at most two leaves deep (n <= 248: all = leaf + leaf,
+// halves = one leaf each) takes four warp-uniform leaf steps; anything longer walks numpy's recursion per
+// subgroup (sg_pw_sum).  `on` = the subgroup has a record to sum.
+#define PCCF_FLAT_MAX_N 248
+template <bool LDG>
+__device__ __forceinline__ void pass_sums(const double *a, long long n, bool on, int j, unsigned sgmask,
+                                          double &sum, double &s1, double &s2)
+{
+    sum = 0.0; s1 = 0.0; s2 = 0.0;
+    const int nn = (int)n;
+    const int half = nn / 2;
+    const bool flat = on && nn <= PCCF_FLAT_MAX_N;
+    int n2 = nn >> 1;
+    n2 -= n2 & 7;                                    // numpy's split of the whole range when n > 128
+    const int c0 = !flat ? 0 : (nn > 128 ? n2 : nn);
+    const int c1 = !flat ? 0 : (nn > 128 ? nn - n2 : 0);
+    const double l0 = sg_leaf_uniform<LDG>(a, c0, j);
+    const double l1 = sg_leaf_uniform<LDG>(a + c0, c1, j);
+    const double l2 = sg_leaf_uniform<LDG>(a, flat ? half : 0, j);
+    const double l3 = sg_leaf_uniform<LDG>(a + half, flat ? nn - half : 0, j);
+    if (flat) {
+        sum = (nn > 128) ? l0 + l1 : l0;
+        s1 = l2; s2 = l3;
+    } else if (on) {                                 // subgroup-divergent: deeper recursions
+        sum = sg_pw_sum<LDG>(a, nn, j, sgmask);
+        if (half >= 1) { s1 = sg_pw_sum<LDG>(a, half, j, sgmask); s2 = sg_pw_sum<LDG>(a + half, nn - half, j, sgmask); }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Ingest kernel.  UNIQUE: every flow appears at most once in the batch (checked): metrics, conn-min entry,
 // history row and observation in this one kernel.  !UNIQUE: the per-record part only; rows[R][F] (scaled
@@ -220,10 +272,37 @@ __device__ __forceinline__ void flows_finish_record(const FlowsDev &p, const Bat
                                                     double sum, double s1, double s2, bool good, int j, int sg0,
                                                     unsigned sgmask, uint32_t batch_no, double *__restrict__ obs,
                                                     double *__restrict__ metrics, double *__restrict__ rows,
-                                                    double *__restrict__ avg_out)
+                                                    double *__restrict__ avg_out, double *xs)
 {
+    // xs: 16 doubles of shared memory private to the subgroup (the new history row, handed to the lanes that
+    // write the observation)
     const int H = p.H, F = p.F, HF = H * F;
     const long long half = n / 2;
+    // ---- per-flow state and the old history row: requested first, consumed after the divisions -----------
+    uint32_t fl = 0; double cmin = 0.0, cm = 0.0;
+    bool has_min = false;
+    uint32_t n_rec = 0;
+    double hold[4] = {0.0, 0.0, 0.0, 0.0};
+    int rot = 0;
+    uint32_t head = 0, nhead = 0;
+    if (UNIQUE && good) {
+        const FlowState fs = p.st[flow];              // one 32-byte sector
+        fl = fs.flags; cmin = fs.conn_min; n_rec = fs.n_rec;
+        has_min = (fl & PCCF_HAS_MIN) != 0;
+        head = fl & PCCF_HEAD_MASK;
+        nhead = (head + 1 == (uint32_t)H) ? 0u : head + 1;
+        rot = (int)nhead * F;
+        if (obs && HF <= 32) {                        // as_array (:68-73): oldest row first = the ring rotated by nhead
+            const double *hrow = p.hist + (size_t)flow * HF;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int k = j + 8 * t;
+                int src = k + rot;
+                if (src >= HF) src -= HF;
+                if (k < HF) hold[t] = hrow[src];
+            }
+        }
+    }
     // ---- the record's scalar fields (loaded after the sums: they are not live across the sample passes) --
     long long bs = 0, ba = 0, bl = 0, ps = 0;
     double ss = 0., se = 0., rs = 0., re = 0.;
@@ -246,24 +325,16 @@ __device__ __forceinline__ void flows_finish_record(const FlowsDev &p, const Bat
     else if (j == 5) { num = (double)bl; den = (double)(bl + ba); ok = (bl + ba) > 0; }     // loss ratio
     double q = num / (ok ? den : 1.0);
     if (!ok) q = 0.0;
-    const double send_rate = __shfl_sync(sgmask, q, sg0 + 0);
-    const double recv_rate = __shfl_sync(sgmask, q, sg0 + 1);
-    const double avg = __shfl_sync(sgmask, q, sg0 + 2);
-    const double m1 = __shfl_sync(sgmask, q, sg0 + 3);
-    const double m2 = __shfl_sync(sgmask, q, sg0 + 4);
-    const double loss = __shfl_sync(sgmask, q, sg0 + 5);
+    const double send_rate = __shfl_sync(PCCF_FULL, q, sg0 + 0);
+    const double recv_rate = __shfl_sync(PCCF_FULL, q, sg0 + 1);
+    const double avg = __shfl_sync(PCCF_FULL, q, sg0 + 2);
+    const double m1 = __shfl_sync(PCCF_FULL, q, sg0 + 3);
+    const double m2 = __shfl_sync(PCCF_FULL, q, sg0 + 4);
+    const double loss = __shfl_sync(PCCF_FULL, q, sg0 + 5);
     const double inc = (half >= 1) ? m2 - m1 : 0.0;
 
     // ---- conn-min dict entry (:158-176) -----------------------------------------------------------------
-    uint32_t fl = 0; double cmin = 0.0, cm = 0.0;
-    bool has_min = false;
-    uint32_t n_rec = 0;
-    if (UNIQUE && good) {
-        const FlowState fs = p.st[flow];          // one 32-byte sector
-        fl = fs.flags; cmin = fs.conn_min; n_rec = fs.n_rec;
-        has_min = (fl & PCCF_HAS_MIN) != 0;
-        cm = flow_conn_min(avg, has_min, cmin, p.touch_conn != 0);
-    }
+    if (UNIQUE && good) cm = flow_conn_min(avg, has_min, cmin, p.touch_conn != 0);
 
     // ---- round 2 --------------------------------------------------------------------------------------
     double dflt = 0.0;
@@ -277,12 +348,12 @@ __device__ __forceinline__ void flows_finish_record(const FlowsDev &p, const Bat
     else if (j == 5) { num = recv_rate; den = 1e7; ok = true; }
     q = num / (ok ? den : 1.0);
     if (!ok) q = dflt;
-    const double ack_infl = __shfl_sync(sgmask, q, sg0 + 0);
-    const double sent_infl = __shfl_sync(sgmask, q, sg0 + 1);
-    const double lat_ratio = __shfl_sync(sgmask, q, sg0 + 2);
-    const double send_ratio = __shfl_sync(sgmask, q, sg0 + 3);
-    const double send_rate_s = __shfl_sync(sgmask, q, sg0 + 4);
-    const double recv_rate_s = __shfl_sync(sgmask, q, sg0 + 5);
+    const double ack_infl = __shfl_sync(PCCF_FULL, q, sg0 + 0);
+    const double sent_infl = __shfl_sync(PCCF_FULL, q, sg0 + 1);
+    const double lat_ratio = __shfl_sync(PCCF_FULL, q, sg0 + 2);
+    const double send_ratio = __shfl_sync(PCCF_FULL, q, sg0 + 3);
+    const double send_rate_s = __shfl_sync(PCCF_FULL, q, sg0 + 4);
+    const double recv_rate_s = __shfl_sync(PCCF_FULL, q, sg0 + 5);
 
     auto raw = [&](int id) -> double {
         switch (id) {
@@ -307,14 +378,13 @@ __device__ __forceinline__ void flows_finish_record(const FlowsDev &p, const Bat
         if (j + 8 < N_METRICS) metrics[r * N_METRICS + j + 8] = raw(j + 8);
     }
     if (UNIQUE) {
-        const uint32_t head = fl & PCCF_HEAD_MASK;
         double *hrow = p.hist + (size_t)flow * HF;
         for (int f = j; f < F; f += 8) {                                // SenderHistory.step (:64-66)
             const int id = p.ids[f];
             const double v = (id == M_SEND_RATE) ? send_rate_s : (id == M_RECV_RATE) ? recv_rate_s : raw(id);
             hrow[head * F + f] = v;
+            xs[f] = v;
         }
-        const uint32_t nhead = (head + 1 == (uint32_t)H) ? 0u : head + 1;
         if (j == 0) {
             FlowState *fs = p.st + flow;
             if (atomicExch(&fs->stamp, batch_no) == batch_no) atomicAdd(&p.meta[0], 1ull);
@@ -325,11 +395,21 @@ __device__ __forceinline__ void flows_finish_record(const FlowsDev &p, const Bat
         if (obs) {                                                      // as_array (:68-73): oldest row first
             __syncwarp(sgmask);
             double *ob = obs + (size_t)r * HF;
-            const int rot = (int)nhead * F;
-            for (int k = j; k < HF; k += 8) {
-                int src = k + rot;
-                if (src >= HF) src -= HF;
-                ob[k] = hrow[src];
+            const int lo = (int)head * F;                               // the slot that now holds the new row
+            if (HF <= 32) {                                             // old rows were requested at the top
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int k = j + 8 * t;
+                    int src = k + rot;
+                    if (src >= HF) src -= HF;
+                    if (k < HF) ob[k] = (src >= lo && src < lo + F) ? xs[src - lo] : hold[t];
+                }
+            } else {
+                for (int k = j; k < HF; k += 8) {
+                    int src = k + rot;
+                    if (src >= HF) src -= HF;
+                    ob[k] = hrow[src];
+                }
             }
         }
     } else {
@@ -352,6 +432,7 @@ pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__res
     const int sg0 = sg * 8;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    __shared__ double xchg[(PCCF_THREADS / 32) * 4 * 16];
 
     // A warp owns a contiguous run of records (4 per pass, one per subgroup): its offsets, fields and samples are
     // one sequential stream; the next pass's offsets and flow id are loaded a pass ahead.  (Measured: an additional
@@ -383,24 +464,15 @@ pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__res
         bool good = valid && flow >= 0 && (long long)flow < p.n_flows && n >= 0;
         if (valid && !good && j == 0) atomicAdd(&p.meta[1], 1ull);
         if (!good) n = 0;
-        const long long half = n / 2;
 
-        // ---- the three pairwise sums (all, first half, second half): one code site, three passes ------------
-        // Passes 2 and 3 re-read the samples the first pass pulled from HBM (L1/L2 hits; numpy's summation trees
-        // of the three ranges share nothing, so the sums cannot be shared either).
-        double sum = 0.0, s1 = 0.0, s2 = 0.0;
+        // ---- the three pairwise sums (all, first half, second half) ------------------------------------------
+        // The halves re-read the samples the first range pulled from HBM (L1/L2 hits; numpy's summation trees of
+        // the three ranges share nothing, so the sums cannot be shared either).
+        double sum, s1, s2;
         if (n > PCCF_SG_MAX_N) good = false;      // a very long sample list: left to pcc_flows_long_kernel
-        const bool in_sg = good && n > 0;
-#pragma unroll 1
-        for (int q = 0; q < 3; q++) {
-            const long long lo = (q == 2) ? half : 0;
-            const long long len = (q == 0) ? n : (q == 1) ? half : n - half;
-            if (in_sg && (q == 0 || half >= 1)) {
-                const double v = sg_pw_sum<true>(a + lo, (int)len, j, sgmask);
-                if (q == 0) sum = v; else if (q == 1) s1 = v; else s2 = v;
-            }
-        }
-        flows_finish_record<UNIQUE>(p, b, r, flow, n, sum, s1, s2, good, j, sg0, sgmask, batch_no, obs, metrics, rows, avg_out);
+        pass_sums<true>(a, n, good && n > 0, j, sgmask, sum, s1, s2);
+        flows_finish_record<UNIQUE>(p, b, r, flow, n, sum, s1, s2, good, j, sg0, sgmask, batch_no, obs, metrics, rows, avg_out,
+                                    xchg + ((threadIdx.x >> 5) * 4 + sg) * 16);
     }
 }
 
@@ -425,7 +497,7 @@ pcc_flows_ingest_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__res
 #ifndef PCCF_TMA_MINBLOCKS
 #define PCCF_TMA_MINBLOCKS 8     // 8 blocks x 4 warps per SM: 64 registers, 8 x 24.1 KB of shared memory
 #endif
-#define PCCF_TMA_SMEM ((size_t)PCCF_TMA_WARPS * PCCF_TMA_SLOT * 8 + (size_t)PCCF_TMA_WARPS * 8)
+#define PCCF_TMA_SMEM ((size_t)PCCF_TMA_WARPS * PCCF_TMA_SLOT * 8 + (size_t)PCCF_TMA_WARPS * 8 + (size_t)PCCF_TMA_WARPS * 4 * 16 * 8)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
@@ -472,6 +544,8 @@ pcc_flows_ingest_tma_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *_
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     double *stage = reinterpret_cast<double *>(pccf_smem) + (size_t)wib * PCCF_TMA_SLOT;
     uint64_t *bar = reinterpret_cast<uint64_t *>(pccf_smem + (size_t)PCCF_TMA_WARPS * PCCF_TMA_SLOT * 8) + wib;
+    double *xs = reinterpret_cast<double *>(pccf_smem + (size_t)PCCF_TMA_WARPS * PCCF_TMA_SLOT * 8 + (size_t)PCCF_TMA_WARPS * 8) +
+                 (wib * 4 + sg) * 16;
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
@@ -532,25 +606,15 @@ pcc_flows_ingest_tma_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *_
         if (valid && !good && j == 0) atomicAdd(&p.meta[1], 1ull);
         if (!good) n = 0;
         if (n > PCCF_SG_MAX_N) good = false;                               // left to pcc_flows_long_kernel
-        const long long half = n / 2;
         mbar_wait(bar, (uint32_t)(pass & 1));
         const double *a = (e0a_c >= 0) ? stage + (o0c - e0a_c) : b.rtt + o0c;
-        double sum = 0.0, s1 = 0.0, s2 = 0.0;
-        const bool in_sg = good && n > 0;
-#pragma unroll 1
-        for (int q = 0; q < 3; q++) {
-            const long long lo = (q == 2) ? half : 0;
-            const long long len = (q == 0) ? n : (q == 1) ? half : n - half;
-            if (in_sg && (q == 0 || half >= 1)) {
-                const double v = sg_pw_sum<false>(a + lo, (int)len, j, sgmask);
-                if (q == 0) sum = v; else if (q == 1) s1 = v; else s2 = v;
-            }
-        }
+        double sum, s1, s2;
+        pass_sums<false>(a, n, good && n > 0, j, sgmask, sum, s1, s2);
         __syncwarp();                                                      // the stage has been read: refill it ...
         long long e0a_n = -1;
         if (base + 4 < wend) e0a_n = issue(base + 4, o0n, o1n);
         // ... while this pass's records are finished
-        flows_finish_record<UNIQUE>(p, b, r, flow, n, sum, s1, s2, good, j, sg0, sgmask, batch_no, obs, metrics, rows, avg_out);
+        flows_finish_record<UNIQUE>(p, b, r, flow, n, sum, s1, s2, good, j, sg0, sgmask, batch_no, obs, metrics, rows, avg_out, xs);
         o0c = o0n; o1c = o1n; flowc = flown; e0a_c = e0a_n;
         o0n = o0f; o1n = o1f; flown = flowf;
     }
