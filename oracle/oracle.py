@@ -333,7 +333,7 @@ class OracleFlows(object):
                                       _p(m, C.c_double) if want_metrics else None)
         return m
 
-    def give_batch(self, b):
+    def give_batch(self, b, n_threads=1):
         """b: dict in the layout of tests/flows_util.synth_batch; returns seconds spent in C."""
         import time
         v = lambda k, dt: np.ascontiguousarray(b[k], dtype=dt)
@@ -341,8 +341,12 @@ class OracleFlows(object):
             [v(k, np.float64) for k in ("send_start", "send_end", "recv_start", "recv_end")] + \
             [v("packet_size", np.int64), v("rtt_off", np.int64), v("rtt", np.float64)]
         self.L.pcco_flows_give_batch.argtypes = [C.c_void_p, C.c_long] + [C.c_void_p] * 11
+        self.L.pcco_flows_give_batch_mt.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 11
         t0 = time.perf_counter()
-        self.L.pcco_flows_give_batch(self.h, len(a[0]), *[x.ctypes.data for x in a])
+        if n_threads > 1:
+            self.L.pcco_flows_give_batch_mt(self.h, int(n_threads), len(a[0]), *[x.ctypes.data for x in a])
+        else:
+            self.L.pcco_flows_give_batch(self.h, len(a[0]), *[x.ctypes.data for x in a])
         return time.perf_counter() - t0
 
     def obs(self, flow):

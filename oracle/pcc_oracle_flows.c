@@ -258,3 +258,39 @@ void pcco_flows_give_batch(pccf_flows *fs, long n_records, const int *flow, cons
                                recv_start[r], recv_end[r], rtt + rtt_off[r], (long)(rtt_off[r + 1] - rtt_off[r]),
                                packet_size[r], NULL);
 }
+
+/* The same batch on n_threads host threads (bench.py --impl reference --workload flows): a flow's records stay on
+ * one thread (flow % n_threads), so per-flow order is preserved and no state is shared. */
+#include <pthread.h>
+typedef struct {
+    pccf_flows *fs; long n_records; int tid, n_threads;
+    const int *flow; const long long *bs, *ba, *bl; const double *ss, *se, *rs, *re; const long long *ps, *off;
+    const double *rtt;
+} pccf_job;
+static void *pccf_worker(void *arg)
+{
+    pccf_job *j = (pccf_job *)arg;
+    for (long r = 0; r < j->n_records; r++) {
+        if (j->flow[r] % j->n_threads != j->tid) continue;
+        pcco_flows_give_sample(j->fs, j->flow[r], j->bs[r], j->ba[r], j->bl[r], j->ss[r], j->se[r], j->rs[r], j->re[r],
+                               j->rtt + j->off[r], (long)(j->off[r + 1] - j->off[r]), j->ps[r], NULL);
+    }
+    return NULL;
+}
+void pcco_flows_give_batch_mt(pccf_flows *fs, int n_threads, long n_records, const int *flow, const long long *bytes_sent,
+                              const long long *bytes_acked, const long long *bytes_lost, const double *send_start,
+                              const double *send_end, const double *recv_start, const double *recv_end,
+                              const long long *packet_size, const long long *rtt_off, const double *rtt)
+{
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 512) n_threads = 512;
+    pthread_t th[512];
+    pccf_job jobs[512];
+    for (int t = 0; t < n_threads; t++) {
+        pccf_job jb = {fs, n_records, t, n_threads, flow, bytes_sent, bytes_acked, bytes_lost, send_start, send_end,
+                       recv_start, recv_end, packet_size, rtt_off, rtt};
+        jobs[t] = jb;
+        pthread_create(&th[t], NULL, pccf_worker, &jobs[t]);
+    }
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+}
