@@ -1,6 +1,6 @@
 #!/bin/bash
 # Runs of record on the B200 box (under gpurun): GPU test suite, bench lines, ncu launch lists and full captures.
-# Usage: gpurun -- 'bash tools/run_of_record.sh r02'      (outputs under gpurun_out/<tag>_*)
+# Usage: gpurun -- 'bash tools/run_of_record.sh r01b'      (outputs under gpurun_out/<tag>_*)
 tag=${1:-rXX}
 out=gpurun_out
 mkdir -p $out
