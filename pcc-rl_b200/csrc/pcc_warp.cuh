@@ -457,6 +457,7 @@ __device__ __forceinline__ void lane_send_phase(LaneChain &c, const EnvState &s,
         lane_send_one(c, s, ring, h2, cap, inv_rate, res53(rng.w2, rng.w3));
         rng.draws++;
     }
+#ifdef PCC_NO_PHILOX_PIPELINE
     while (c.t < end) {
         uint32_t a, b;
         rng.block(rng.draws >> 1, a, b, rng.w2, rng.w3);
@@ -467,8 +468,27 @@ __device__ __forceinline__ void lane_send_phase(LaneChain &c, const EnvState &s,
             rng.draws++;
         }
     }
+#else
+    // Software pipeline: the Philox block of the NEXT two packets is computed next to the queue recurrence of the
+    // current two.  The two are independent dependency chains (about 100 and 2 x 42 cycles of latency), so issued
+    // interleaved they overlap instead of adding up; the price is one unused block per env and MI.
+    if (!(c.t < end)) return;
+    uint32_t a, b, w2, w3;
+    rng.block(rng.draws >> 1, a, b, w2, w3);
+    for (;;) {      // here: c.t < end, draws even, (a, b, w2, w3) = block draws >> 1
+        uint32_t na, nb, nw2, nw3;
+        rng.block((rng.draws >> 1) + 1, na, nb, nw2, nw3);
+        lane_send_one(c, s, ring, h2, cap, inv_rate, res53(a, b));
+        rng.draws++;
+        rng.w2 = w2; rng.w3 = w3;                       // the cached second half of the block `draws` now points into
+        if (!(c.t < end)) break;
+        lane_send_one(c, s, ring, h2, cap, inv_rate, res53(w2, w3));
+        rng.draws++;
+        if (!(c.t < end)) break;
+        a = na; b = nb; w2 = nw2; w3 = nw3;
+    }
+#endif
 }
-
 
 // Same as lane_send_phase, but the records are staged in shared memory (8 per lane) and written to
 // the rings by the whole warp: 8 lanes copy one env's 128-byte line, 4 envs per store instruction.
