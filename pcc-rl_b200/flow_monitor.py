@@ -40,7 +40,10 @@ _FIELDS_F64 = ("send_start", "send_end", "recv_start", "recv_end")
 
 class PccFlowMonitor(object):
     def __init__(self, n_flows, history_len=10, features=sender_obs.DEFAULT_FEATURES, device=None,
-                 delta_scale=0.05, min_rate=0.5, max_rate=300.0, rate_style=_lib.PCC_RATE_CLIENT, start_rate=0.0):
+                 delta_scale=0.05, min_rate=0.5, max_rate=300.0, rate_style=_lib.PCC_RATE_CLIENT, start_rate=0.0,
+                 workspace=None):
+        """workspace: a uint8 CUDA tensor holding the state of another monitor of the same shape (its `.workspace`,
+        e.g. restored with torch.load): the new monitor adopts it as is (pcc_flows_attach) -- checkpoint / resume."""
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("pcc_rl_b200.PccFlowMonitor needs a CUDA device; there is no CPU fallback")
@@ -62,12 +65,18 @@ class PccFlowMonitor(object):
         nb = C.c_uint64()
         _lib.check(self.L.pcc_flows_workspace_bytes(C.byref(cfg), C.byref(nb)))
         with torch.cuda.device(self.device):
-            self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)   # = the checkpoint
             self.h = C.c_void_p()
-            _lib.check(self.L.pcc_flows_create(C.byref(self.h), C.byref(cfg), self.workspace.data_ptr()))
+            if workspace is not None:
+                if workspace.dtype != torch.uint8 or workspace.numel() != nb.value or not workspace.is_cuda:
+                    raise ValueError("workspace must be a uint8 CUDA tensor of %d bytes" % nb.value)
+                self.workspace = workspace.to(self.device).contiguous()
+                _lib.check(self.L.pcc_flows_attach(C.byref(self.h), C.byref(cfg), self.workspace.data_ptr()))
+            else:
+                self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)   # = the checkpoint
+                _lib.check(self.L.pcc_flows_create(C.byref(self.h), C.byref(cfg), self.workspace.data_ptr()))
         self._keep = None
         self._policy = None
-        if start_rate:
+        if start_rate and workspace is None:
             self.set_rates(rate=start_rate)
 
     # -- plumbing ---------------------------------------------------------------------------------------

@@ -288,3 +288,25 @@ def test_flows_both_ingest_kernels_and_misaligned_samples(kernel, monkeypatch):
     for i in range(0, n_flows, 7):
         assert np.array_equal(final[i], fl.obs(i)), "flow %d" % i
     mon.check()
+
+
+def test_flows_checkpoint_attach():
+    """The workspace is the whole state: a monitor attached to a copy continues bit-identically."""
+    import pcc_rl_b200
+    import torch
+    n_flows = 5000
+    rng = np.random.default_rng(9)
+    feats = "conn min latency,latency ratio,send ratio,loss ratio"
+    a = pcc_rl_b200.PccFlowMonitor(n_flows, 7, feats, start_rate=6.0)
+    for it in range(3):
+        a.give_samples(a.make_batch(**synth_batch(rng, n_flows, n_flows, mean_samples=50, t0=float(it))), unique_flows=True,
+                       want_obs=False)
+    a.get_rates(actions=rng.normal(0, 1, n_flows))
+    torch.cuda.synchronize()
+    b = pcc_rl_b200.PccFlowMonitor(n_flows, 7, feats, workspace=a.workspace.clone())
+    assert torch.equal(a.obs(), b.obs()) and torch.equal(a.get_rates(), b.get_rates())
+    nxt = synth_batch(rng, n_flows, n_flows, mean_samples=50, t0=9.0)
+    oa, _ = a.give_samples(a.make_batch(**nxt), unique_flows=True)
+    ob, _ = b.give_samples(b.make_batch(**nxt), unique_flows=False)
+    assert torch.equal(oa, ob) and torch.equal(a.column("conn_min"), b.column("conn_min"))
+    a.check(); b.check()
