@@ -385,11 +385,28 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
 #pragma unroll 1
     for (int j = 0; j < cnt; j++) {
         if (!__shfl_sync(PCC_FULL, (int)owner, j)) continue;
-        if (j + 1 < cnt && __shfl_sync(PCC_FULL, (int)owner, j + 1)) {
-            // pull the next env's cursor neighbourhoods into L1 while this one is processed
-            const long long en = __shfl_sync(PCC_FULL, (long long)e, j + 1);
-            const uint32_t h1n = __shfl_sync(PCC_FULL, s.h1, j + 1), h2n = __shfl_sync(PCC_FULL, s.h2, j + 1);
-            const uint32_t tn = __shfl_sync(PCC_FULL, c.tail, j + 1);
+#ifndef PCC_PREFETCH_AHEAD
+#define PCC_PREFETCH_AHEAD 1
+#endif
+        const int jn = j + PCC_PREFETCH_AHEAD;
+        if (j == 0 && PCC_PREFETCH_AHEAD > 1) {   // envs 1 .. AHEAD-1 are not covered by the steady-state prefetch
+#pragma unroll
+            for (int jj = 1; jj < PCC_PREFETCH_AHEAD; jj++)
+                if (jj < cnt && __shfl_sync(PCC_FULL, (int)owner, jj)) {
+                    const long long en = __shfl_sync(PCC_FULL, (long long)e, jj);
+                    const uint32_t h1n = __shfl_sync(PCC_FULL, s.h1, jj), h2n = __shfl_sync(PCC_FULL, s.h2, jj);
+                    const uint32_t tn = __shfl_sync(PCC_FULL, c.tail, jj);
+                    const Rec *bn = p.rings + (size_t)en * p.cap;
+                    const uint32_t o = lane * 8u;
+                    if (o < (uint32_t)(tn - h1n)) prefetch_l1(bn + ((h1n + o) & (p.cap - 1u)));
+                    if (o < (uint32_t)(tn - h2n)) prefetch_l1(bn + ((h2n + o) & (p.cap - 1u)));
+                }
+        }
+        if (jn < cnt && __shfl_sync(PCC_FULL, (int)owner, jn)) {
+            // pull a later env's cursor neighbourhoods into L1 while this one is processed
+            const long long en = __shfl_sync(PCC_FULL, (long long)e, jn);
+            const uint32_t h1n = __shfl_sync(PCC_FULL, s.h1, jn), h2n = __shfl_sync(PCC_FULL, s.h2, jn);
+            const uint32_t tn = __shfl_sync(PCC_FULL, c.tail, jn);
             const Rec *bn = p.rings + (size_t)en * p.cap;
             const uint32_t o = lane * 8u;
             if (o < (uint32_t)(tn - h1n)) prefetch_l1(bn + ((h1n + o) & (p.cap - 1u)));

@@ -61,7 +61,12 @@ MIN_RATE = 40
 REWARD_SCALE = 0.001
 MAX_STEPS = 400
 BYTES_PER_PACKET = 1500
+# The reference's module switches (network_sim.py:51-54).  This drop-in class runs the shipped configuration
+# (both False) on the three-cursor kernels with Python's own MT19937 stream.  The two variants exist on the GPU
+# too -- PccMultiSenderEnv(n, n_senders=1, use_cwnd=True, use_latency_noise=True), Philox streams -- but not
+# behind this class: setting a switch here raises instead of silently simulating something else.
 USE_CWND = False
+USE_LATENCY_NOISE = False
 
 
 class SimulatedNetworkEnv(_EnvBase):
@@ -69,6 +74,9 @@ class SimulatedNetworkEnv(_EnvBase):
     def __init__(self, history_len=10,
                  features="sent latency inflation,latency ratio,send ratio", device=None):
         import torch
+        if USE_CWND or USE_LATENCY_NOISE:
+            raise NotImplementedError("USE_CWND / USE_LATENCY_NOISE: use pcc_rl_b200.PccMultiSenderEnv(n, n_senders=1, "
+                                      "use_cwnd=..., use_latency_noise=...) -- the drop-in env runs the shipped configuration")
         if not torch.cuda.is_available():
             raise RuntimeError("pcc_rl_b200.SimulatedNetworkEnv needs a CUDA device; there is no CPU fallback")
         self.torch = torch

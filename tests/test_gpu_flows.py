@@ -197,7 +197,7 @@ def test_flows_unique_equals_general_and_order_independent():
     and the record order inside a unique batch does not matter."""
     import pcc_rl_b200
     import torch
-    n_flows = 300000
+    n_flows = 1 << 20                   # the bench workload's size
     rng = np.random.default_rng(77)
     b = synth_batch(rng, n_flows, n_flows, mean_samples=100, unique=True)
     mons = [pcc_rl_b200.PccFlowMonitor(n_flows) for _ in range(3)]
