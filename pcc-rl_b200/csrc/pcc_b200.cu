@@ -328,12 +328,24 @@ pcc_reset_coop_kernel(DevState p, const uint8_t *__restrict__ mask, const double
 #define PCC_WARP_MINBLOCKS 4
 #endif
 
+// Small batches (PAIR): every block is a worker warp plus a helper warp.  When the worker owns a single heavy env it
+// offers the in-order consumption of the records that already exist (consume_scan_warp) to the helper, which runs it
+// while the worker is in its send phase; two named barriers (offer visible / result visible) order the hand-over.
+struct PairOffer {
+    int32_t valid, use_g;
+    uint32_t h1, h2, tail;
+    double end, dl;
+    long long e;
+    ScanOut res;
+};
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 // One MI for the E envs of this warp.  `owner` lanes hold their env's state in `s`.
-template <bool WANT_MEANS, bool DO_SEND>
+template <bool WANT_MEANS, bool DO_SEND, bool PAIR = false>
 __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, bool owner, int cnt, int64_t e, EnvState &s,
                                         PhiloxRng &rng, double dur, double *buf, int wbuf, WarpStage &stage, MiOut &mo,
                                         double &avg_lat, double &lat_inc, int32_t sent_before = 0,
-                                        long long *prof = nullptr, double *gscratch = nullptr)
+                                        long long *prof = nullptr, double *gscratch = nullptr, PairOffer *offer = nullptr)
 {
     const unsigned lane = g.gl;
     const double end = s.cur_time + dur;            // network_sim.py:124
@@ -344,6 +356,28 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
     c.sent = sent_before & 0x7fffffff; c.ovf = sent_before < 0;
     mo.start = s.cur_time;                          // reset_obs :319-324
     PCC_TICK(0);
+    bool offered = false;
+    int offered_use_g = 0;
+    if (PAIR) {
+        // lane 0 owns the env when cnt == 1.  Worth offering when there is something to consume already.
+        const uint32_t pend_old = __shfl_sync(PCC_FULL, (uint32_t)(s.tail - s.h2), 0);
+        offered = (cnt == 1) && (buf != nullptr) && pend_old >= 64u;
+        if (offered) {
+            // the staging buffer both warps will use: pending hop-2 events bound this MI's acked samples, and this
+            // MI adds at most (end - t) * rate + 3 records
+            double est = (end - s.next_send) * s.rate + 3.0;
+            est = __shfl_sync(PCC_FULL, est, 0);
+            const bool big = !(est < 1e9) || ((double)pend_old + est > (double)wbuf);
+            offered_use_g = (gscratch != nullptr && big) ? 1 : 0;
+        }
+        if (lane == 0) {
+            offer->valid = offered ? 1 : 0;
+            offer->use_g = offered_use_g;
+            offer->h1 = s.h1; offer->h2 = s.h2; offer->tail = s.tail;
+            offer->end = end; offer->dl = s.dl; offer->e = (long long)e;
+        }
+        pair_bar(1);                                 // the offer is visible to the helper warp
+    }
     // phase A: E serial chains side by side (already done by pcc_send_kernel when !DO_SEND)
     if (DO_SEND) {
         if (cnt == 1 && buf != nullptr) {
@@ -419,10 +453,18 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
         in.tail = __shfl_sync(PCC_FULL, c.tail, j);
         in.h1 = __shfl_sync(PCC_FULL, s.h1, j);
         in.h2 = __shfl_sync(PCC_FULL, s.h2, j);
+        in.acked0 = 0; in.lost0 = 0; in.s_begin = in.h2;
         // staging of this MI's acked latencies: shared memory, or -- when more than wbuf packets could be acked
         // (pending hop-2 events bound it) -- the warp's global scratch
         double *sbuf_j = buf;
         in.wbuf = wbuf;
+        if (PAIR && offered) {
+            // the helper warp has scanned the records that existed before the send phase: resume from its cursors
+            pair_bar(2);                             // its result (and the staged samples) are visible
+            if (offered_use_g) { sbuf_j = gscratch; in.wbuf = PCC_GSCRATCH; }
+            in.h1 = offer->res.h1; in.h2 = offer->res.h2;
+            in.acked0 = offer->res.acked; in.lost0 = offer->res.lost;
+        } else
         if (gscratch != nullptr && (uint32_t)(in.tail - in.h2) > (uint32_t)wbuf) { sbuf_j = gscratch; in.wbuf = PCC_GSCRATCH; }
 #ifdef PCC_PROFILE
         const long long tc0 = clock64();
@@ -472,30 +514,46 @@ struct WarpPartition {
     int32_t wbuf;             // staging capacity (samples) per warp
 };
 
-template <bool SPLIT>   // SPLIT: the sends of this MI were already done by pcc_send_kernel
+// SPLIT: the sends of this MI were already done by pcc_send_kernel.  PAIR (small batches): 64-thread blocks, warp 0
+// is the worker of partition slot blockIdx.x, warp 1 its helper (see PairOffer).
+template <bool SPLIT, bool PAIR = false>
 __global__ void __launch_bounds__(PCC_WARP_THREADS, PCC_WARP_MINBLOCKS)
 pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__ sent_tmp, unsigned long long head_step,
                      const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
                      uint8_t *__restrict__ done, int32_t *__restrict__ counts, double *__restrict__ info)
 {
-    extern __shared__ double dyn_smem[];      // per warp: warp_smem_bytes(part.wbuf)
+    extern __shared__ double dyn_smem[];      // per worker warp: warp_smem_bytes(part.wbuf)
     __shared__ WarpStage sstage[(SPLIT || !PCC_STAGED_STORES) ? 1 : PCC_WARP_THREADS / 32];
-    double *wsm = dyn_smem + (size_t)(threadIdx.x >> 5) * (warp_smem_bytes(part.wbuf) / 8);
+    __shared__ PairOffer pair_offer;
+    double *wsm = dyn_smem + (PAIR ? (size_t)0 : (size_t)(threadIdx.x >> 5) * (warp_smem_bytes(part.wbuf) / 8));
     const Grp<32> g;
     const unsigned lane = threadIdx.x & 31u;
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t w = PAIR ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
     int64_t first;
     int cnt;
     if (part.starts) {
         const int nw = *part.n_warps;
-        if (w >= nw) return;                       // whole warp
+        if (w >= nw) return;                       // whole warp (PAIR: the whole block)
         first = part.starts[w];
         cnt = (int)(part.starts[w + 1] - first);
     } else {
         first = w * part.static_e;
         if (first >= p.n) return;
         cnt = (int)((p.n - first < part.static_e) ? (p.n - first) : part.static_e);
+    }
+    if (PAIR && (threadIdx.x >> 5) == 1) {          // the helper warp
+        pair_bar(1);
+        if (pair_offer.valid) {
+            DevRing rj{p.rings + (size_t)pair_offer.e * p.cap, p.cap - 1u};
+            double *sb = pair_offer.use_g ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : wsm;
+            ScanOut so;
+            consume_scan_warp(g, pair_offer.end, pair_offer.dl, pair_offer.h1, pair_offer.h2, pair_offer.tail, rj, sb,
+                              pair_offer.use_g ? PCC_GSCRATCH : part.wbuf, so);
+            if (lane == 0) pair_offer.res = so;
+            pair_bar(2);
+        }
+        return;
     }
     const bool owner = (int)lane < cnt;
     const int64_t e = owner ? (part.perm ? (int64_t)part.perm[first + lane] : first + lane) : 0;
@@ -512,10 +570,10 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
 #else
     long long *prof = nullptr;
 #endif
-    warp_mi<true, !SPLIT>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf,
-                          sstage[(SPLIT || !PCC_STAGED_STORES) ? 0 : (threadIdx.x >> 5)], o.mi, avg_lat, lat_inc,
-                          SPLIT ? sent_tmp[e] : 0, prof,
-                          p.mean_scratch ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : nullptr);   // :416
+    warp_mi<true, !SPLIT, PAIR>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf,
+                                sstage[(SPLIT || !PCC_STAGED_STORES || PAIR) ? 0 : (threadIdx.x >> 5)], o.mi, avg_lat, lat_inc,
+                                SPLIT ? sent_tmp[e] : 0, prof,
+                                p.mean_scratch ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : nullptr, &pair_offer);   // :416
     if (!owner) return;
     mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
     s.steps += 1;                                                                // :419
@@ -984,6 +1042,7 @@ struct pcc_handle_s {
     bool split;
     bool scalar_sorted;
     int wbuf, warp_threads;   // warp kernel: staging capacity per warp, threads per block
+    bool pair;                // small batches: worker + helper warp per partition slot (pcc_step_warp_kernel<false, true>)
     int64_t max_warps;
     CostModel cm;
     // staging for pcc_step_host
@@ -1146,6 +1205,13 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         if (h->warp_threads != 32 && h->warp_threads != 64 && h->warp_threads != 128) h->warp_threads = 64;
         if (h->epw) {
             const size_t dyn = (size_t)(h->warp_threads / 32) * warp_smem_bytes(h->wbuf);
+            {
+                const char *pe = getenv("PCC_B200_PAIR");
+                h->pair = pe ? atoi(pe) != 0 : small_batch;
+                cudaError_t cp = cudaFuncSetAttribute(pcc_step_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      (int)warp_smem_bytes(h->wbuf));
+                if (cp != cudaSuccess) h->pair = false;
+            }
             cudaError_t ce = cudaFuncSetAttribute(pcc_step_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (ce == cudaSuccess) ce = cudaFuncSetAttribute(pcc_step_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (ce != cudaSuccess) { delete h; return fail(PCC_ECUDA, "dynamic shared memory: %s", cudaGetErrorString(ce)); }
@@ -1370,6 +1436,9 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
                                                                            obs_dev, reward_dev, done_dev, counts_dev,
                                                                            info_dev);
             h->launches++;
+        } else if (h->pair && part.perm) {
+            pcc_step_warp_kernel<false, true><<<(unsigned)nwarps, 64, warp_smem_bytes(h->wbuf), st>>>(
+                h->d, part, nullptr, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
         } else {
             pcc_step_warp_kernel<false><<<wgrid, h->warp_threads, dyn, st>>>(h->d, part, nullptr, h->head, actions_dev,
                                                                             obs_dev, reward_dev, done_dev, counts_dev,

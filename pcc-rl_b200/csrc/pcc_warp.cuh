@@ -39,7 +39,12 @@ struct ConsumeIn {
     double end, dl, tnext;
     uint32_t tail, h1, h2;
     int wbuf;          // capacity of the staging buffer
+    // resuming after consume_scan_warp (a helper warp ran the in-order scans over the records that existed before
+    // this MI's sends): events already counted and staged, and the MI's first hop-2 position.  Fresh: 0, 0, h2.
+    int32_t acked0, lost0;
+    uint32_t s_begin;
 };
+struct ScanOut { uint32_t h1, h2; int32_t acked, lost; };
 struct ConsumeOut {
     uint32_t h1, h2, s_begin, s_end;
     int32_t acked, lost;
@@ -116,6 +121,77 @@ __device__ __noinline__ void boundary2_slow(Ring ring, uint32_t h1, uint32_t h2,
     }
 }
 
+// The in-order part of phases (2) and (3) alone -- the two cursor scans, with the acked latencies staged -- over the
+// records below `tail`.  Both scans are prefix scans that stop at the first record they cannot consume, so running
+// them first with an earlier tail (the records that existed before this MI's sends) and then handing the cursors and
+// counts to consume_mi_warp with the final tail gives exactly what consume_mi_warp alone would: a helper warp does
+// this while the env's own warp is still in its send phase.  No boundary analysis, nothing is written to the ring.
+template <class Ring>
+__device__ __forceinline__ void consume_scan_warp(const Grp<32> &g, double end, double dl, uint32_t h1, uint32_t h2,
+                                                  uint32_t tail, Ring &ring, double *buf, int wbuf, ScanOut &out)
+{
+    constexpr int G = 32;
+    int32_t acked = 0, lost = 0;
+    for (;;) {
+        unsigned bm[PCC_SCAN_W];
+#pragma unroll
+        for (int w = 0; w < PCC_SCAN_W; w++) {
+            bool valid;
+            const Rec r = load_window(g, ring, h1 + (uint32_t)(w * G), tail, true, valid);
+            bm[w] = __ballot_sync(PCC_FULL, valid && (sgn(r.a) || r.a < end));
+        }
+        int adv = 0;
+        bool stop = false;
+#pragma unroll
+        for (int w = 0; w < PCC_SCAN_W; w++) {
+            const int nl = Grp<G>::lead_ones(bm[w]);
+            if (!stop) adv += nl;
+            stop = stop || (nl < G);
+        }
+        h1 += (uint32_t)adv;
+        if (stop) break;
+    }
+    for (;;) {
+        unsigned bm[PCC_SCAN_W], am[PCC_SCAN_W], lm[PCC_SCAN_W];
+        double l2[PCC_SCAN_W];
+#pragma unroll
+        for (int w = 0; w < PCC_SCAN_W; w++) {
+            bool valid;
+            const uint32_t i = h2 + (uint32_t)(w * G);
+            const Rec r = load_window(g, ring, i, tail, true, valid);
+            const bool dead = is_dead(r.a);
+            const bool c1 = ((int32_t)(i + g.gl - h1) < 0) || sgn(r.a);
+            const bool early = (absd(r.a) + dl) < end;
+            const bool cons = valid && (dead || (c1 && early));
+            bm[w] = __ballot_sync(PCC_FULL, cons);
+            am[w] = __ballot_sync(PCC_FULL, cons && !dead && !sgn(r.l));
+            lm[w] = __ballot_sync(PCC_FULL, cons && !dead && sgn(r.l));
+            l2[w] = r.l + dl;
+        }
+        int adv = 0;
+        bool stop = false;
+#pragma unroll
+        for (int w = 0; w < PCC_SCAN_W; w++) {
+            const int nl = Grp<G>::lead_ones(bm[w]);
+            const unsigned lead = Grp<G>::lowmask(nl);
+            const unsigned a_w = stop ? 0u : (am[w] & lead);
+            if ((a_w >> g.gl) & 1u) {
+                const int pos = acked + __popc(a_w & Grp<G>::lowmask((int)g.gl));
+                if (pos < wbuf) buf[pos] = l2[w];
+            }
+            if (!stop) {
+                acked += __popc(a_w);
+                lost += __popc(lm[w] & lead);
+                adv += nl;
+            }
+            stop = stop || (nl < G);
+        }
+        h2 += (uint32_t)adv;
+        if (stop) break;
+    }
+    out.h1 = h1; out.h2 = h2; out.acked = acked; out.lost = lost;
+}
+
 // Phases (2)-(4) of run_mi for ONE env by the whole warp.  All inputs and outputs warp-uniform.
 template <class Ring>
 __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeIn &in, Ring &ring, double *buf,
@@ -125,10 +201,10 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
     const double end = in.end;
     const uint32_t tail = in.tail;
     uint32_t h1 = in.h1, h2 = in.h2;
-    int32_t acked = 0, lost = 0;
+    int32_t acked = in.acked0, lost = in.lost0;
     out.has_extra = false;
     out.extra = 0.0;
-    out.s_begin = h2;
+    out.s_begin = in.s_begin;
 
     // ---- hop-1 events with a < end ----------------------------------------------------------
     for (;;) {
