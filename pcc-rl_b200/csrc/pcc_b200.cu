@@ -345,7 +345,8 @@ template <bool WANT_MEANS, bool DO_SEND, bool PAIR = false>
 __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, bool owner, int cnt, int64_t e, EnvState &s,
                                         PhiloxRng &rng, double dur, double *buf, int wbuf, WarpStage &stage, MiOut &mo,
                                         double &avg_lat, double &lat_inc, int32_t sent_before = 0,
-                                        long long *prof = nullptr, double *gscratch = nullptr, PairOffer *offer = nullptr)
+                                        long long *prof = nullptr, double *gscratch = nullptr, PairOffer *offer = nullptr,
+                                        bool pair = PAIR, int bar0 = 1)
 {
     const unsigned lane = g.gl;
     const double end = s.cur_time + dur;            // network_sim.py:124
@@ -358,7 +359,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
     PCC_TICK(0);
     bool offered = false;
     int offered_use_g = 0;
-    if (PAIR) {
+    if (PAIR && pair) {
         // lane 0 owns the env when cnt == 1.  Worth offering when there is something to consume already.
         const uint32_t pend_old = __shfl_sync(PCC_FULL, (uint32_t)(s.tail - s.h2), 0);
         offered = (cnt == 1) && (buf != nullptr) && pend_old >= 64u;
@@ -376,7 +377,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
             offer->h1 = s.h1; offer->h2 = s.h2; offer->tail = s.tail;
             offer->end = end; offer->dl = s.dl; offer->e = (long long)e;
         }
-        pair_bar(1);                                 // the offer is visible to the helper warp
+        pair_bar(bar0);                              // the offer is visible to the helper warp
     }
     // phase A: E serial chains side by side (already done by pcc_send_kernel when !DO_SEND)
     if (DO_SEND) {
@@ -460,7 +461,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
         in.wbuf = wbuf;
         if (PAIR && offered) {
             // the helper warp has scanned the records that existed before the send phase: resume from its cursors
-            pair_bar(2);                             // its result (and the staged samples) are visible
+            pair_bar(bar0 + 1);                      // its result (and the staged samples) are visible
             if (offered_use_g) { sbuf_j = gscratch; in.wbuf = PCC_GSCRATCH; }
             in.h1 = offer->res.h1; in.h2 = offer->res.h2;
             in.acked0 = offer->res.acked; in.lost0 = offer->res.lost;
@@ -512,11 +513,15 @@ struct WarpPartition {
     const int32_t *n_warps;   // device scalar
     int32_t static_e;
     int32_t wbuf;             // staging capacity (samples) per warp
+    int32_t n_pair_blocks;    // PAIRMODE 2: the first n_pair_blocks blocks (the heaviest slots) are worker + helper blocks
 };
 
-// SPLIT: the sends of this MI were already done by pcc_send_kernel.  PAIR (small batches): 64-thread blocks, warp 0
-// is the worker of partition slot blockIdx.x, warp 1 its helper (see PairOffer).
-template <bool SPLIT, bool PAIR = false>
+// SPLIT: the sends of this MI were already done by pcc_send_kernel.  PAIRMODE 1 (small batches): every block is
+// workers + helpers (64 threads: worker of partition slot blockIdx.x and its helper, see PairOffer).  PAIRMODE 2 (big
+// batches): only the first part.n_pair_blocks blocks -- the heaviest slots of the cost-sorted list, whose residency is
+// the kernel's critical path -- are worker + helper blocks; the others are all workers as in PAIRMODE 0 (a helper for
+// every slot would halve the occupancy that big batches live on).
+template <bool SPLIT, int PAIRMODE = 0>
 __global__ void __launch_bounds__(PCC_WARP_THREADS, PCC_WARP_MINBLOCKS)
 pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__ sent_tmp, unsigned long long head_step,
                      const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
@@ -524,11 +529,21 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
 {
     extern __shared__ double dyn_smem[];      // per worker warp: warp_smem_bytes(part.wbuf)
     __shared__ WarpStage sstage[(SPLIT || !PCC_STAGED_STORES) ? 1 : PCC_WARP_THREADS / 32];
-    __shared__ PairOffer pair_offer;
-    double *wsm = dyn_smem + (PAIR ? (size_t)0 : (size_t)(threadIdx.x >> 5) * (warp_smem_bytes(part.wbuf) / 8));
+    __shared__ PairOffer pair_offers[PCC_WARP_THREADS / 64];
+    constexpr bool PAIR = PAIRMODE != 0;
+    const bool pair_blk = PAIRMODE == 1 || (PAIRMODE == 2 && (int)blockIdx.x < part.n_pair_blocks);
+    const int wib = (int)(threadIdx.x >> 5), wpb = (int)(blockDim.x >> 5), half = wpb >> 1;
+    // pair block: warps 0 .. half-1 are workers, warp half + i is the helper of worker i
+    const int pi = pair_blk ? wib % half : 0;
+    const bool helper = pair_blk && wib >= half;
+    PairOffer &pair_offer = pair_offers[pi];
+    const int bar0 = 1 + 2 * pi;
+    double *wsm = dyn_smem + (size_t)(pair_blk ? pi : wib) * (warp_smem_bytes(part.wbuf) / 8);
     const Grp<32> g;
     const unsigned lane = threadIdx.x & 31u;
-    const int64_t w = PAIR ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t w = pair_blk ? (int64_t)blockIdx.x * half + pi
+                    : PAIRMODE == 2 ? (int64_t)part.n_pair_blocks * half + ((int64_t)blockIdx.x - part.n_pair_blocks) * wpb + wib
+                                    : (int64_t)blockIdx.x * wpb + wib;
     if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
     int64_t first;
     int cnt;
@@ -542,8 +557,8 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
         if (first >= p.n) return;
         cnt = (int)((p.n - first < part.static_e) ? (p.n - first) : part.static_e);
     }
-    if (PAIR && (threadIdx.x >> 5) == 1) {          // the helper warp
-        pair_bar(1);
+    if (PAIR && helper) {                            // the helper warp
+        pair_bar(bar0);
         if (pair_offer.valid) {
             DevRing rj{p.rings + (size_t)pair_offer.e * p.cap, p.cap - 1u};
             double *sb = pair_offer.use_g ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : wsm;
@@ -551,7 +566,7 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
             consume_scan_warp(g, pair_offer.end, pair_offer.dl, pair_offer.h1, pair_offer.h2, pair_offer.tail, rj, sb,
                               pair_offer.use_g ? PCC_GSCRATCH : part.wbuf, so);
             if (lane == 0) pair_offer.res = so;
-            pair_bar(2);
+            pair_bar(bar0 + 1);
         }
         return;
     }
@@ -573,7 +588,7 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
     warp_mi<true, !SPLIT, PAIR>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf,
                                 sstage[(SPLIT || !PCC_STAGED_STORES || PAIR) ? 0 : (threadIdx.x >> 5)], o.mi, avg_lat, lat_inc,
                                 SPLIT ? sent_tmp[e] : 0, prof,
-                                p.mean_scratch ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : nullptr, &pair_offer);   // :416
+                                p.mean_scratch ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : nullptr, &pair_offer, pair_blk, bar0);   // :416
     if (!owner) return;
     mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
     s.steps += 1;                                                                // :419
@@ -1042,7 +1057,8 @@ struct pcc_handle_s {
     bool split;
     bool scalar_sorted;
     int wbuf, warp_threads;   // warp kernel: staging capacity per warp, threads per block
-    bool pair;                // small batches: worker + helper warp per partition slot (pcc_step_warp_kernel<false, true>)
+    bool pair;                // small batches: worker + helper warp per partition slot (pcc_step_warp_kernel<false, 1>)
+    int n_pair;               // big batches: helpers for the n_pair heaviest slots only (pcc_step_warp_kernel<false, 2>)
     int64_t max_warps;
     CostModel cm;
     // staging for pcc_step_host
@@ -1208,9 +1224,14 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
             {
                 const char *pe = getenv("PCC_B200_PAIR");
                 h->pair = pe ? atoi(pe) != 0 : small_batch;
-                cudaError_t cp = cudaFuncSetAttribute(pcc_step_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                cudaError_t cp = cudaFuncSetAttribute(pcc_step_warp_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                       (int)warp_smem_bytes(h->wbuf));
                 if (cp != cudaSuccess) h->pair = false;
+                const char *np_ = getenv("PCC_B200_NPAIR");
+                h->n_pair = np_ ? atoi(np_) : 0;
+                if (h->n_pair < 0) h->n_pair = 0;
+                cp = cudaFuncSetAttribute(pcc_step_warp_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+                if (cp != cudaSuccess) h->n_pair = 0;
             }
             cudaError_t ce = cudaFuncSetAttribute(pcc_step_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (ce == cudaSuccess) ce = cudaFuncSetAttribute(pcc_step_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -1410,7 +1431,7 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
         scalar_perm = h->perm;
     }
     if (h->epw) {
-        WarpPartition part{nullptr, nullptr, nullptr, h->epw, h->wbuf};
+        WarpPartition part{nullptr, nullptr, nullptr, h->epw, h->wbuf, 0};
         const int wpb = h->warp_threads / 32;
         const size_t dyn = (size_t)wpb * warp_smem_bytes(h->wbuf);
         int64_t nwarps = (h->cfg.n_envs + h->epw - 1) / h->epw;
@@ -1437,7 +1458,14 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
                                                                            info_dev);
             h->launches++;
         } else if (h->pair && part.perm) {
-            pcc_step_warp_kernel<false, true><<<(unsigned)nwarps, 64, warp_smem_bytes(h->wbuf), st>>>(
+            pcc_step_warp_kernel<false, 1><<<(unsigned)nwarps, 64, warp_smem_bytes(h->wbuf), st>>>(
+                h->d, part, nullptr, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
+        } else if (h->n_pair > 0 && part.perm && wpb >= 2 && nwarps > h->n_pair) {
+            const int half = wpb / 2;
+            part.n_pair_blocks = (h->n_pair + half - 1) / half;
+            const int64_t paired = (int64_t)part.n_pair_blocks * half;
+            const unsigned mgrid = (unsigned)(part.n_pair_blocks + (nwarps - paired + wpb - 1) / wpb);
+            pcc_step_warp_kernel<false, 2><<<mgrid, h->warp_threads, dyn, st>>>(
                 h->d, part, nullptr, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
         } else {
             pcc_step_warp_kernel<false><<<wgrid, h->warp_threads, dyn, st>>>(h->d, part, nullptr, h->head, actions_dev,
@@ -1475,7 +1503,7 @@ int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const 
         return fail(PCC_EINVAL, "policy shape does not fit (n_in = history_len * n_features <= 128, hidden <= 64)");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    WarpPartition part{nullptr, nullptr, nullptr, h->epw, h->wbuf};
+    WarpPartition part{nullptr, nullptr, nullptr, h->epw, h->wbuf, 0};
     const int wpb = h->warp_threads / 32;
     const size_t dyn = (size_t)wpb * warp_smem_bytes(h->wbuf);
     int64_t nwarps = (h->cfg.n_envs + h->epw - 1) / h->epw;
