@@ -342,12 +342,12 @@ def run_flows(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
     peak, peak_kind = measured_peak_gbs()
     bytes_total = flows_algorithmic_bytes(n_global * K, g_samples)
     achieved = bytes_total / (dev_ms * 1e-3) / 1e9 / world
-    traffic, traffic_src = None, None
+    traffic, traffic_src, kernel_name = None, None, "pcc_flows_ingest_tma_kernel<true>"
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)["flows"]
         if n == WORKLOADS["flows"]["envs"]:
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/" + tj["source"]
+            traffic, traffic_src, kernel_name = tj["dram_bytes_per_launch"], "profiles/" + tj["source"], tj["kernel"]
     except Exception:
         pass
     line = {
@@ -366,7 +366,7 @@ def run_flows(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "pcc_flows_ingest_kernel<true>",
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
                      "algorithmic_bytes_per_launch": bytes_total / (K * world)},
         "clocks": clocks,
     }
