@@ -11,11 +11,20 @@
 //     tree, so np.mean is bit-exact; every load of a subgroup is a contiguous 64 B run of the sample array;
 //   * the divisions of a record are spread over the subgroup's lanes (two rounds of one DDIV each instead
 //     of twelve in sequence), the result row and the observation are written by the subgroup cooperatively;
-//   * records with more than 128 samples (numpy's recursion kicks in) are handed to the whole warp: the
-//     leaves of the recursion are independent, four at a time (one per subgroup), folded in numpy's order;
-//   * persistent grid (a multiple of the SM count), warps stride over the batch.
-// State per flow (caller-owned workspace): hist[flow][H][F] (a ring over H with a per-flow head), the
-// conn-min dict entry, the sending rate, record counter.
+//   * numpy's recursion (n > 128: split at n/2 rounded down to a multiple of 8) is walked per subgroup: records up
+//     to 248 samples (ranges at most two leaves deep) take four warp-uniform leaf steps with full-mask shuffles,
+//     longer ones a register-resident stack walk, and only lists beyond 1 800 samples a separate whole-warp kernel
+//     (four leaves at a time, one per subgroup, folded in numpy's order);
+//   * the four records of a pass are consecutive, hence ONE contiguous span of the sample array: a single
+//     cp.async.bulk (TMA) per pass stages it in the warp's shared-memory stage, refilled for the next pass while
+//     the sample-free tail of the current pass runs (pcc_flows_ingest_tma_kernel; the read-only-path variant
+//     pcc_flows_ingest_kernel serves sample arrays that are not 16-byte aligned);
+//   * persistent grid (SM count x resident blocks), every warp streams a contiguous run of records.
+// State per flow (caller-owned workspace): hist[flow][H][F] (a ring over H with a per-flow head) and one 32-byte
+// FlowState (conn-min dict entry, sending rate, head / flags, record counter, batch stamp).  The batch stamp is the
+// unique-batch check (a flow seen twice in a batch declared unique is reported by pcc_flows_check); it is a 32-bit
+// batch counter, so a flow idle for exactly 2^32 batches could be flagged spuriously.  The CSR offsets are trusted
+// to be non-decreasing and within the sample array (negative counts and out-of-range flow ids are reported).
 #pragma once
 #include "pcc_flows_core.cuh"
 
