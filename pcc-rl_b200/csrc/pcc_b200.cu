@@ -338,7 +338,20 @@ struct PairOffer {
     long long e;
     ScanOut res;
 };
-__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// Producer / consumer named barriers between the two warps of a pair (64 threads): the producer signals with
+// bar.arrive (does not wait), the consumer waits with bar.sync; memory written by the producer before its arrive is
+// visible to the consumer after its sync.  Both are aligned instructions: the warp arrives converged (__syncwarp;
+// the lane-0-only writes just before would otherwise leave it diverged).
+__device__ __forceinline__ void pair_signal(int id)
+{
+    __syncwarp();
+    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void pair_wait(int id)
+{
+    __syncwarp();
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
 
 // One MI for the E envs of this warp.  `owner` lanes hold their env's state in `s`.
 template <bool WANT_MEANS, bool DO_SEND, bool PAIR = false>
@@ -377,7 +390,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
             offer->h1 = s.h1; offer->h2 = s.h2; offer->tail = s.tail;
             offer->end = end; offer->dl = s.dl; offer->e = (long long)e;
         }
-        pair_bar(bar0);                              // the offer is visible to the helper warp
+        pair_signal(bar0);                           // the offer is published to the helper warp
     }
     // phase A: E serial chains side by side (already done by pcc_send_kernel when !DO_SEND)
     if (DO_SEND) {
@@ -461,7 +474,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
         in.wbuf = wbuf;
         if (PAIR && offered) {
             // the helper warp has scanned the records that existed before the send phase: resume from its cursors
-            pair_bar(bar0 + 1);                      // its result (and the staged samples) are visible
+            pair_wait(bar0 + 1);                     // its result (and the staged samples) are visible
             if (offered_use_g) { sbuf_j = gscratch; in.wbuf = PCC_GSCRATCH; }
             in.h1 = offer->res.h1; in.h2 = offer->res.h2;
             in.acked0 = offer->res.acked; in.lost0 = offer->res.lost;
@@ -558,7 +571,7 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
         cnt = (int)((p.n - first < part.static_e) ? (p.n - first) : part.static_e);
     }
     if (PAIR && helper) {                            // the helper warp
-        pair_bar(bar0);
+        pair_wait(bar0);
         if (pair_offer.valid) {
             DevRing rj{p.rings + (size_t)pair_offer.e * p.cap, p.cap - 1u};
             double *sb = pair_offer.use_g ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : wsm;
@@ -566,7 +579,7 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
             consume_scan_warp(g, pair_offer.end, pair_offer.dl, pair_offer.h1, pair_offer.h2, pair_offer.tail, rj, sb,
                               pair_offer.use_g ? PCC_GSCRATCH : part.wbuf, so);
             if (lane == 0) pair_offer.res = so;
-            pair_bar(bar0 + 1);
+            pair_signal(bar0 + 1);
         }
         return;
     }
