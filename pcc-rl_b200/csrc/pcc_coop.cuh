@@ -179,9 +179,10 @@ __device__ __forceinline__ void coop_send_chunks(const Grp<G> &g, bool alive, co
                     const bool rdrop = (dm & 1ull) != 0ull;                    // :73
                     dm >>= 1;
                     const double y = q - (tt - tu);                            // :66-67
-                    const double pll = s.dl + pw;                              // :69-70 (previous packet)
-                    const double pls = __longlong_as_double(__double_as_longlong(pll) | (pd ? (long long)PCC_SIGN : 0ll));
-                    stage[k] = make_double2(pt + pll, pls);                    // :173-175 (previous packet)
+                    // the previous packet is staged RAW -- send time and queue delay seen (>= +0.0, so its sign bit
+                    // carries the drop flag); the two binary64 adds that turn it into a record are done by all lanes
+                    // at copy-out, off the chain lane's in-order instruction stream
+                    stage[k] = make_double2(pt, __longlong_as_double(__double_as_longlong(pw) | (pd ? (long long)PCC_SIGN : 0ll)));
                     const double cpos = s.d_bw + y;                            // :82 if 0 < y <= w_full
                     const bool pos = y > 0.0;
                     const bool fullp = y > s.w_full;                           // :77-79 (tail_drop_threshold)
@@ -194,11 +195,8 @@ __device__ __forceinline__ void coop_send_chunks(const Grp<G> &g, bool alive, co
                     pw = w; pt = tt; pd = rdrop || full;
                     tt = tt + inv_rate;                                        // :161
                 }
-                if (cntk > 0) {
-                    const double pll = s.dl + pw;
-                    const double pls = __longlong_as_double(__double_as_longlong(pll) | (pd ? (long long)PCC_SIGN : 0ll));
-                    stage[cntk] = make_double2(pt + pll, pls);
-                }
+                if (cntk > 0)
+                    stage[cntk] = make_double2(pt, __longlong_as_double(__double_as_longlong(pw) | (pd ? (long long)PCC_SIGN : 0ll)));
                 t = tt; qd = q; t_upd = tu;
             }
         }
@@ -206,8 +204,11 @@ __device__ __forceinline__ void coop_send_chunks(const Grp<G> &g, bool alive, co
         k = packed & 0xff;
         __syncwarp();
         for (int j = (int)g.gl; j < k; j += G) {
-            const double2 v = stage[j + 1];          // slot j + 1 holds packet j
-            Rec r; r.a = v.x; r.l = v.y;
+            const double2 v = stage[j + 1];          // slot j + 1 holds packet j: (send time, +-queue delay seen)
+            const double ll = s.dl + absd(v.y);                                // :69-70
+            Rec r;
+            r.a = v.x + ll;                                                    // :173-174
+            r.l = __longlong_as_double(__double_as_longlong(ll) | (__double_as_longlong(v.y) & (long long)PCC_SIGN));   // :175
             ring.store(tail + (uint32_t)j, r);
         }
         __syncwarp();
