@@ -288,8 +288,13 @@ PCC_HD uint32_t scan_hop2(Ring &ring, uint32_t i, uint32_t tail, uint32_t h1, do
     return i;
 }
 
+// `prescan`: run the two in-order cursor scans once BEFORE the sends, over the records that already exist, and let
+// phases (2) and (3) continue from there.  Both scans are prefix scans that stop at the first record they cannot
+// consume and neither writes the ring, so the result is the same as without -- this is the scalar statement of what
+// the helper warp of pcc_step_warp_kernel<.., 1> does concurrently with the send phase (consume_scan_warp); the host
+// twin checks it against the heap oracle (tests/test_twin.py).
 template <class Ring, class Rng>
-PCC_HD void run_mi(EnvState &s, Ring &ring, Rng &rng, double dur, MiOut &out)
+PCC_HD void run_mi(EnvState &s, Ring &ring, Rng &rng, double dur, MiOut &out, bool prescan = false)
 {
     const double end = s.cur_time + dur;            // network_sim.py:124
     const double inv_rate = 1.0 / s.rate;           // :161 (rate is constant within an MI)
@@ -324,6 +329,10 @@ PCC_HD void run_mi(EnvState &s, Ring &ring, Rng &rng, double dur, MiOut &out)
         t = t + inv_rate;                                    /* :161 */                    \
     }
 
+    if (prescan) {
+        h1 = scan_hop1(ring, h1, tail, end);
+        h2 = scan_hop2(ring, h2, tail, h1, s.dl, end, acked, lost, at_live);
+    }
     // ---- (1) sends with t < end -------------------------------------------------------
     // Ring capacity: records stay in the ring until the END of the MI in which their hop-2
     // event is consumed (the RTT samples are re-read from them for the exact np.mean), so the
@@ -630,10 +639,10 @@ struct StepOut {
 
 template <class Ring, class Rng>
 PCC_HD void step_env(EnvState &s, Ring &ring, Rng &rng, double action, const Consts &c,
-                     bool need_increase, StepOut &o)
+                     bool need_increase, StepOut &o, bool prescan = false)
 {
     s.rate = apply_rate_delta(s.rate, action, c);                    // :412
-    run_mi(s, ring, rng, s.run_dur, o.mi);                           // :416
+    run_mi(s, ring, rng, s.run_dur, o.mi, prescan);                  // :416
     mi_stats(o.mi, ring, s.dl, c, need_increase, s.conn_min, true, o.st);
     s.steps += 1;                                                    // :419
     if (o.st.avg_lat > 0.0) s.run_dur = 0.5 * o.st.avg_lat;          // :437-438

@@ -50,13 +50,14 @@ def test_twin_matches_reference_on_philox_stream(name):
 
 
 def _lockstep(seed, n_eps, n_steps, sampler, act_sigma, ring_capacity=1 << 16, ring_base=0,
-              features=oracle.DEFAULT_FEATURES):
+              features=oracle.DEFAULT_FEATURES, prescan=False):
     g = np.random.default_rng(seed)
     o = oracle.OracleEnv(10, features)
     t = TwinEnv(10, features, ring_capacity)
     o.seed_philox(seed)
     t.seed_philox(seed)
     t.set_ring_cursor(ring_base)
+    t.set_prescan(prescan)
     steps = 0
     for ep in range(n_eps):
         p = sampler(g)
@@ -95,6 +96,16 @@ def nasty_ranges(g):
 @pytest.mark.parametrize("seed", range(12))
 def test_twin_equals_oracle_default_ranges(seed):
     _lockstep(1000 + seed, n_eps=3, n_steps=400, sampler=default_ranges, act_sigma=1.0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_twin_two_stage_consumption_equals_oracle(seed):
+    """The claim behind the helper warp of the small-batch step kernel: scanning the cursors over the records that
+    exist before the MI's sends, then resuming with the final tail, changes nothing (prefix scans)."""
+    _lockstep(3000 + seed, n_eps=2, n_steps=400, sampler=default_ranges, act_sigma=1.0, prescan=True)
+    _lockstep(4000 + seed, n_eps=3, n_steps=150, sampler=nasty_ranges, act_sigma=3.0, prescan=True,
+              features="send rate,recv rate,avg latency,loss ratio,sent latency inflation,conn min latency,"
+                       "latency increase,latency ratio,send ratio")
 
 
 @pytest.mark.parametrize("seed", range(12))

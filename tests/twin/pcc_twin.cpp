@@ -31,6 +31,7 @@ struct Twin {
     PhiloxRng ph;
     std::vector<double> hist;  // [H][F], oldest first
     bool overflow;
+    bool prescan;              // two-stage consumption (see run_mi)
 };
 
 extern "C" {
@@ -48,6 +49,7 @@ Twin *twin_create(int history_len, const int *feature_ids, int n_features, int r
     t->rng_kind = 1; t->ph.init(0, 0);
     t->hist.assign((size_t)history_len * n_features, 0.0);
     t->overflow = false;
+    t->prescan = false;
     memset(&t->s, 0, sizeof(t->s));
     return t;
 }
@@ -56,6 +58,7 @@ void twin_seed_philox(Twin *t, uint64_t seed) { t->rng_kind = 1; t->ph.init(seed
 void twin_mt_setstate(Twin *t, const uint32_t *st) { t->rng_kind = 0; memcpy(t->mt, st, sizeof(t->mt)); }
 void twin_mt_getstate(Twin *t, uint32_t *st) { memcpy(st, t->mt, sizeof(t->mt)); }
 void twin_set_max_steps(Twin *t, int n) { t->c.max_steps = n; }
+void twin_set_prescan(Twin *t, int on) { t->prescan = on != 0; }
 void twin_set_ring_cursor(Twin *t, uint32_t base) { t->s.tail = t->s.h1 = t->s.h2 = base; }
 
 void twin_get_obs(Twin *t, double *obs) { memcpy(obs, t->hist.data(), sizeof(double) * t->hist.size()); }
@@ -74,8 +77,8 @@ void twin_reset(Twin *t, double bw, double dl, int64_t queue, double lr, double 
 void twin_step(Twin *t, double action, double *obs, double *reward, int *done, int64_t *counts, double *info)
 {
     StepOut o;
-    if (t->rng_kind == 0) { Mt19937Rng r; r.init(t->mt); step_env(t->s, t->ring, r, action, t->c, true, o); }
-    else step_env(t->s, t->ring, t->ph, action, t->c, true, o);
+    if (t->rng_kind == 0) { Mt19937Rng r; r.init(t->mt); step_env(t->s, t->ring, r, action, t->c, true, o, t->prescan); }
+    else step_env(t->s, t->ring, t->ph, action, t->c, true, o, t->prescan);
     t->overflow |= o.mi.overflow;
     memmove(t->hist.data(), t->hist.data() + t->F, sizeof(double) * (size_t)(t->H - 1) * t->F);
     for (int f = 0; f < t->F; f++) t->hist[(size_t)(t->H - 1) * t->F + f] = metric_value(o.st, t->ids[f]);

@@ -42,6 +42,7 @@ def lib():
         L.twin_mt_getstate.argtypes = [vp, C.POINTER(C.c_uint32)]
         L.twin_set_max_steps.argtypes = [vp, i]
         L.twin_set_ring_cursor.argtypes = [vp, C.c_uint32]
+        L.twin_set_prescan.argtypes = [vp, i]
         L.twin_get_obs.argtypes = [vp, C.POINTER(d)]
         L.twin_reset.argtypes = [vp, d, d, C.c_int64, d, d]
         L.twin_step.argtypes = [vp, d, C.POINTER(d), C.POINTER(d), C.POINTER(i),
@@ -82,6 +83,10 @@ class TwinEnv(object):
         st = np.zeros(625, dtype=np.uint32)
         self.L.twin_mt_getstate(self.h, st.ctypes.data_as(C.POINTER(C.c_uint32)))
         return st
+
+    def set_prescan(self, on=True):
+        """Two-stage consumption: the cursor scans once before the sends, then resumed (see pcc_core.cuh run_mi)."""
+        self.L.twin_set_prescan(self.h, int(on))
 
     def set_ring_cursor(self, base):
         self.L.twin_set_ring_cursor(self.h, base)
