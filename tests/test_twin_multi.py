@@ -57,11 +57,58 @@ class TwinMulti(object):
     ok = property(lambda self: bool(self.L.twin_multi_ok(self.h)))
 
 
+class TwinMultiFast(TwinMulti):
+    """pcc_multi_fast.cuh: the same semantics without the event heap (shared ring, merged timers, three cursors)."""
+
+    def __init__(self, S, capacity=1 << 15, ring_base=0):
+        L = self.L = _lib()
+        vp, d, i = C.c_void_p, C.c_double, C.c_int
+        pd = C.POINTER(C.c_double)
+        L.twin_mfast_create.restype = vp
+        L.twin_mfast_create.argtypes = [i, i, C.POINTER(C.c_int), i, i, C.c_uint32]
+        L.twin_mfast_destroy.argtypes = [vp]
+        L.twin_mfast_seed.argtypes = [vp, C.c_uint64]
+        L.twin_mfast_reset.argtypes = [vp, d, d, C.c_int64, d, pd]
+        L.twin_mfast_step.argtypes = [vp, pd, pd, pd, C.POINTER(i), C.POINTER(C.c_int32)]
+        for n in ("twin_mfast_cur_time", "twin_mfast_run_dur"):
+            getattr(L, n).restype = d
+            getattr(L, n).argtypes = [vp]
+        L.twin_mfast_ok.argtypes = [vp]
+        ids = np.asarray(oracle.feature_ids(), dtype=np.int32)
+        self.S = S
+        self.h = L.twin_mfast_create(S, 10, ids.ctypes.data_as(C.POINTER(C.c_int)), len(ids), capacity, ring_base)
+
+    def __del__(self):
+        self.L.twin_mfast_destroy(self.h)
+
+    def reset(self, seed, bw, lat, queue, loss, rates):
+        self.L.twin_mfast_seed(self.h, int(seed))
+        r = np.ascontiguousarray(rates, dtype=np.float64)
+        self.L.twin_mfast_reset(self.h, bw, lat, int(queue), loss, r.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        obs = np.zeros((self.S, 30)); rew = np.zeros(self.S); cnt = np.zeros((self.S, 3), dtype=np.int32)
+        dn = C.c_int()
+        pd = C.POINTER(C.c_double)
+        self.L.twin_mfast_step(self.h, a.ctypes.data_as(pd), obs.ctypes.data_as(pd), rew.ctypes.data_as(pd), C.byref(dn),
+                               cnt.ctypes.data_as(C.POINTER(C.c_int32)))
+        return obs, rew, bool(dn.value), cnt
+
+    cur_time = property(lambda self: self.L.twin_mfast_cur_time(self.h))
+    run_dur = property(lambda self: self.L.twin_mfast_run_dur(self.h))
+    ok = property(lambda self: bool(self.L.twin_mfast_ok(self.h)))
+
+
+IMPLS = {"heap": TwinMulti, "stream": TwinMultiFast}
+
+
+@pytest.mark.parametrize("impl", ["heap", "stream"])
 @pytest.mark.parametrize("name", golden_names("multi_"))
-def test_twin_multi_matches_reference_golden(name):
+def test_twin_multi_matches_reference_golden(name, impl):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     bw, lat, queue, loss = z["params"]
-    t = TwinMulti(len(z["rates"]))
+    t = IMPLS[impl](len(z["rates"]))
     t.reset(int(z["seed"]), bw, lat, int(queue), loss, z["rates"])
     assert t.cur_time == float(z["cur_time0"])
     for k in range(len(z["action"])):
@@ -72,8 +119,9 @@ def test_twin_multi_matches_reference_golden(name):
     assert t.ok
 
 
+@pytest.mark.parametrize("impl", ["heap", "stream"])
 @pytest.mark.parametrize("seed", range(8))
-def test_twin_multi_equals_oracle_on_grid_points(seed):
+def test_twin_multi_equals_oracle_on_grid_points(seed, impl):
     g = np.random.default_rng(300 + seed)
     for trial in range(3):
         S = int(g.choice([2, 2, 3, 4]))
@@ -85,7 +133,7 @@ def test_twin_multi_equals_oracle_on_grid_points(seed):
         o = oracle.OracleEnv()
         o.seed_philox(seed)
         o.reset_multi(bw, lat, queue, loss, rates)
-        t = TwinMulti(S)
+        t = IMPLS[impl](S)
         t.reset(seed, bw, lat, queue, loss, rates)
         assert o.cur_time == t.cur_time
         for k in range(150):
@@ -206,4 +254,34 @@ def test_twin_variant_equals_oracle_random(seed):
             assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2], (seed, trial, k)
             assert o.cur_time == t.cur_time and o.run_dur == t.run_dur
             assert [o.cwnd(i) for i in range(S)] == [t.cwnd(i) for i in range(S)]
+        assert t.ok
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_twin_multi_stream_nasty_ties_and_wrap(seed):
+    """The heap-free path where it is most fragile: senders with IDENTICAL rates (their timers tie exactly, so the
+    sender index decides every send order and many hop ties), heavy random loss and tiny queues (long drop clusters),
+    ring cursors starting just below the u32 wrap."""
+    g = np.random.default_rng(7000 + seed)
+    for trial in range(3):
+        S = int(g.choice([2, 3, 4]))
+        bw = float(np.exp(g.uniform(np.log(40.0), np.log(5000.0))))
+        lat = float(np.exp(g.uniform(np.log(0.001), np.log(0.3))))
+        queue = 1 + int(np.exp(g.uniform(0, 4)))
+        loss = float(g.choice([0.0, 0.05, 0.3, 0.9]))
+        r0 = float(g.uniform(40, 1000))
+        rates = np.full(S, r0) if trial != 1 else np.array([r0, r0 * 2, r0, r0 * 0.5][:S])
+        o = oracle.OracleEnv()
+        o.seed_philox(seed)
+        o.reset_multi(bw, lat, queue, loss, rates)
+        t = TwinMultiFast(S, ring_base=0xFFFFFF00)
+        t.reset(seed, bw, lat, queue, loss, rates)
+        assert o.cur_time == t.cur_time
+        for k in range(200):
+            a = np.full(S, float(g.normal(0, 2.0))) if k % 3 else g.normal(0, 2.5, S)   # equal actions keep the rates tied
+            x = o.step_multi(a)
+            y = t.step(a)
+            assert np.array_equal(x[3], y[3]), (seed, trial, k)
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2], (seed, trial, k)
+            assert o.cur_time == t.cur_time and o.run_dur == t.run_dur
         assert t.ok

@@ -219,3 +219,69 @@ double twin_flow_apply_rate_delta(double rate, double action, double scale, doub
     return flow_apply_rate_delta(rate, action, scale, mn, mx, style);
 }
 }
+
+// ---- several senders without the heap (pcc_multi_fast.cuh), host build ------------------------------------------
+#include "../../pcc-rl_b200/csrc/pcc_multi_fast.cuh"
+
+struct HostSidRing {
+    Rec *buf; uint8_t *sids; uint32_t mask;
+    uint32_t capacity() const { return mask + 1; }
+    Rec load(uint32_t i) const { return buf[i & mask]; }
+    void store(uint32_t i, Rec r) { buf[i & mask] = r; }
+    void store_a(uint32_t i, double a) { buf[i & mask].a = a; }
+    int sid(uint32_t i) const { return sids[i & mask]; }
+    void set_sid(uint32_t i, int s) { sids[i & mask] = (uint8_t)s; }
+};
+struct TwinMultiFast {
+    int S, H, F, cap_s; int ids[PCC_MAX_FEATURES]; bool need_inc;
+    Consts c; MNet net; MSender snd[PCC_MAX_SENDERS]; MFast f;
+    std::vector<Rec> ring; std::vector<uint8_t> sids; std::vector<double> samples, hist;
+    PhiloxRng ph; bool ok;
+};
+extern "C" {
+TwinMultiFast *twin_mfast_create(int n_senders, int history_len, const int *feature_ids, int n_features, int capacity,
+                                 uint32_t ring_base)
+{
+    TwinMultiFast *t = new TwinMultiFast();
+    t->S = n_senders; t->H = history_len; t->F = n_features; t->cap_s = capacity;
+    for (int i = 0; i < n_features; i++) t->ids[i] = feature_ids[i];
+    t->need_inc = features_need_increase(t->ids, t->F);
+    t->c.max_rate = 1000.0; t->c.min_rate = 40.0; t->c.delta_scale = 0.025; t->c.reward_scale = 0.001;
+    t->c.max_steps = 400; t->c.bytes_per_packet = 1500;
+    t->ring.resize((size_t)capacity); t->sids.resize((size_t)capacity);
+    t->samples.resize((size_t)capacity * n_senders);
+    t->hist.assign((size_t)n_senders * history_len * n_features, 0.0);
+    t->f.tail = t->f.h1 = t->f.h2 = ring_base;                      // cursors may start anywhere (u32 wrap test)
+    t->ph.init(0, 0); t->ok = true;
+    return t;
+}
+void twin_mfast_destroy(TwinMultiFast *t) { delete t; }
+void twin_mfast_seed(TwinMultiFast *t, uint64_t seed) { t->ph.init(seed, 0); }
+void twin_mfast_reset(TwinMultiFast *t, double bw, double dl, int64_t queue, double lr, const double *rates)
+{
+    HostSidRing rg{t->ring.data(), t->sids.data(), (uint32_t)t->ring.size() - 1u};
+    t->ok = mfast_reset(t->net, t->snd, t->S, t->f, rg, t->samples.data(), t->cap_s, t->ph, bw, dl, queue, lr, rates) && t->ok;
+    for (int i = 0; i < t->S; i++)
+        for (int h = 0; h < t->H; h++)
+            for (int k = 0; k < t->F; k++) t->hist[((size_t)i * t->H + h) * t->F + k] = metric_empty(t->ids[k]);
+}
+void twin_mfast_step(TwinMultiFast *t, const double *actions, double *obs, double *rewards, int *done, int32_t *counts)
+{
+    HostSidRing rg{t->ring.data(), t->sids.data(), (uint32_t)t->ring.size() - 1u};
+    double rows[PCC_MAX_SENDERS * PCC_MAX_FEATURES];
+    bool dn;
+    t->ok = mfast_step(t->net, t->snd, t->S, t->f, rg, t->samples.data(), t->cap_s, t->ph, actions, t->c, t->ids, t->F,
+                       t->need_inc, rows, rewards, counts, dn) && t->ok;
+    const size_t hf = (size_t)t->H * t->F;
+    for (int i = 0; i < t->S; i++) {
+        double *hs = t->hist.data() + i * hf;
+        memmove(hs, hs + t->F, sizeof(double) * (hf - t->F));
+        for (int k = 0; k < t->F; k++) hs[hf - t->F + k] = rows[i * t->F + k];
+    }
+    memcpy(obs, t->hist.data(), sizeof(double) * t->hist.size());
+    *done = dn;
+}
+double twin_mfast_cur_time(TwinMultiFast *t) { return t->net.cur_time; }
+double twin_mfast_run_dur(TwinMultiFast *t) { return t->net.run_dur; }
+int twin_mfast_ok(TwinMultiFast *t) { return t->ok; }
+}

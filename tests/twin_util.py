@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "twin", "pcc_twin.cpp")
 _CSRC = os.path.join(os.path.dirname(_HERE), "pcc-rl_b200", "csrc")
 _CORE = os.path.join(_CSRC, "pcc_core.cuh")
-_DEPS = [os.path.join(_CSRC, f) for f in ("pcc_core.cuh", "pcc_multi_core.cuh", "pcc_flows_core.cuh")]
+_DEPS = [os.path.join(_CSRC, f) for f in ("pcc_core.cuh", "pcc_multi_core.cuh", "pcc_multi_fast.cuh", "pcc_flows_core.cuh")]
 _LIB = os.path.join(_HERE, "twin", "libpcc_twin.so")
 
 
