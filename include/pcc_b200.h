@@ -201,9 +201,12 @@ int64_t pcc_launch_count(pcc_handle h);
  * The reference's Network takes lists of senders (gym/network_sim.py:100-126, 140-178) although its env
  * creates one.  Semantics here: all senders share links [l0, l1]; heap ties are broken by sender index;
  * step applies actions[i] to sender i (:409-412 generalised); every sender has its own MI, history, obs and
- * reward (:194,205 on its own MI); the MI duration follows sender 0 (:437-438 as written).  Generic per-env
- * event heap, one env per thread: exact, not fast.  cfg->ring_capacity sizes the heap (x n_senders events)
- * and the per-sender RTT sample buffers; Philox streams only.  Arrays: [n_envs][n_senders]... row-major. */
+ * reward (:194,205 on its own MI); the MI duration follows sender 0 (:437-438 as written).  Two engines with identical
+ * results, fixed at the first pcc_multi_reset: the heap-free streaming MI (default: one shared in-flight ring with a
+ * sender id per record, timers merged by (time, sender), three cursors) and the per-env event heap (environment
+ * PCC_MULTI_MODE=heap, and always for the cwnd / latency-noise variants below).  One env per thread.  cfg->ring_capacity
+ * (a power of two) sizes the in-flight ring / the heap (x n_senders events) and the per-sender RTT sample buffers;
+ * Philox streams only.  Arrays: [n_envs][n_senders]... row-major. */
 typedef struct pcc_multi_handle_s *pcc_multi_handle;
 int pcc_multi_workspace_bytes(const pcc_config *cfg, int32_t n_senders, uint64_t *bytes);
 int pcc_multi_create(pcc_multi_handle *out, const pcc_config *cfg, int32_t n_senders, void *workspace_dev);

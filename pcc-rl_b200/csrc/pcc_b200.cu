@@ -25,6 +25,7 @@
 #include "pcc_coop.cuh"
 #include "pcc_warp.cuh"
 #include "pcc_multi_core.cuh"
+#include "pcc_multi_fast.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -1638,7 +1639,30 @@ struct MultiDev {
     int32_t need_inc;
     Consts c;
     Variant v;
+    MFast *fast;         // [n] heap-free mode: timers + ring cursors; the heap region then holds Rec[cap] + sender ids[cap]
+    int32_t ring_cap;    // records per env in heap-free mode (power of two)
 };
+// heap-free mode: the env's slice of the heap region reinterpreted as the shared in-flight ring
+struct DevSidRing {
+    Rec *base; uint8_t *sids; uint32_t mask;
+    __device__ __forceinline__ uint32_t capacity() const { return mask + 1u; }
+    __device__ __forceinline__ Rec load(uint32_t i) const
+    {
+        const double2 v = *reinterpret_cast<const double2 *>(base + (i & mask));
+        Rec r; r.a = v.x; r.l = v.y;
+        return r;
+    }
+    __device__ __forceinline__ void store(uint32_t i, Rec r) { *reinterpret_cast<double2 *>(base + (i & mask)) = make_double2(r.a, r.l); }
+    __device__ __forceinline__ void store_a(uint32_t i, double a) { base[i & mask].a = a; }
+    __device__ __forceinline__ int sid(uint32_t i) const { return sids[i & mask]; }
+    __device__ __forceinline__ void set_sid(uint32_t i, int sd) { sids[i & mask] = (uint8_t)sd; }
+};
+__device__ __forceinline__ DevSidRing multi_ring(const MultiDev &p, int64_t e)
+{
+    char *b = reinterpret_cast<char *>(p.heaps + (size_t)e * p.heap_cap);
+    return DevSidRing{reinterpret_cast<Rec *>(b), reinterpret_cast<uint8_t *>(b + (size_t)p.ring_cap * sizeof(Rec)),
+                      (uint32_t)p.ring_cap - 1u};
+}
 struct DevHeap {
     MEvent *base; int cap;
     __device__ __forceinline__ int capacity() const { return cap; }
@@ -1729,13 +1753,90 @@ __global__ void pcc_multi_seed_kernel(MultiDev p, const unsigned long long *__re
     p.envs[e].draws = 0ull;
 }
 
+// heap-free mode (pcc_multi_fast.cuh): the same kernels' work on the streaming MI, one env per thread
+__global__ void pcc_mfast_reset_kernel(MultiDev p, const uint8_t *__restrict__ mask, const double *__restrict__ bw,
+                                       const double *__restrict__ delay, const long long *__restrict__ queue,
+                                       const double *__restrict__ loss, const double *__restrict__ rates,
+                                       double *__restrict__ obs)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n || (mask && !mask[e])) return;
+    MEnv &me = p.envs[e];
+    MNet net = me.net;
+    MSender snd[PCC_MAX_SENDERS];
+    MFast f = p.fast[e];
+    PhiloxRng rng;
+    rng.init(me.seed, me.draws);
+    DevSidRing ring = multi_ring(p, e);
+    double r[PCC_MAX_SENDERS];
+    for (int i = 0; i < p.S; i++) r[i] = rates[(size_t)e * p.S + i];
+    const bool ok = mfast_reset(net, snd, p.S, f, ring, p.samples + (size_t)e * p.S * p.cap_s, p.cap_s, rng, bw[e], delay[e],
+                                (int64_t)queue[e], loss[e], r);
+    me.net = net;
+    for (int i = 0; i < p.S; i++) me.snd[i] = snd[i];
+    me.draws = rng.draws;
+    p.fast[e] = f;
+    if (!ok) atomicAdd(&p.meta[1], 1ull);
+    const int HF = p.H * p.F;
+    for (int i = 0; i < p.S; i++)
+        for (int k = 0; k < HF; k++) {
+            const double v = metric_empty(p.ids[k % p.F]);
+            p.hist[((size_t)e * p.S + i) * HF + k] = v;
+            if (obs) obs[((size_t)e * p.S + i) * HF + k] = v;
+        }
+}
+
+__global__ void pcc_mfast_step_kernel(MultiDev p, unsigned long long head_step, const double *__restrict__ actions,
+                                      double *__restrict__ obs, double *__restrict__ reward, uint8_t *__restrict__ done,
+                                      int32_t *__restrict__ counts)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    MEnv &me = p.envs[e];
+    MNet net = me.net;
+    MSender snd[PCC_MAX_SENDERS];
+    for (int i = 0; i < p.S; i++) snd[i] = me.snd[i];
+    MFast f = p.fast[e];
+    PhiloxRng rng;
+    rng.init(me.seed, me.draws);
+    DevSidRing ring = multi_ring(p, e);
+    double acts[PCC_MAX_SENDERS], rows[PCC_MAX_SENDERS * PCC_MAX_FEATURES], rew[PCC_MAX_SENDERS];
+    int32_t cnt[PCC_MAX_SENDERS * 3];
+    for (int i = 0; i < p.S; i++) acts[i] = actions[(size_t)e * p.S + i];
+    bool dn;
+    const bool ok = mfast_step(net, snd, p.S, f, ring, p.samples + (size_t)e * p.S * p.cap_s, p.cap_s, rng, acts, p.c,
+                               p.ids, p.F, p.need_inc != 0, rows, rew, cnt, dn);
+    me.net = net;
+    for (int i = 0; i < p.S; i++) me.snd[i] = snd[i];
+    me.draws = rng.draws;
+    p.fast[e] = f;
+    if (!ok) atomicAdd(&p.meta[1], 1ull);
+    const int H = p.H, F = p.F, HF = H * F;
+    const int slot_new = (int)(head_step % (unsigned long long)H);
+    for (int i = 0; i < p.S; i++) {
+        double *hrow = p.hist + ((size_t)e * p.S + i) * HF;
+        double *ob = obs + ((size_t)e * p.S + i) * HF;
+        for (int k = 0; k < F; k++) hrow[slot_new * F + k] = rows[i * F + k];
+        for (int h = 0; h < H; h++) {
+            int sl = slot_new + 1 + h;
+            if (sl >= H) sl -= H;
+            for (int k = 0; k < F; k++) ob[h * F + k] = hrow[sl * F + k];
+        }
+        reward[(size_t)e * p.S + i] = rew[i];
+        if (counts) for (int k = 0; k < 3; k++) counts[((size_t)e * p.S + i) * 3 + k] = cnt[3 * i + k];
+    }
+    done[e] = dn ? 1 : 0;
+}
+
 struct pcc_multi_handle_s {
     pcc_config cfg;
     MultiDev d;
     unsigned long long head;
+    int mode;            // 0 undecided (before the first reset), 1 heap-free streaming MI, 2 event heap
+    bool heap_forced;    // PCC_MULTI_MODE=heap
 };
 
-static void multi_layout(const pcc_config *cfg, int S, size_t off[5], size_t &total)
+static void multi_layout(const pcc_config *cfg, int S, size_t off[6], size_t &total)
 {
     const size_t n = (size_t)cfg->n_envs, HF = (size_t)cfg->history_len * cfg->n_features;
     size_t o = 0;
@@ -1744,6 +1845,7 @@ static void multi_layout(const pcc_config *cfg, int S, size_t off[5], size_t &to
     off[2] = o; o = align_up(o + n * (size_t)S * (size_t)cfg->ring_capacity * sizeof(MEvent));
     off[3] = o; o = align_up(o + n * (size_t)S * (size_t)cfg->ring_capacity * 8);
     off[4] = o; o = align_up(o + 64);
+    off[5] = o; o = align_up(o + n * sizeof(MFast));
     total = o;
 }
 
@@ -1754,7 +1856,7 @@ int pcc_multi_workspace_bytes(const pcc_config *cfg, int32_t n_senders, uint64_t
     int rc = validate(cfg);
     if (rc) return rc;
     if (n_senders < 1 || n_senders > PCC_MAX_SENDERS) return fail(PCC_EINVAL, "n_senders out of range (1..4)");
-    size_t off[5], total;
+    size_t off[6], total;
     multi_layout(cfg, n_senders, off, total);
     if (bytes) *bytes = total;
     return PCC_OK;
@@ -1775,12 +1877,18 @@ int pcc_multi_create(pcc_multi_handle *out, const pcc_config *cfg, int32_t n_sen
     if (!h) return fail(PCC_EINVAL, "out of host memory");
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
-    size_t off[5], total;
+    size_t off[6], total;
     multi_layout(cfg, n_senders, off, total);
     char *b = (char *)workspace_dev;
     MultiDev &d = h->d;
     d.envs = (MEnv *)(b + off[0]); d.hist = (double *)(b + off[1]); d.heaps = (MEvent *)(b + off[2]);
     d.samples = (double *)(b + off[3]); d.meta = (unsigned long long *)(b + off[4]);
+    d.fast = (MFast *)(b + off[5]); d.ring_cap = (int32_t)cfg->ring_capacity;
+    {
+        const char *mm = getenv("PCC_MULTI_MODE");
+        h->heap_forced = mm && !strcmp(mm, "heap");
+        h->mode = 0;
+    }
     d.n = cfg->n_envs; d.S = n_senders; d.H = cfg->history_len; d.F = cfg->n_features;
     d.heap_cap = (int32_t)(cfg->ring_capacity * n_senders); d.cap_s = (int32_t)cfg->ring_capacity;
     for (int i = 0; i < PCC_MAX_FEATURES; i++) d.ids[i] = i < cfg->n_features ? cfg->feature_ids[i] : 0;
@@ -1791,6 +1899,7 @@ int pcc_multi_create(pcc_multi_handle *out, const pcc_config *cfg, int32_t n_sen
     d.v = default_variant();
     cudaError_t e = cudaMemset(b + off[0], 0, off[1] - off[0]);
     if (e == cudaSuccess) e = cudaMemset(b + off[4], 0, 64);
+    if (e == cudaSuccess) e = cudaMemset(b + off[5], 0, total - off[5]);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "multi init: %s", cudaGetErrorString(e)); }
     *out = h;
@@ -1814,6 +1923,15 @@ int pcc_multi_reset(pcc_multi_handle h, const uint8_t *mask_dev, const double *b
 {
     if (!h || !bw_dev || !delay_dev || !queue_dev || !loss_dev || !start_rates_dev) return fail(PCC_EINVAL, "null pointer");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    // The streaming MI (no heap) serves the shipped configuration; the cwnd / latency-noise variants need the heap.
+    // The two keep different per-env state, so the mode is fixed by the first reset.
+    const int want = (h->heap_forced || h->d.v.use_cwnd || h->d.v.use_noise) ? 2 : 1;
+    if (h->mode == 0) h->mode = want;
+    else if (h->mode != want) return fail(PCC_EINVAL, "the variant switches changed after the first reset (create a new handle)");
+    if (h->mode == 1)
+        pcc_mfast_reset_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
+            h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rates_dev, obs_dev);
+    else
     pcc_multi_reset_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
         h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rates_dev, obs_dev);
     CUDA_TRY(cudaGetLastError());
@@ -1825,7 +1943,13 @@ int pcc_multi_step_cwnd(pcc_multi_handle h, const double *actions_dev, const dou
 {
     if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(PCC_EINVAL, "null pointer");
     if (cwnd_actions_dev && !h->d.v.use_cwnd) return fail(PCC_EINVAL, "cwnd actions given but use_cwnd is off (pcc_multi_set_variant)");
+    if (h->mode == 0) return fail(PCC_EINVAL, "pcc_multi_step before pcc_multi_reset");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->mode == 1) {
+        pcc_mfast_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
+            h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev);
+        if (cwnd_dev) CUDA_TRY(cudaMemsetAsync(cwnd_dev, 0, (size_t)h->d.n * h->d.S * sizeof(int32_t), (cudaStream_t)stream));
+    } else
     pcc_multi_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
         h->d, h->head, actions_dev, cwnd_actions_dev, obs_dev, reward_dev, done_dev, counts_dev, cwnd_dev);
     h->head++;

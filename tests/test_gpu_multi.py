@@ -11,8 +11,15 @@ from golden_util import GOLDEN_DIR, golden_names
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["stream", "heap"])
+def multi_mode(request, monkeypatch):
+    """Both engines of the multi-sender path: the heap-free streaming MI (default) and the per-env event heap."""
+    monkeypatch.setenv("PCC_MULTI_MODE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", golden_names("multi_"))
-def test_cuda_multi_sender_matches_reference_golden(name):
+def test_cuda_multi_sender_matches_reference_golden(name, multi_mode):
     import pcc_rl_b200
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     bw, lat, queue, loss = z["params"]
@@ -27,7 +34,7 @@ def test_cuda_multi_sender_matches_reference_golden(name):
     env.check()
 
 
-def test_cuda_config5_grid_sweep_vs_oracle():
+def test_cuda_config5_grid_sweep_vs_oracle(multi_mode):
     """32 x 32 grid of (bandwidth, delay), 2 senders per link, 60 steps: every grid point against the oracle."""
     import pcc_rl_b200
     p = pcc_rl_b200.grid_sweep_params(n_bw=32, n_lat=32, queue=40, loss=0.01)

@@ -1,0 +1,29 @@
+"""Throughput of the multi-sender path (BASELINE config 5: bw x delay grid, 2 senders per link) for both engines.
+python tools/time_multi.py [grid_side] [steps]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+side = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+for mode in ("stream", "heap"):
+    os.environ["PCC_MULTI_MODE"] = mode
+    import pcc_rl_b200
+    p = pcc_rl_b200.grid_sweep_params(n_bw=side, n_lat=side, queue=40, loss=0.01)
+    n, S = side * side, 2
+    g = np.random.default_rng(7)
+    env = pcc_rl_b200.PccMultiSenderEnv(n, n_senders=S, seed=500, ring_capacity=1 << 13)
+    env.reset(p, g.uniform(40, 1000, (n, S)))
+    acts = torch.randn((steps + 5, n, S), dtype=torch.float64, device=env.device) * 2.0
+    for t in range(5):
+        env.step(acts[t])
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for t in range(steps):
+        env.step(acts[5 + t])
+    e.record()
+    torch.cuda.synchronize()
+    env.check()
+    ms = s.elapsed_time(e) / steps
+    print("%-6s grid %dx%d, %d senders: %.3f ms/step = %.3f M env-steps/s (%.3f M sender-steps/s)"
+          % (mode, side, side, S, ms, n / ms / 1e3, n * S / ms / 1e3))
