@@ -41,6 +41,8 @@ WORKLOADS = {
 }
 WORKLOADS["flows"] = dict(envs=1 << 20, desc="MI-sample ingestion (SURVEY 8f rank 4): 1 Mi live flows per GPU, one MI record per flow "
                                              "per step (~150 RTT samples each), history_len=10, 3 features")
+WORKLOADS["config5"] = dict(envs=64 * 64, desc="link-parameter grid sweep (bw 1-1000 Mbit/s x delay 1-500 ms, 64 x 64 log grid), "
+                                                "2 senders per link, 1xB200")
 ACTION_SIGMA = 1.0   # a ~ N(0,1), BASELINE.md §3
 
 
@@ -190,6 +192,98 @@ def run_reference_arm_flows(args, oracle):
                          "sample": "%d records per step (one per flow) on %d host threads; C restatement of "
                                    "sender_obs.py / loaded_client.give_sample (oracle/pcc_oracle_flows.c)" % (ns, cores)},
         "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_config5(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
+    """BASELINE config 5: every rank sweeps the same 64 x 64 (bw, delay) grid with 2 senders per link (its own seeds).
+    One step = one MI of every link; an env-step here carries two senders' MIs."""
+    K, W, S = args.steps, args.warmup, 2
+    side = int(round(n ** 0.5))
+    p = pcc_rl_b200.grid_sweep_params(n_bw=side, n_lat=side, queue=40, loss=0.01)
+    n = side * side
+    g = np.random.default_rng(args.seed + rank)
+    rates = g.uniform(40, 1000, (n, S))
+    env = pcc_rl_b200.PccMultiSenderEnv(n, n_senders=S, seed=args.seed + 1000 * rank, ring_capacity=1 << 13, device=dev)
+    env.reset(p, rates)
+    acts = torch.randn((W + K, n, S), dtype=torch.float64, device=dev) * 2.0
+    for t in range(W):
+        env.step(acts[t])
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else dev.index)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    tot = torch.zeros(3, dtype=torch.int64, device=dev)
+    for t in range(K):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        ev_s[t].record()
+        obs, rew, done, info = env.step(acts[W + t])
+        ev_e[t].record()
+        tot += info["counts"].sum((0, 1))
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    env.check()
+    dev_ms = D.max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(ev_s, ev_e)), dev)
+    sent, acked, _ = [D.sum_over_ranks(int(x), dev) for x in tot.cpu().tolist()]
+    # end to end: host actions in, obs / reward / done back
+    ke = min(K, 50)
+    h_act = acts[W:W + ke].cpu().pin_memory()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for t in range(ke):
+        o_, r_, d_, _i = env.step(h_act[t].to(dev, non_blocking=True))
+        acc += float(r_.cpu()[0, 0]) + float(o_.cpu()[0, 0, 0])
+        d_.cpu()
+    torch.cuda.synchronize(dev)
+    e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak_gbs()
+    hf = env.obs_dim
+    # per sender the single-sender figure (677 + 48 sent + 8 acked) without a second copy of the link parameters
+    bytes_total = (677 * S - 32 * (S - 1)) * n * world * K + 48 * sent + 8 * acked
+    achieved = bytes_total / (dev_ms * 1e-3) / 1e9 / world
+    line = {
+        "metric": "env-steps/sec (batched MI sim)", "value": n * world * K / (dev_ms * 1e-3), "unit": "env-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config5: " + WORKLOADS["config5"]["desc"], "links_per_gpu": n, "senders_per_link": S,
+                   "engine": os.environ.get("PCC_MULTI_MODE", "stream (heap-free)"), "actions": "N(0,2) per sender",
+                   "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB write outside the event brackets)"},
+        "sender_steps_per_s": n * world * S * K / (dev_ms * 1e-3),
+        "e2e": {"value": n * world * ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": 8 * n * S,
+                "d2h_bytes_per_step": n * S * (8 * hf + 8) + n, "ms_per_step": 1e3 * e2e_s / ke, "steps": ke,
+                "api": "PccMultiSenderEnv.step with pinned host actions, obs / reward / done copied back"},
+        "gpu_launches": K,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                     "traffic": None, "kernel": "pcc_mfast_step_kernel", "algorithmic_bytes_per_launch": bytes_total / (K * world)},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        import oracle
+        ns, ks = 64, 40                       # a bounded sample: 64 grid points x (reset + 40 steps), one host thread
+        idx = np.linspace(0, n - 1, ns).astype(int)
+        t0 = time.perf_counter()
+        for i in idx:
+            o = oracle.OracleEnv()
+            o.seed_philox(args.seed + int(i))
+            o.reset_multi(p["bw"][i], p["lat"][i], int(p["queue"][i]), p["loss"][i], rates[i])
+            for k in range(ks):
+                o.step_multi(g.normal(0, 2.0, S))
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ns * ks / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                "sample": "%d grid points spread over the grid x (reset + %d steps), one host thread; C "
+                                          "restatement of the reference's heap loop with 2 senders (oracle/)" % (ns, ks)}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def run_config4(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
@@ -407,6 +501,9 @@ def main():
         return
     if args.workload == "flows":
         run_flows(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global)
+        return
+    if args.workload == "config5":
+        run_config5(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global)
         return
 
     def make_env():
