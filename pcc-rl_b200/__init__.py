@@ -9,6 +9,8 @@ from .batch_env import PccBatchEnv
 from .multi_env import PccMultiSenderEnv, grid_sweep_params
 from .flow_monitor import PccFlowMonitor
 from . import flow_monitor
+from . import event_log
+from .event_log import EventRecorder
 
 
 def build(force=False, verbose=False):
