@@ -585,6 +585,9 @@ pcc_flows_ingest_tma_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *_
                 stage[nel - 1] = __ldg(b.rtt + e0a + nel - 1);
             }
             if (ncopy > 0) {
+                // the stage was last READ through the generic proxy (all lanes are past __syncwarp); the bulk copy
+                // writes it through the async proxy: order the two proxies before re-using the buffer
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(bar, (uint32_t)(ncopy * 8));
                 tma_load_1d(stage, b.rtt + e0a, (uint32_t)(ncopy * 8), bar);
             } else {
