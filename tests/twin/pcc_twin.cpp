@@ -285,3 +285,63 @@ double twin_mfast_cur_time(TwinMultiFast *t) { return t->net.cur_time; }
 double twin_mfast_run_dur(TwinMultiFast *t) { return t->net.run_dur; }
 int twin_mfast_ok(TwinMultiFast *t) { return t->ok; }
 }
+
+// ---- executable specification of the flows kernels' lane-level summation (pcc_flows.cuh) --------------------------
+// The CUDA code cannot run here (shuffles), so this is a lane-by-lane emulation of the SAME algorithm: 8 lanes =
+// numpy's 8 accumulators, three xor-exchange rounds = its combination tree, sequential tail; records up to 248 samples
+// by four flat leaf steps, longer ones by the 4-frame register stack walk (PCCF_SG_MAX_N = 1800).  tests/test_twin_flows.py
+// checks it against numpy for every n; the GPU tests check the real kernels against the same oracle.
+static double emu_sg_leaf(const double *a, int n)
+{
+    const int nb = (n >= 8) ? n - (n & 7) : 0;
+    double r[8];
+    for (int j = 0; j < 8; j++) {
+        r[j] = 0.0;
+        if (nb) r[j] = a[j];
+        for (int k = 8; k < nb; k += 8) r[j] += a[k + j];
+    }
+    for (int x = 1; x <= 4; x <<= 1) {                 // r += shfl_xor(r, x), all lanes at once
+        double t[8];
+        for (int j = 0; j < 8; j++) t[j] = r[j] + r[j ^ x];
+        for (int j = 0; j < 8; j++) r[j] = t[j];
+    }
+    double res = r[0];
+    for (int k = nb; k < n; k++) res += a[k];          // the (up to 7) tail elements, in order
+    return res;
+}
+static double emu_sg_pw_sum(const double *a, int n)
+{
+    if (n <= 128) return emu_sg_leaf(a, n);
+    int rn[4] = {0, 0, 0, 0}; double ls[4] = {0, 0, 0, 0};
+    unsigned have_left = 0u; int sp = 0, cur = n; const double *p = a;
+    for (;;) {
+        while (cur > 128) {
+            int n2 = cur >> 1; n2 -= n2 & 7;
+            if (sp >= 4) return 0.0 / 0.0;              // deeper than the register stack: not this path's job
+            rn[sp] = cur - n2; have_left &= ~(1u << sp); sp++; cur = n2;
+        }
+        double res = emu_sg_leaf(p, cur); p += cur;
+        for (;;) {
+            if (sp == 0) return res;
+            const int t = sp - 1;
+            if (!((have_left >> t) & 1u)) { ls[t] = res; have_left |= 1u << t; cur = rn[t]; break; }
+            res = ls[t] + res; sp--;
+        }
+    }
+}
+extern "C" void twin_flows_pass_sums(const double *a, int n, double *out3)
+{
+    const int half = n / 2;
+    if (n <= 248) {                                     // PCCF_FLAT_MAX_N: four leaf steps
+        int n2 = n >> 1; n2 -= n2 & 7;
+        const int c0 = n > 128 ? n2 : n, c1 = n > 128 ? n - n2 : 0;
+        const double l0 = emu_sg_leaf(a, c0), l1 = emu_sg_leaf(a + c0, c1);
+        out3[0] = n > 128 ? l0 + l1 : l0;
+        out3[1] = emu_sg_leaf(a, half);
+        out3[2] = emu_sg_leaf(a + half, n - half);
+    } else {
+        out3[0] = emu_sg_pw_sum(a, n);
+        out3[1] = emu_sg_pw_sum(a, half);
+        out3[2] = emu_sg_pw_sum(a + half, n - half);
+    }
+}
