@@ -16,6 +16,28 @@ def shard_range(n_global, rank, world_size):
     return lo, hi
 
 
+def shard_flow_batch(batch, rank, world_size, n_flows_global):
+    """The records of a global MI batch (numpy arrays in the structure-of-arrays + CSR layout of
+    PccFlowMonitor.make_batch, `flow` = global flow id) that belong to `rank`: flows shard by contiguous id range like
+    envs do, a flow's records stay on one rank in batch order, flow ids are rebased to the rank's monitor.  No
+    collective is involved: every rank can cut its own slice from the global batch, or a front end can route."""
+    import numpy as np
+    lo, hi = shard_range(n_flows_global, rank, world_size)
+    flow = np.asarray(batch["flow"])
+    sel = np.nonzero((flow >= lo) & (flow < hi))[0]
+    off = np.asarray(batch["rtt_off"], dtype=np.int64)
+    n = (off[1:] - off[:-1])[sel]
+    new_off = np.zeros(len(sel) + 1, dtype=np.int64)
+    new_off[1:] = np.cumsum(n)
+    rtt = np.asarray(batch["rtt"])
+    parts = [rtt[off[r]:off[r + 1]] for r in sel]
+    out = {k: np.asarray(v)[sel] for k, v in batch.items() if k not in ("rtt", "rtt_off", "flow")}
+    out["flow"] = (flow[sel] - lo).astype(np.int32)
+    out["rtt_off"] = new_off
+    out["rtt"] = np.concatenate(parts) if parts else np.zeros(0)
+    return out, (lo, hi)
+
+
 def init_from_env(backend=None):
     """Initialises torch.distributed from torchrun's environment; returns (rank, local_rank, world)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))

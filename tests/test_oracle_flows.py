@@ -88,3 +88,30 @@ def test_oracle_flows_vs_live_reference():
             fl.give_sample(i, f["bytes_sent"], f["bytes_acked"], f["bytes_lost"], f["send_start"], f["send_end"],
                            f["recv_start"], f["recv_end"], rtt, f["packet_size"])
         assert np.array_equal(hist[i].as_array(), fl.obs(i)), "step %d" % step
+
+
+def test_flow_sharding_equals_the_unsharded_monitor():
+    """Flows shard by contiguous id range with no exchange (SURVEY.md §8e applied to the ingestion path): the oracle
+    fed with each rank's slice of two global batches (pcc_rl_b200.distributed.shard_flow_batch) reproduces, flow by
+    flow, the oracle fed with the whole batches."""
+    from pcc_rl_b200 import distributed as D
+    from flows_util import synth_batch
+    n_flows, world = 1000, 3
+    g = np.random.default_rng(21)
+    batches = [synth_batch(g, 2500, n_flows, mean_samples=20, unique=False, t0=float(t)) for t in range(2)]
+    whole = oracle.OracleFlows(n_flows)
+    for b in batches:
+        whole.give_batch(b)
+    seen = 0
+    for rank in range(world):
+        lo, hi = D.shard_range(n_flows, rank, world)
+        part = oracle.OracleFlows(hi - lo)
+        for b in batches:
+            sb, rng_ = D.shard_flow_batch(b, rank, world, n_flows)
+            assert rng_ == (lo, hi) and sb["flow"].min() >= 0 and sb["flow"].max() < hi - lo
+            seen += len(sb["flow"])
+            part.give_batch(sb)
+        for i in range(lo, hi):
+            assert np.array_equal(part.obs(i - lo), whole.obs(i)), (rank, i)
+            assert part.conn_min(i - lo) == whole.conn_min(i)
+    assert seen == 2 * 2500
