@@ -39,6 +39,7 @@ class EventRecorder(object):
         self.records = {e: {"Events": []} for e in self.env_ids}
         self.steps = {e: 0 for e in self.env_ids}
         self.episodes = {e: 0 for e in self.env_ids}
+        self.last_finished = {}          # env id -> record of its last completed episode
 
     def record(self, reward, info, done=None):
         """reward [N], info [N, >= 7] (tensors or arrays) of one step; done [N] optional."""
@@ -57,7 +58,6 @@ class EventRecorder(object):
             self.records[e]["Events"].append(make_event(self.steps[e], r[k], m[k]))
             if d is not None and bool(d[k]):
                 self.episodes[e] += 1
-                self.last_finished = getattr(self, "last_finished", {})
                 self.last_finished[e] = self.records[e]
                 self.records[e] = {"Events": []}
                 self.steps[e] = 0
