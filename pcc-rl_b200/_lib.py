@@ -84,9 +84,12 @@ def load(rebuild_if_stale=True):
     if path == _build.LIB and rebuild_if_stale and not _build.up_to_date():
         try:
             _build.build()
-        except Exception:
+        except Exception as ex:
             if not os.path.exists(path):
                 raise
+            import warnings
+            warnings.warn("libpcc_b200.so is older than its sources and rebuilding failed (%s): loading the STALE "
+                          "library" % str(ex).splitlines()[0])
     if not os.path.exists(path):
         raise RuntimeError("libpcc_b200.so is missing (run `python __graft_entry__.py build`); "
                            "there is no CPU fallback")

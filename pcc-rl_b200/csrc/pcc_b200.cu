@@ -109,6 +109,8 @@ __device__ __forceinline__ void flag_overflow(const DevState &p, int64_t e)
     atomicCAS(&p.meta[META_OVF_ENV], 0ull, (unsigned long long)(e + 1));
 }
 
+#include "pcc_packed.cuh"
+
 // ---------------------------------------------------------------------------------------
 // kernels (v1: one thread per env, every phase scalar; see DESIGN.md for the roofline)
 // ---------------------------------------------------------------------------------------
@@ -412,7 +414,12 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
             int32_t bsent = 0;
             bool bovf = false;
             double2 *stage2 = reinterpret_cast<double2 *>(reinterpret_cast<char *>(buf) + (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch));
+#ifdef PCC_SOLO_V1
             coop_send_chunks(g, true, sb, r0, bseed, bdraws, bend, binv, stage2, bt, bq, btu, btail, bh2, bsent, bovf);
+#else
+            group_send_chunks(g, true, sb, r0, bseed, bdraws, bend, binv, *reinterpret_cast<SoloSendSmem *>(stage2), bt, bq,
+                              btu, btail, bh2, bsent, bovf);
+#endif
             if (owner) {
                 c.t = bt; c.q = bq; c.tu = btu; c.tail = btail; c.sent += bsent; c.ovf = c.ovf || bovf;
                 rng.init(rng.seed, bdraws);
@@ -645,6 +652,366 @@ pcc_step_warp_kernel(DevState p, WarpPartition part, const int32_t *__restrict__
         q[7] = (double)o.mi.sent; q[8] = (double)o.mi.acked; q[9] = (double)(clock64() - tk0);
 #endif
     }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// kernels (v5: a lane owns an env, see pcc_packed.cuh) -- Philox streams only
+// ---------------------------------------------------------------------------------------
+// Work partition of a packed step: `perm` is the batch sorted by predicted packets of THIS step (descending).  The
+// first n_solo entries (predicted packets above the solo threshold; their serial chain would make a lane-per-env warp
+// the step's critical path) get a warp each -- the cooperative single-env path of pcc_warp.cuh --, the rest is cut
+// into groups of 32 consecutive entries, one warp per group, one env per lane: similar work on every lane.
+struct PackedPartition {
+    const int32_t *perm;      // [n] env ids, heaviest first
+    const uint32_t *sched;    // [units] launch order: (role << 28) | unit index, longest estimated run time first
+    const int32_t *counts;    // device: [0] envs above the solo threshold, [1] envs above the quad threshold (and not solo),
+                              //         [2] number of work units (warps with work)
+    int32_t n_solo_cap;       // launch geometry covers at most this many solo warps ...
+    int32_t n_quad_cap;       // ... and this many quad ENVS (four per warp)
+    int32_t wbuf;             // staging capacity (samples) of a solo warp
+};
+#define PCC_PACKED_THREADS 128
+#ifndef PCC_PACKED_SOLO_WBUF
+#define PCC_PACKED_SOLO_WBUF 1024
+#endif
+__host__ __device__ inline size_t packed_warp_smem_bytes()
+{
+    const size_t a = sizeof(PackedSmem), b = warp_smem_bytes(PCC_PACKED_SOLO_WBUF), c = 4 * sizeof(GroupSmemV2<8>);
+    const size_t m = a > b ? (a > c ? a : c) : (b > c ? b : c);
+    return (m + 127) & ~(size_t)127;
+}
+
+// Phase C of a lane-per-env warp: MI metrics, reward, state write-back per lane; the history ring and the observation
+// row (oldest -> newest) of every owned env are written by the whole warp, one contiguous H*F row per instruction.
+__device__ __forceinline__ void packed_emit(const DevState &p, double *rowbuf, bool owner, int64_t e, EnvState &s,
+                                            const MiOut &mo, double avg_lat, double lat_inc, unsigned long long draws,
+                                            unsigned long long head_step, double *__restrict__ obs,
+                                            double *__restrict__ reward, uint8_t *__restrict__ done,
+                                            int32_t *__restrict__ counts, double *__restrict__ info)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int H = p.H, F = p.F, HF = H * F;
+    if (owner) {
+        MiStats st;
+        mi_stats_finish(mo, p.c, avg_lat, lat_inc, s.conn_min, true, st);
+        s.steps += 1;                                                                // :419
+        if (st.avg_lat > 0.0) s.run_dur = 0.5 * st.avg_lat;                          // :437-438
+        const bool dn = s.steps >= p.c.max_steps;                                    // :444
+        store_env_dynamic(p, e, s);
+        p.draws[e] = draws;
+        if (mo.overflow) flag_overflow(p, e);
+        for (int f = 0; f < F; f++) rowbuf[lane * PCC_MAX_FEATURES + f] = metric_value(st, p.ids[f]);
+        reward[e] = st.reward;
+        done[e] = dn ? 1 : 0;
+        const double acc = p.ret_acc[e] + st.reward;                                 // :443
+        p.ret_acc[e] = acc;
+        if (dn) p.ret_last[e] = acc;
+        if (counts) { counts[3 * e + 0] = mo.sent; counts[3 * e + 1] = mo.acked; counts[3 * e + 2] = mo.lost; }
+        if (info) {
+            double *q = info + (size_t)e * PCC_INFO_WIDTH;
+            q[0] = st.send_rate; q[1] = st.recv_rate; q[2] = st.avg_lat; q[3] = st.loss_ratio;
+            q[4] = st.lat_infl; q[5] = st.lat_ratio; q[6] = st.send_ratio; q[7] = st.dur;
+            q[8] = s.cur_time; q[9] = s.rate; q[10] = s.run_dur; q[11] = s.conn_min;
+        }
+    }
+    __syncwarp();
+    const unsigned om = __ballot_sync(PCC_FULL, owner);
+    const int slot_new = (int)(head_step % (unsigned long long)H);
+    double *__restrict__ hist = p.hist;
+    if (HF <= 32) {
+        // one lane per element of the row; the history reads of four envs are in flight before their stores
+        const int k = (int)lane;
+        const int h = k / F, f = k - h * F;
+        int sl = slot_new + 1 + h;
+        if (sl >= H) sl -= H;
+        const bool act = k < HF, isnew = act && (h == H - 1);
+        const int src = isnew ? 0 : sl * F + f;
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32; j0 += 4) {
+            if (!((om >> j0) & 0xFu)) continue;                                      // warp-uniform
+            double v[4];
+            long long ej[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                ej[u] = __shfl_sync(PCC_FULL, (long long)e, j0 + u);
+                v[u] = 0.0;
+                if (((om >> (j0 + u)) & 1u) && act && !isnew) v[u] = hist[(size_t)ej[u] * HF + src];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (!((om >> (j0 + u)) & 1u) || !act) continue;
+                if (isnew) {
+                    v[u] = rowbuf[(j0 + u) * PCC_MAX_FEATURES + f];
+                    hist[(size_t)ej[u] * HF + slot_new * F + f] = v[u];            // the new row replaces the oldest slot
+                }
+                obs[(size_t)ej[u] * HF + k] = v[u];
+            }
+        }
+    } else {
+        for (int j = 0; j < 32; j++) {
+            if (!((om >> j) & 1u)) continue;                                         // warp-uniform
+            const long long ej = __shfl_sync(PCC_FULL, (long long)e, j);
+            double *hrow = hist + (size_t)ej * HF;
+            double *ob = obs + (size_t)ej * HF;
+            for (int k = (int)lane; k < HF; k += 32) {
+                const int h = k / F, f = k - h * F;
+                double v;
+                if (h == H - 1) {
+                    v = rowbuf[j * PCC_MAX_FEATURES + f];
+                    hrow[slot_new * F + f] = v;                                      // the new row replaces the oldest slot
+                } else {
+                    int sl = slot_new + 1 + h;
+                    if (sl >= H) sl -= H;
+                    v = hrow[sl * F + f];
+                }
+                ob[k] = v;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+#ifndef PCC_PACKED_MINBLOCKS
+#define PCC_PACKED_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(PCC_PACKED_THREADS, PCC_PACKED_MINBLOCKS)
+pcc_step_packed_kernel(DevState p, PackedPartition part, unsigned long long head_step,
+                       const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
+                       uint8_t *__restrict__ done, int32_t *__restrict__ counts, double *__restrict__ info)
+{
+    extern __shared__ double dyn_smem[];      // per warp: packed_warp_smem_bytes()
+    const int wib = (int)(threadIdx.x >> 5);
+    double *wsm = dyn_smem + (size_t)wib * (packed_warp_smem_bytes() / 8);
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t w = (int64_t)blockIdx.x * (PCC_PACKED_THREADS / 32) + wib;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
+    int n_solo = part.counts[0], n_quad = part.counts[1];
+    if (n_solo > part.n_solo_cap) n_solo = part.n_solo_cap;
+    if ((int64_t)n_solo > p.n) n_solo = (int)p.n;
+    if (n_quad > part.n_quad_cap) n_quad = part.n_quad_cap;
+    const int nqw = (n_quad + 3) / 4;                                                 // quad warps
+    int64_t pos_packed = (int64_t)n_solo + 4 * (int64_t)nqw;                          // first sorted position of the packed part
+    if (pos_packed > p.n) pos_packed = p.n;
+    // launch order: the unit this warp runs (pcc_schedule_kernel: longest estimated run time first, whatever its role)
+    if (w >= part.counts[2]) return;                                                  // whole warp
+    const uint32_t unit = part.sched[w];
+    const int role = (int)(unit >> 28);
+    const int64_t uj = (int64_t)(unit & 0x0fffffffu);
+    if (role == 1) {
+        // ---- four envs of similar (medium / heavy) work, 8 lanes each: the group-cooperative MI of pcc_coop.cuh with the
+        // second-generation send phase; the four chain lanes share one instruction stream
+        const Grp<8> g;
+        const int grp = (int)(lane >> 3);
+        int64_t pos = (int64_t)n_solo + 4 * uj + grp;
+        const bool alive = pos < p.n;
+        if (!alive) pos = p.n - 1;
+        const int64_t e = (int64_t)part.perm[pos];
+        GroupSmemV2<8> &sm = reinterpret_cast<GroupSmemV2<8> *>(wsm)[grp];
+        EnvState s;
+        load_env(p, e, s);
+        DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
+        const uint64_t seed = p.seed[e];
+        uint64_t draws = p.draws[e];
+        StepOut o;
+        s.rate = apply_rate_delta(s.rate, actions[e], p.c);                          // :412
+        double *gbuf = p.mean_scratch ? p.mean_scratch + (size_t)e * PCC_GSCRATCH : nullptr;
+#ifdef PCC_PROFILE
+        const long long tq0 = clock64();
+        unsigned long long gtq0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gtq0));
+        long long qprof[8];
+        run_mi_coop(g, alive, s, ring, seed, draws, s.run_dur, sm, o.mi, qprof, gbuf, PCC_GSCRATCH);
+        qprof[6] = clock64();
+#else
+        run_mi_coop(g, alive, s, ring, seed, draws, s.run_dur, sm, o.mi, nullptr, gbuf, PCC_GSCRATCH);   // :416
+#endif
+        double avg_lat, lat_inc;
+        mi_means_coop(g, alive, o.mi, ring, s.dl, sm, p.need_inc != 0, avg_lat, lat_inc, gbuf, PCC_GSCRATCH);
+#ifdef PCC_PROFILE
+        qprof[7] = clock64();
+#endif
+        mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
+        s.steps += 1;                                                                // :419
+        if (o.st.avg_lat > 0.0) s.run_dur = 0.5 * o.st.avg_lat;                      // :437-438
+        o.done = s.steps >= p.c.max_steps;                                           // :444
+        if (!alive) return;
+        coop_emit(g, p, e, head_step, o.st, obs);
+        if (g.gl == 0) {
+            store_env_dynamic(p, e, s);
+            p.draws[e] = draws;
+            if (o.mi.overflow) flag_overflow(p, e);
+            reward[e] = o.st.reward;
+            done[e] = o.done ? 1 : 0;
+            const double acc = p.ret_acc[e] + o.st.reward;                           // :443
+            p.ret_acc[e] = acc;
+            if (o.done) p.ret_last[e] = acc;
+            if (counts) { counts[3 * e + 0] = o.mi.sent; counts[3 * e + 1] = o.mi.acked; counts[3 * e + 2] = o.mi.lost; }
+            if (info) {
+                double *q = info + (size_t)e * PCC_INFO_WIDTH;
+                q[0] = o.st.send_rate; q[1] = o.st.recv_rate; q[2] = o.st.avg_lat; q[3] = o.st.loss_ratio;
+                q[4] = o.st.lat_infl; q[5] = o.st.lat_ratio; q[6] = o.st.send_ratio; q[7] = o.st.dur;
+                q[8] = s.cur_time; q[9] = s.rate; q[10] = s.run_dur; q[11] = s.conn_min;
+#ifdef PCC_PROFILE   // profiling build: cycles of send, hop1+bnd1, hop2+bnd2+cross, means; role -4, counts, times
+                unsigned long long gt1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+                q[0] = (double)(qprof[1] - qprof[0]); q[1] = (double)(qprof[3] - qprof[1]); q[2] = (double)(qprof[6] - qprof[3]);
+                q[3] = 0.0; q[4] = (double)(qprof[7] - qprof[6]); q[5] = (double)(clock64() - qprof[7]);
+                q[6] = -4.0; q[7] = (double)o.mi.sent; q[8] = (double)o.mi.acked; q[9] = (double)(clock64() - tq0);
+                q[10] = (double)gtq0; q[11] = (double)gt1;
+#endif
+            }
+        }
+        return;
+    }
+    if (role == 0) {
+        // ---- a heavy env alone in its warp: cooperative path (chain on lane 0, Philox / scans / means on all lanes)
+        const Grp<32> g;
+        const bool owner = lane == 0;
+        const int64_t e = owner ? (int64_t)part.perm[uj] : 0;
+        EnvState s;
+        load_env(p, e, s);
+        PhiloxRng rng;
+        rng.init(p.seed[e], p.draws[e]);
+        s.rate = apply_rate_delta(s.rate, actions[e], p.c);                          // :412
+        MiOut mo;
+        double avg_lat, lat_inc;
+#ifdef PCC_PROFILE
+        const long long tsolo0 = clock64();
+        unsigned long long gtsolo0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gtsolo0));
+#endif
+#ifdef PCC_PROFILE
+        long long sprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#else
+        long long *sprof = nullptr;
+#endif
+        warp_mi<true, true, false>(g, p, owner, 1, e, s, rng, s.run_dur, wsm, part.wbuf,
+                                   *reinterpret_cast<WarpStage *>(wsm), mo, avg_lat, lat_inc, 0, sprof,
+                                   p.mean_scratch ? p.mean_scratch + (size_t)__shfl_sync(PCC_FULL, (long long)e, 0) * PCC_GSCRATCH
+                                                  : nullptr);   // :416 (scratch rows are per env)
+        __syncwarp();
+#ifdef PCC_PROFILE
+        const long long tsolo1 = clock64();
+#endif
+        packed_emit(p, wsm, owner, e, s, mo, avg_lat, lat_inc, rng.draws, head_step, obs, reward, done, counts, info);
+#ifdef PCC_PROFILE
+        if (owner && info) {
+            unsigned long long gt1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+            double *q = info + (size_t)e * PCC_INFO_WIDTH;
+            for (int k = 0; k < 6; k++) q[k] = 0.0;
+            q[0] = (double)(sprof[1] - sprof[0]); q[1] = (double)sprof[2]; q[2] = (double)sprof[3];
+            q[6] = -1.0; q[7] = (double)mo.sent; q[8] = (double)mo.acked; q[9] = (double)(tsolo1 - tsolo0);
+            q[10] = (double)gtsolo0; q[11] = (double)gt1;
+        }
+#endif
+        return;
+    }
+    // ---- 32 envs of similar predicted work, one per lane ------------------------------------------------------------
+    const int64_t first = pos_packed + uj * 32;
+    if (first >= p.n) return;                                                        // whole warp
+    const int cnt = (int)((p.n - first < 32) ? (p.n - first) : 32);
+    const bool owner = (int)lane < cnt;
+    const int64_t e = owner ? (int64_t)part.perm[first + lane] : 0;
+    EnvState s;
+    load_env(p, e, s);
+    s.rate = apply_rate_delta(s.rate, actions[e], p.c);                              // :412
+    LaneDraws rng;
+    rng.init(p.seed[e], p.draws[e], s.lr);
+    PackedSmem &sm = *reinterpret_cast<PackedSmem *>(wsm);
+    const RingSet rs{p.rings, p.cap, p.cap - 1u};
+    PackedOut po;
+#ifdef PCC_PROFILE
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long gt0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+    packed_mi<true>(rs, sm, owner, (int)e, s, rng, s.run_dur, p.need_inc != 0, po, prof);
+#else
+    packed_mi<true>(rs, sm, owner, (int)e, s, rng, s.run_dur, p.need_inc != 0, po);  // :416
+#endif
+    MiOut mo;
+    mo.sent = po.sent; mo.acked = po.acked; mo.lost = po.lost; mo.start = po.start; mo.end = po.end;
+    mo.overflow = po.overflow;
+    packed_emit(p, wsm, owner, e, s, mo, po.avg_lat, po.lat_inc, rng.draws, head_step, obs, reward, done, counts, info);
+#ifdef PCC_PROFILE   // profiling build: info = cycles of the warp's phases A, B1, B2, crossing, B3, emit; role, counts, times
+    if (owner && info) {
+        const long long tend = clock64();
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+        double *q = info + (size_t)e * PCC_INFO_WIDTH;
+        for (int k = 0; k < 5; k++) q[k] = (double)(prof[k + 1] - prof[k]);
+        q[5] = (double)(tend - prof[5]); q[6] = (double)cnt; q[7] = (double)mo.sent; q[8] = (double)mo.acked;
+        q[9] = (double)(tend - prof[0]); q[10] = (double)gt0; q[11] = (double)gt1;
+    }
+#endif
+}
+
+// predicted packets of the step about to run (its action applied): the sort key of the packed partition
+__global__ void pcc_cost_packed_kernel(DevState p, const double *__restrict__ actions, uint32_t solo_packets,
+                                       uint32_t quad_packets, uint32_t *__restrict__ keys, int32_t *__restrict__ vals,
+                                       int32_t *__restrict__ cnt_w, int32_t *__restrict__ cnt_clear)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) { cnt_clear[0] = 0; cnt_clear[1] = 0; }   // the counters of the NEXT rebalance
+    if (e >= p.n) return;
+    const double rate = apply_rate_delta(p.rate[e], actions[e], p.c);
+    double pk = (p.cur_time[e] + p.run_dur[e] - p.next_send[e]) * rate + 1.0;
+    if (!(pk > 0.0)) pk = 0.0;
+    const uint32_t key = (uint32_t)fmin(pk, 65535.0);
+    keys[e] = key;
+    vals[e] = (int32_t)e;
+    if (key > solo_packets) atomicAdd(cnt_w, 1);
+    else if (key > quad_packets) atomicAdd(cnt_w + 1, 1);
+}
+
+// Launch order of the packed step: every warp-sized work unit -- a solo env, four quad envs, 32 lane-per-env envs --
+// gets an estimated run time (cycles per packet of its heaviest env, measured per role: tools/phase_profile_packed.py)
+// and the units are ranked longest first across the roles (each role's list is already sorted: a rank is the unit's own
+// index plus a binary search in each of the two other lists).  Blocks are dispatched in index order, so the long units
+// start at once and the short ones fill the tail.
+struct SchedCost { float solo, quad, lanes; };
+__device__ __forceinline__ int sched_count_greater(const uint32_t *__restrict__ keys, int64_t base, int stride, int count,
+                                                   float a, float mine, bool ties_first)
+{
+    int lo = 0, hi = count;                        // units [0, lo) of the other role run before mine
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float c = a * (float)keys[base + (int64_t)mid * stride];
+        if (c > mine || (ties_first && c == mine)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__global__ void pcc_schedule_kernel(const uint32_t *__restrict__ sorted_keys, int64_t n, int32_t *__restrict__ counts,
+                                    int n_solo_cap, int n_quad_cap, SchedCost sc, uint32_t *__restrict__ sched)
+{
+    int n_solo = counts[0], n_quad = counts[1];
+    if (n_solo > n_solo_cap) n_solo = n_solo_cap;
+    if ((int64_t)n_solo > n) n_solo = (int)n;
+    if (n_quad > n_quad_cap) n_quad = n_quad_cap;
+    const int nqw = (n_quad + 3) / 4;
+    int64_t pos_packed = (int64_t)n_solo + 4 * (int64_t)nqw;
+    if (pos_packed > n) pos_packed = n;
+    const int nqw_eff = (int)((pos_packed - n_solo + 3) / 4);
+    const int npw = (int)((n - pos_packed + 31) / 32);
+    const int units = n_solo + nqw_eff + npw;
+    const int u = (int)((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (u == 0) counts[2] = units;
+    if (u >= units) return;
+    int role, j;
+    if (u < n_solo) { role = 0; j = u; }
+    else if (u < n_solo + nqw_eff) { role = 1; j = u - n_solo; }
+    else { role = 2; j = u - n_solo - nqw_eff; }
+    const int64_t base[3] = {0, (int64_t)n_solo, pos_packed};
+    const int stride[3] = {1, 4, 32};
+    const int count[3] = {n_solo, nqw_eff, npw};
+    const float a[3] = {sc.solo, sc.quad, sc.lanes};
+    const float mine = a[role] * (float)sorted_keys[base[role] + (int64_t)j * stride[role]];
+    int rank = j;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        if (r != role) rank += sched_count_greater(sorted_keys, base[r], stride[r], count[r], a[r], mine, r < role);
+    sched[rank] = ((uint32_t)role << 28) | (uint32_t)j;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1075,6 +1442,16 @@ struct pcc_handle_s {
     int n_pair;               // big batches: helpers for the n_pair heaviest slots only (pcc_step_warp_kernel<false, 2>)
     int64_t max_warps;
     CostModel cm;
+    // packed mode (pcc_step_packed_kernel): a lane owns an env, the batch re-sorted by predicted packets
+    bool packed;
+    int packed_every;         // re-sort every this many steps (1 = every step)
+    int solo_packets;         // predicted packets above which an env gets a warp to itself
+    int quad_packets;         // predicted packets above which an env is run by 8 lanes (four envs per warp)
+    int n_solo_cap, n_quad_cap;
+    int32_t *n_solo_dev;      // [2][4] device counters (solo, quad, units), alternating between rebalances
+    uint32_t *sched;          // launch order of the work units
+    SchedCost sched_cost;
+    int reb_parity;
     // staging for pcc_step_host
     double *st_actions, *st_obs, *st_reward;
     uint8_t *st_done;
@@ -1216,16 +1593,18 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     const char *epw = getenv("PCC_B200_EPW");
     const bool small_batch = cfg->n_envs <= 16384;
     h->epw = 0;
-    if (!mode || !strcmp(mode, "warp")) {
+    if (!mode || !strcmp(mode, "warp") || !strcmp(mode, "packed")) {
         h->epw = epw ? atoi(epw) : 8;   // static envs per warp, used only when rebalancing is off
         if (h->epw != 4 && h->epw != 8 && h->epw != 16 && h->epw != 32) h->epw = 8;
         h->group = 0;
+        // big batches: lane-per-env packed execution (throughput); small batches: warp-per-heavy-env (latency)
+        h->packed = mode ? !strcmp(mode, "packed") : !small_batch;
     } else if (!strcmp(mode, "scalar")) {
         h->group = 0;
     } else if (!grp) {
         h->group = small_batch ? 32 : 8;
     }
-    if (cfg->rng_kind != PCC_RNG_PHILOX) { h->group = 0; h->epw = 0; }   // MT19937 (fidelity mode): scalar kernels
+    if (cfg->rng_kind != PCC_RNG_PHILOX) { h->group = 0; h->epw = 0; h->packed = false; }   // MT19937 (fidelity mode): scalar kernels
     {
         const char *wb = getenv("PCC_B200_WBUF");
         h->wbuf = wb ? atoi(wb) : (small_batch ? 4096 : 512);   // big batches: small shared buffer -> 16 warps/SM; heavy MIs stage to global scratch
@@ -1290,10 +1669,37 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         if (ce == cudaSuccess) ce = cudaMalloc(&h->starts, 4 * (n + 2));
         if (ce == cudaSuccess) ce = cudaMalloc(&h->n_warps, 4);
         if (ce == cudaSuccess) ce = cudaMalloc(&h->sent_tmp, 4 * n);
-        if (ce == cudaSuccess && h->wbuf < PCC_GSCRATCH && !getenv("PCC_B200_NO_GSCRATCH"))
+        if (ce == cudaSuccess && (h->wbuf < PCC_GSCRATCH || h->packed) && !getenv("PCC_B200_NO_GSCRATCH"))
             ce = cudaMalloc(&h->d.mean_scratch, (size_t)n * PCC_GSCRATCH * 8);   // one row per (possible) warp
         const char *sp = getenv("PCC_B200_SPLIT");
         h->split = sp ? atoi(sp) != 0 : false;   // two-kernel variant: measured slower, kept for experiments
+        if (h->packed) {
+            const char *pe = getenv("PCC_B200_PACKED_EVERY"), *so = getenv("PCC_B200_SOLO");
+            h->packed_every = pe ? atoi(pe) : 1;
+            if (h->packed_every < 1) h->packed_every = 1;
+            const char *qu = getenv("PCC_B200_QUAD");
+            h->solo_packets = so ? atoi(so) : 1200;
+            if (h->solo_packets < 32) h->solo_packets = 32;
+            if (h->solo_packets > 65534) h->solo_packets = 65534;
+            h->quad_packets = qu ? atoi(qu) : 192;
+            if (h->quad_packets < 8) h->quad_packets = 8;
+            if (h->quad_packets > h->solo_packets) h->quad_packets = h->solo_packets;
+            h->n_solo_cap = (int)(n / 32 > 64 ? n / 32 : 64);
+            if ((int64_t)h->n_solo_cap > (int64_t)n) h->n_solo_cap = (int)n;
+            h->n_quad_cap = (int)(n / 2 > 256 ? n / 2 : 256);
+            if ((int64_t)h->n_quad_cap > (int64_t)n) h->n_quad_cap = (int)n;
+            if (ce == cudaSuccess) ce = cudaMalloc(&h->n_solo_dev, 8 * sizeof(int32_t));
+            if (ce == cudaSuccess) ce = cudaMemset(h->n_solo_dev, 0, 8 * sizeof(int32_t));
+            if (ce == cudaSuccess) ce = cudaMalloc(&h->sched, sizeof(uint32_t) * (size_t)(h->n_solo_cap + (h->n_quad_cap + 3) / 4 + (n + 31) / 32 + 8));
+            // estimated cycles per packet of a unit's heaviest env, per role (B200, 65 536 envs, profiles/r02_phase_profile_packed.txt)
+            const char *cs = getenv("PCC_B200_SCHED_COST");
+            h->sched_cost = SchedCost{1e9f, 1e5f, 1.0f};   // role order; a merged order (225;755;2900) measured no better
+            if (cs && sscanf(cs, "%f;%f;%f", &h->sched_cost.solo, &h->sched_cost.quad, &h->sched_cost.lanes) != 3)
+                sscanf(cs, "%f,%f,%f", &h->sched_cost.solo, &h->sched_cost.quad, &h->sched_cost.lanes);
+            if (ce == cudaSuccess)
+                ce = cudaFuncSetAttribute(pcc_step_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)((PCC_PACKED_THREADS / 32) * packed_warp_smem_bytes()));
+        }
         if (ce != cudaSuccess) { delete h; return fail(PCC_ECUDA, "rebalance scratch: %s", cudaGetErrorString(ce)); }
     }
     if (init) {
@@ -1327,7 +1733,7 @@ void pcc_destroy(pcc_handle h)
     cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_reward);
     cudaFree(h->st_done); cudaFree(h->st_counts);
     cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->perm); cudaFree(h->sort_tmp);
-    cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps); cudaFree(h->sent_tmp); cudaFree(h->d.mean_scratch);
+    cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps); cudaFree(h->sent_tmp); cudaFree(h->d.mean_scratch); cudaFree(h->n_solo_dev); cudaFree(h->sched);
     delete h;
 }
 
@@ -1444,7 +1850,31 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
         h->steps_since_rebalance++;
         scalar_perm = h->perm;
     }
-    if (h->epw) {
+    if (h->packed && h->perm) {
+        const int64_t n = h->cfg.n_envs;
+        if (h->rebalance_now || h->steps_since_rebalance >= h->packed_every) {
+            // sort the batch by the packets this step will send (16-bit keys: two radix passes)
+            h->reb_parity ^= 1;
+            pcc_cost_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                h->d, actions_dev, (uint32_t)h->solo_packets, (uint32_t)h->quad_packets, h->sort_keys_in, h->sort_vals_in,
+                h->n_solo_dev + 4 * h->reb_parity, h->n_solo_dev + 4 * (h->reb_parity ^ 1));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp, h->sort_tmp_bytes, h->sort_keys_in,
+                                                               h->sort_keys_out, h->sort_vals_in, h->perm, (int)n, 0, 16, st));
+            const int64_t max_units = (int64_t)h->n_solo_cap + (h->n_quad_cap + 3) / 4 + (n + 31) / 32;
+            pcc_schedule_kernel<<<(unsigned)((max_units + 255) / 256), 256, 0, st>>>(
+                h->sort_keys_out, n, h->n_solo_dev + 4 * h->reb_parity, h->n_solo_cap, h->n_quad_cap, h->sched_cost, h->sched);
+            h->rebalance_now = false;
+            h->steps_since_rebalance = 0;
+            h->launches += 3;
+        }
+        h->steps_since_rebalance++;
+        PackedPartition pp{h->perm, h->sched, h->n_solo_dev + 4 * h->reb_parity, h->n_solo_cap, h->n_quad_cap, PCC_PACKED_SOLO_WBUF};
+        const int wpb = PCC_PACKED_THREADS / 32;
+        const int64_t nwarps = (int64_t)h->n_solo_cap + (h->n_quad_cap + 3) / 4 + (n + 31) / 32;
+        pcc_step_packed_kernel<<<(unsigned)((nwarps + wpb - 1) / wpb), PCC_PACKED_THREADS, wpb * packed_warp_smem_bytes(), st>>>(
+            h->d, pp, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
+    }
+    else if (h->epw) {
         WarpPartition part{nullptr, nullptr, nullptr, h->epw, h->wbuf, 0};
         const int wpb = h->warp_threads / 32;
         const size_t dyn = (size_t)wpb * warp_smem_bytes(h->wbuf);

@@ -80,6 +80,15 @@ __device__ __forceinline__ uint64_t interleave_bits(uint32_t even_bits, uint32_t
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// One instruction per scan round: lane gl asks L2 for the 128-byte line (8 records) that starts 8 * gl records past the
+// round's windows, so the next 8 * G records -- two rounds -- are on their way while this round's loads are consumed.
+template <int G, class Ring>
+__device__ __forceinline__ void scan_prefetch(const Grp<G> &g, Ring &ring, uint32_t i, uint32_t lim, bool on)
+{
+    const uint32_t o = (uint32_t)(PCC_SCAN_W * G) + g.gl * 8u;
+    if (on && o < (uint32_t)(lim - i)) prefetch_l2_line(ring.addr(i + o));
+}
 
 // window load: lane gl gets record i + gl if `on` and it lies before `lim`, else a neutral
 // dummy (a = +inf: never consumable, not flagged; l = +1: not dropped)
@@ -119,6 +128,7 @@ __device__ __forceinline__ void window_argmin(const Grp<G> &g, bool cand, double
 // Per-group shared-memory scratch
 template <int G>
 struct GroupSmem {
+    static constexpr bool kSendV2 = false;
     double2 stage[2 * G + 1];    // records of one send chunk (slot k + 1 = packet k)
     double buf[PCC_LEAF + ((G == 32) ? 4 : 1) * G];    // acked-latency staging for np.mean
 };
@@ -221,6 +231,182 @@ __device__ __forceinline__ void coop_send_chunks(const Grp<G> &g, bool alive, co
     __syncwarp();   // record stores above are read by other lanes below
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Send phase, second generation: G lanes per env, the 32/G groups of a warp in lock step (G = 32: a heavy env alone in
+// its warp; G = 8: four envs per warp).  What is serial in binary64 is only the queue recurrence  q' = f(q - x)  over
+// the packets that were NOT randomly dropped (network_sim.py:66-84); the first version's chain lane also ran the
+// pacing-timer recurrence, tested the drop bit, built every record and stored it (115-200 cycles per packet in situ
+// against 42 for the bare recurrence, profiles/r01_chain_microbench.txt).  Here, per chunk of 64 packets:
+//   S1  loss draws: 32/G Philox blocks per lane, compared as 53-bit integers (loss_threshold), ballots -> drop mask;
+//   S2  how many of the chunk's send times are < end (the times are already in shared memory, see S4);
+//   S3  x_k = t_k - t_(last packet before k that reached the queue), COMPACTED over the packets that reach the queue;
+//   S4  lane 0 of the group runs  y = q - x,  q = f(y)  in place over that compact array: one LDS, two DADD, two DSETP
+//       and the selects per packet.  The SAME instruction stream, on lane 1, is the pacing-timer recurrence
+//       t_(k+1) = fl(t_k + 1/rate) (:161) of the NEXT chunk: its array is pre-filled with x = -1/rate and its tail-drop
+//       threshold is -inf, so it computes y = t + 1/rate and selects it -- exact, and free, because the dependency
+//       chain of lane 0 leaves most issue slots idle.  With G = 8 the four chains and four timers of a warp share it;
+//   S5  all lanes turn (t_k, y, drop bits) into records -- a randomly dropped packet sees y = f(y of the previous
+//       packet that reached the queue) - x_k, recomputed here -- and store them to the ring, coalesced.
+// Every lane of a group holds the same (t, qd, t_upd, tail, draws, sent) on entry and on exit.  Warp-uniform control
+// flow: all 32 lanes call it together.
+struct SoloSendSmem {
+    double ts[2][72];      // send times of the current / next chunk: ts[b][k] = packet k, ts[b][navail] = the one after
+    double xs[64];         // x of the packets that reach the queue, compact; overwritten in place by y
+};
+
+template <int G>
+struct GroupSmemV2 {
+    static constexpr bool kSendV2 = true;
+    SoloSendSmem send;
+    double buf[PCC_LEAF + ((G == 32) ? 4 : 1) * G];    // acked-latency staging for np.mean
+};
+
+template <int G, class Ring>
+__device__ __forceinline__ void group_send_chunks(const Grp<G> &g, bool alive, const EnvState &s, Ring &ring, uint64_t seed,
+                                                  uint64_t &draws, double end, double inv_rate, SoloSendSmem &sm, double &t,
+                                                  double &qd, double &t_upd, uint32_t &tail, uint32_t h2, int32_t &sent,
+                                                  bool &ovf)
+{
+    constexpr int NB = 32 / G;          // Philox blocks per lane and chunk
+    constexpr int PPL = 64 / G;         // packets per lane and chunk
+    const uint32_t cap = ring.capacity();
+    bool more = alive && (t < end);
+    if (!__any_sync(PCC_FULL, more)) return;                  // warp-uniform
+    const uint64_t thr = loss_threshold(s.lr);
+    const double k0 = (0.0 > s.w_full) ? 0.0 : s.d_bw;        // q' when the queue has drained (w = 0)
+    const bool full0 = 0.0 > s.w_full;
+    const bool timer = g.gl == 1;
+    const double r_dbw = timer ? 0.0 : s.d_bw;
+    const double r_wfull = timer ? __longlong_as_double((long long)PCC_NEG_INF) : s.w_full;
+    const double neg_rate = -inv_rate;
+    // send times of the first chunk: the recurrence (:161), once per MI; the timer lane's array of the next chunk
+    if (g.gl == 0 && more) {
+        double tt = t;
+#pragma unroll 13
+        for (int k = 0; k < 65; ++k) { sm.ts[0][k] = tt; tt = tt + inv_rate; }
+    }
+#pragma unroll
+    for (int u = 0; u < PPL; u++) sm.ts[1][1 + (int)g.gl + u * G] = neg_rate;
+    __syncwarp();
+    int b = 0;
+    double q = qd, tu = t_upd;
+    while (__any_sync(PCC_FULL, more)) {
+        const unsigned off = (unsigned)(draws & 1ull);
+        const int navail = 64 - (int)off;
+        // S1: bit k of dm = packet k of the chunk is randomly dropped (:73)
+        unsigned be = 0u, bo = 0u;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            uint32_t c0, c1, c2, c3;
+            philox_block(seed, (draws >> 1) + (uint64_t)(j * G) + g.gl, c0, c1, c2, c3);
+            be |= g.ballot(u53(c0, c1) < thr) << (j * G);
+            bo |= g.ballot(u53(c2, c3) < thr) << (j * G);
+        }
+        const uint64_t dm = interleave_bits(be, bo) >> off;
+        // S2: packets of this chunk that are sent in this MI (send times increase: a prefix)
+        double tk[PPL];
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < PPL; u++) {
+            const int k = (int)g.gl + u * G;
+            tk[u] = sm.ts[b][k];
+            cnt += __popc(g.ballot(k < navail && tk[u] < end));
+        }
+        bool fits = true;
+        if (more && (uint32_t)(tail - h2) + (uint32_t)cnt > cap) { ovf = true; fits = false; }   // fatal, reported by the host
+        const bool work = more && fits;
+        if (!work) cnt = 0;
+        const double t_after = sm.ts[b][navail];
+        const bool next = work && (cnt == navail) && (t_after < end);
+        const uint64_t sentm = (cnt >= 64) ? ~0ull : ((1ull << cnt) - 1ull);
+        const uint64_t ndm = ~dm & sentm;                     // sent packets that reach the queue
+        const int cnt_nd = __popcll(ndm);
+        // S3: x_k (:66-67 with :75-76: the update time is the send time of the last packet that reached the queue)
+#pragma unroll
+        for (int u = 0; u < PPL; u++) {
+            const int k = (int)g.gl + u * G;
+            const uint64_t before = ndm & ((1ull << k) - 1ull);
+            if ((ndm >> k) & 1ull) {
+                const double tuk = before ? sm.ts[b][63 - __clzll((long long)before)] : tu;
+                sm.xs[__popcll(before)] = tk[u] - tuk;
+            }
+        }
+        __syncwarp();
+        // S4: the two recurrences of every group, one instruction stream, in place
+        double state = q;
+        {
+            const int niter = timer ? (next ? 64 : 0) : cnt_nd;
+            int kmax = (g.gl < 2) ? niter : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(PCC_FULL, kmax, o); kmax = v > kmax ? v : kmax; }
+            if (g.gl < 2) {
+                double *io = timer ? &sm.ts[b ^ 1][1] : &sm.xs[0];
+                if (timer) { state = t_after; if (next) sm.ts[b ^ 1][0] = t_after; }
+#pragma unroll 4
+                for (int k = 0; k < kmax; ++k) {
+                    const bool on = k < niter;
+                    const double x = io[k];
+                    const double y = state - x;                               // :66-67 | t + 1/rate
+                    if (on) io[k] = y;
+                    const double cpos = r_dbw + y;                            // :82 if 0 < y <= w_full
+                    const bool pos = y > 0.0;
+                    const bool fullp = y > r_wfull;                           // :77-79 (tail_drop_threshold)
+                    double qn = fullp ? y : cpos;
+                    qn = pos ? qn : k0;
+                    state = on ? qn : state;
+                }
+            }
+        }
+        __syncwarp();
+        // S5: records (:173-175) and the chunk's carry
+#pragma unroll
+        for (int u = 0; u < PPL; u++) {
+            const int k = (int)g.gl + u * G;
+            if (k < cnt) {
+                const uint64_t before = ndm & ((1ull << k) - 1ull);
+                const int rank = __popcll(before);
+                const bool rdrop = ((dm >> k) & 1ull) != 0ull;
+                double y;
+                if (!rdrop) y = sm.xs[rank];
+                else {
+                    // the queue as the last packet that reached it left it (:74: a random drop does not touch it)
+                    double qp = q;
+                    if (rank > 0) {
+                        const double yp = sm.xs[rank - 1];
+                        qp = (yp > 0.0) ? ((yp > s.w_full) ? yp : s.d_bw + yp) : k0;
+                    }
+                    const double tuk = before ? sm.ts[b][63 - __clzll((long long)before)] : tu;
+                    y = qp - (tk[u] - tuk);
+                }
+                const bool pos = y > 0.0;
+                const double w = pos ? y : 0.0;                           // max(0.0, y)
+                const bool full = pos ? (y > s.w_full) : full0;
+                const bool dropped = rdrop || full;
+                const double ll = s.dl + w;                               // :69-70
+                Rec r;
+                r.a = tk[u] + ll;
+                r.l = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
+                ring.store(tail + (uint32_t)k, r);
+            }
+        }
+        double tu_n = tu, t_n = t;
+        if (work) {
+            if (ndm) tu_n = sm.ts[b][63 - __clzll((long long)ndm)];
+            t_n = sm.ts[b][cnt];
+        }
+        const double qs = g.bcast(state, 0);
+        __syncwarp();                                          // all reads of ts[b] / xs are done
+#pragma unroll
+        for (int u = 0; u < PPL; u++) sm.ts[b][1 + (int)g.gl + u * G] = neg_rate;   // the timer's array of the chunk after next
+        if (work) { q = qs; tu = tu_n; t = t_n; tail += (uint32_t)cnt; draws += (uint64_t)cnt; sent += cnt; }
+        more = next;
+        b ^= 1;
+        __syncwarp();
+    }
+    qd = q; t_upd = tu;
+    __syncwarp();   // record stores above are read by other lanes below
+}
+
 // One monitor interval.  Every lane of a group holds the same EnvState copy on entry and on
 // exit.  `alive` = this group has an env (warp-uniform control flow needs all lanes present).
 // On exit, if out.acked <= PCC_LEAF, sm.buf[0..out.acked) holds the MI's samples in order.
@@ -229,10 +415,12 @@ __device__ __forceinline__ void coop_send_chunks(const Grp<G> &g, bool alive, co
 #else
 #define PCC_TICK(k)
 #endif
-template <int G, class Ring>
+// `gbuf` (optional): global staging of ALL acked latencies of the MI (capacity gcap samples per group), read back by
+// means_groups_from_buf when there are more than one numpy leaf of them.
+template <int G, class Ring, class SM>
 __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvState &s, Ring &ring, uint64_t seed,
-                                            uint64_t &draws, double dur, GroupSmem<G> &sm, MiOut &out,
-                                            long long *prof = nullptr)
+                                            uint64_t &draws, double dur, SM &sm, MiOut &out,
+                                            long long *prof = nullptr, double *gbuf = nullptr, int gcap = 0)
 {
     PCC_TICK(0);
     const double end = s.cur_time + dur;            // network_sim.py:124
@@ -247,19 +435,22 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
     uint32_t tail = s.tail, h1 = s.h1, h2 = s.h2;
     bool ovf = false;
 
-    // pull the lines the two cursors will walk into L1 while the send phase runs
+    // pull the lines the two cursors will walk first into L2 while the send phase runs
     if (alive) {
         const uint32_t pend1 = tail - h1, pend2 = tail - h2;   // records pending per stream
 #pragma unroll
         for (int w = 0; w < 2; w++) {
             const uint32_t o = (uint32_t)((w * G + (int)g.gl) * 8);
-            if (o < pend1) prefetch_l1(ring.addr(h1 + o));
-            if (o < pend2) prefetch_l1(ring.addr(h2 + o));
+            if (o < pend1) prefetch_l2_line(ring.addr(h1 + o));
+            if (o < pend2) prefetch_l2_line(ring.addr(h2 + o));
         }
     }
 
     // ---- (1) sends with t < end: chain on lane 0, loss draws from all lanes ---------------
-    coop_send_chunks(g, alive, s, ring, seed, draws, end, inv_rate, sm.stage, t, qd, t_upd, tail, h2, sent, ovf);
+    if constexpr (SM::kSendV2)
+        group_send_chunks(g, alive, s, ring, seed, draws, end, inv_rate, sm.send, t, qd, t_upd, tail, h2, sent, ovf);
+    else
+        coop_send_chunks(g, alive, s, ring, seed, draws, end, inv_rate, sm.stage, t, qd, t_upd, tail, h2, sent, ovf);
     PCC_TICK(1);
 
     // ---- (2) hop-1 events with a < end ------------------------------------------------------
@@ -267,6 +458,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
         bool scanning = alive;
         while (__any_sync(PCC_FULL, scanning)) {
             unsigned bm[PCC_SCAN_W];
+            scan_prefetch(g, ring, h1, tail, scanning);
 #pragma unroll
             for (int w = 0; w < PCC_SCAN_W; w++) {
                 bool valid;
@@ -316,6 +508,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
         while (__any_sync(PCC_FULL, scanning)) {
             unsigned bm[PCC_SCAN_W], am[PCC_SCAN_W], lm[PCC_SCAN_W], lv[PCC_SCAN_W];
             double l2[PCC_SCAN_W];
+            scan_prefetch(g, ring, h2, tail, scanning);
 #pragma unroll
             for (int w = 0; w < PCC_SCAN_W; w++) {
                 bool valid;
@@ -342,6 +535,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
                 if ((a_w >> g.gl) & 1u) {
                     const int pos = acked + __popc(a_w & Grp<G>::lowmask((int)g.gl));
                     if (pos < PCC_LEAF) sm.buf[pos] = l2[w];
+                    if (gbuf != nullptr && pos < gcap) gbuf[pos] = l2[w];
                 }
                 if (on) {
                     acked += __popc(a_w);
@@ -426,6 +620,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
     }
     // the one possible out-of-order sample is the MI's last sample
     if (out.has_extra && acked <= PCC_LEAF && g.gl == 0) sm.buf[acked - 1] = out.extra;
+    if (out.has_extra && gbuf != nullptr && acked <= gcap && g.gl == 0) gbuf[acked - 1] = out.extra;
     __syncwarp();   // orders this MI's flag stores / staging writes before later reads
     s.next_send = t;
     s.qd = qd; s.t_upd = t_upd;
@@ -558,15 +753,95 @@ __device__ __noinline__ double coop_pw_sum(const Grp<G> &g, CoopSamples<G, Ring,
     }
 }
 
-// avg latency (sender_obs.py:119-122) and latency increase (:138-142) of the MI
-template <int G, class Ring>
-__device__ __forceinline__ void mi_means_coop(const Grp<G> &g, bool alive, const MiOut &o, Ring &ring, double dl,
-                                              GroupSmem<G> &sm, bool need_increase, double &avg_lat,
-                                              double &lat_increase)
+// np.mean of n > 128 staged samples a[0..n) per group, the groups of the warp in lock step: every group walks the
+// leaves of numpy's recursion in order (PwStream's descend / leaf_done with the leaf result supplied from outside), a leaf
+// is summed by 8 lanes = numpy's 8 accumulators + the xor-shuffle tree; three walks per group (all, first half, second
+// half).  Warp-uniform call; `on` selects the groups that take part.
+struct NoAcc { __device__ __forceinline__ double get(int) const { return 0.0; } __device__ __forceinline__ void set(int, double) {} };
+struct LocalPwStack {
+    int *right_n; double *left_sum;
+    __device__ __forceinline__ int &rn(int i) { return right_n[i]; }
+    __device__ __forceinline__ double &ls(int i) { return left_sum[i]; }
+};
+template <int G>
+__device__ __noinline__ void means_groups_from_buf(const Grp<G> &g, bool on, const double *a, int n, bool need_increase,
+                                                   double &avg_lat, double &lat_increase)
 {
-    const int n = alive ? o.acked : 0;
+    static_assert(G >= 8, "8 lanes hold numpy's 8 accumulators");
+    const int half = n / 2;
+    const int njobs = on ? ((need_increase && half >= 1) ? 3 : 1) : 0;
+    int rn[PCC_PW_STACK];
+    double ls[PCC_PW_STACK];
+    PwStream<NoAcc, LocalPwStack> m;
+    m.stk.right_n = rn; m.stk.left_sum = ls;
+    int job = 0, joff = 0, consumed = 0;
+    double sum0 = 0.0, sum1 = 0.0, sum2 = 0.0;
+    bool active = njobs > 0;
+    m.begin(active ? n : 0);
+    const int j = (int)(g.gl & 7u);
+    while (__any_sync(PCC_FULL, active)) {
+        const int c = active ? m.cur : 0;
+        const double *p = a + joff + consumed;
+        const int nb = c - (c % 8);
+        int nbmax = nb;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(PCC_FULL, nbmax, o); nbmax = v > nbmax ? v : nbmax; }
+        double r = 0.0;
+        if (c >= 8) r = p[j];
+#pragma unroll 8
+        for (int k = 8; k < nbmax; k += 8)
+            if (k < nb) r += p[k + j];
+        r += __shfl_xor_sync(PCC_FULL, r, 1);    // (r0+r1) (r2+r3) (r4+r5) (r6+r7)
+        r += __shfl_xor_sync(PCC_FULL, r, 2);    // ((r0+r1)+(r2+r3)) ((r4+r5)+(r6+r7))
+        r += __shfl_xor_sync(PCC_FULL, r, 4);
+        if (G > 8) r = g.bcast(r, 0);
+        double res;
+        if (c >= 8) { res = r; for (int k = nb; k < c; k++) res += p[k]; }
+        else { res = 0.; for (int k = 0; k < c; k++) res += p[k]; }
+        if (active) {
+            consumed += c;
+            m.res = res;
+            m.leaf_done();
+            if (m.done) {
+                if (job == 0) sum0 = m.total; else if (job == 1) sum1 = m.total; else sum2 = m.total;
+                job++;
+                if (job < njobs) {
+                    joff = (job == 2) ? half : 0;
+                    consumed = 0;
+                    m.begin(job == 1 ? half : n - half);
+                } else active = false;
+            }
+        }
+    }
+    if (on) {
+        double sum = 0.0;
+        sum += sum0;
+        avg_lat = sum / (double)n;                                              // sender_obs.py:119-122
+        lat_increase = 0.0;
+        if (njobs == 3) {                                                       // :138-142
+            double s1 = 0.0, s2 = 0.0;
+            s1 += sum1;
+            s2 += sum2;
+            lat_increase = s2 / (double)(n - half) - s1 / (double)half;
+        }
+    }
+    __syncwarp();
+}
+
+// avg latency (sender_obs.py:119-122) and latency increase (:138-142) of the MI
+template <int G, class Ring, class SM>
+__device__ __forceinline__ void mi_means_coop(const Grp<G> &g, bool alive, const MiOut &o, Ring &ring, double dl,
+                                              SM &sm, bool need_increase, double &avg_lat,
+                                              double &lat_increase, const double *gbuf = nullptr, int gcap = 0)
+{
+    int n = alive ? o.acked : 0;
     avg_lat = 0.0;
     lat_increase = 0.0;
+    if (gbuf != nullptr) {   // warp-uniform: staged samples of MIs with more than one leaf
+        const bool use_g = n > PCC_LEAF && n <= gcap;
+        if (__any_sync(PCC_FULL, use_g)) means_groups_from_buf(g, use_g, gbuf, n, need_increase, avg_lat, lat_increase);
+        if (use_g) n = 0;    // done
+    }
     const int half = n / 2;
     if (n > 0 && n <= PCC_LEAF) {
         // common case: run_mi_coop left all n samples in sm.buf

@@ -103,6 +103,17 @@ PCC_HD double res53(uint32_t a, uint32_t b)
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// The loss draw `random.random() < lr` (network_sim.py:73) without the int -> double conversions:
+// u = res53(a, b) = k * 2^-53 with the integer k = (a >> 5) * 2^26 + (b >> 6), and k * 2^-53 < lr  <=>  k < ceil(lr * 2^53)
+// (scaling by 2^53 is exact, k is an integer).  lr <= 0 or NaN: never; lr >= 1: always.
+PCC_HD uint64_t loss_threshold(double lr)
+{
+    if (!(lr > 0.0)) return 0ull;
+    if (lr >= 1.0) return 1ull << 53;
+    return (uint64_t)ceil(lr * 9007199254740992.0);
+}
+PCC_HD uint64_t u53(uint32_t a, uint32_t b) { return ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6); }
+
 #define PCC_PHILOX_DOMAIN 0x50434352u
 #if defined(__CUDA_ARCH__) && defined(PCC_PHILOX_NOINLINE)
 __device__ __noinline__
@@ -288,6 +299,64 @@ PCC_HD uint32_t scan_hop2(Ring &ring, uint32_t i, uint32_t tail, uint32_t h1, do
     return i;
 }
 
+// The smallest pending event of a stream at an MI boundary, in the reference's tuple order.
+struct Pending {
+    bool has;
+    uint32_t idx;      // ring position of the record
+    double t, l;       // event time; latency carried by the event (hop 1: ll, hop 2: ll + dl)
+    bool dropped;
+};
+
+// MI boundary of the hop-1 stream (network_sim.py:129 pops in tuple order): the cluster that starts at the
+// cursor -- a run of dropped packets plus the accepted packet that ends it -- is the only place where ring
+// order and time order can differ.  Members with a < end are consumed out of order (flagged), the rest
+// compete for the crossing event by (a, l, dropped).
+template <class Ring>
+PCC_HD void boundary_hop1(Ring &ring, uint32_t h1, uint32_t tail, double end, Pending &m)
+{
+    m.has = false; m.idx = 0; m.t = 0.0; m.l = 0.0; m.dropped = false;
+    for (uint32_t k = h1; k != tail; k++) {
+        Rec r = ring.load(k);
+        bool dr = sgn(r.l);
+        if (!sgn(r.a)) {
+            if (r.a < end) {
+                ring.store_a(k, negd(r.a));          // straggler: consume out of order
+            } else {
+                double l = absd(r.l);
+                bool less = !m.has || r.a < m.t || (r.a == m.t && (l < m.l || (l == m.l && !dr && m.dropped)));
+                if (less) { m.has = true; m.idx = k; m.t = r.a; m.l = l; m.dropped = dr; }
+            }
+        }
+        if (!dr) break;                              // accepted packet closes the cluster
+    }
+}
+
+// MI boundary of the hop-2 stream; call only when the record at h2 carries a live hop-2 event (at_live).
+template <class Ring>
+PCC_HD void boundary_hop2(Ring &ring, uint32_t h1, uint32_t h2, uint32_t tail, double dl, double end,
+                          int32_t &acked, int32_t &lost, double &extra, bool &has_extra, Pending &m)
+{
+    m.has = false; m.idx = 0; m.t = 0.0; m.l = 0.0; m.dropped = false;
+    for (uint32_t k = h2; k != tail; k++) {
+        Rec r = ring.load(k);
+        bool dr = sgn(r.l);
+        if (!is_dead(r.a)) {
+            bool c1 = ((int32_t)(k - h1) < 0) || sgn(r.a);
+            if (!c1) break;                      // later hop-2 events are >= end + dl
+            double b = absd(r.a) + dl;
+            double l2 = absd(r.l) + dl;
+            if (b < end) {                       // straggler
+                if (dr) lost++; else { acked++; extra = l2; has_extra = true; }
+                ring.store_a(k, u2d(PCC_NEG_INF));
+            } else {
+                bool less = !m.has || b < m.t || (b == m.t && (l2 < m.l || (l2 == m.l && !dr && m.dropped)));
+                if (less) { m.has = true; m.idx = k; m.t = b; m.l = l2; m.dropped = dr; }
+            }
+        }
+        if (!dr) break;
+    }
+}
+
 // `prescan`: run the two in-order cursor scans once BEFORE the sends, over the records that already exist, and let
 // phases (2) and (3) continue from there.  Both scans are prefix scans that stop at the first record they cannot
 // consume and neither writes the ring, so the result is the same as without -- this is the scalar statement of what
@@ -347,48 +416,18 @@ PCC_HD void run_mi(EnvState &s, Ring &ring, Rng &rng, double dur, MiOut &out, bo
     // ---- (2) hop-1 events with a < end ------------------------------------------------
     h1 = scan_hop1(ring, h1, tail, end);
     // boundary cluster: stragglers + the smallest pending key (a, l, dropped)
-    bool has1 = false;
-    uint32_t m1 = 0; double m1a = 0.0, m1l = 0.0; bool m1d = false;
-    for (uint32_t k = h1; k != tail; k++) {
-        Rec r = ring.load(k);
-        bool dr = sgn(r.l);
-        if (!sgn(r.a)) {
-            if (r.a < end) {
-                ring.store_a(k, negd(r.a));          // straggler: consume out of order
-            } else {
-                double l = absd(r.l);
-                bool less = !has1 || r.a < m1a || (r.a == m1a && (l < m1l || (l == m1l && !dr && m1d)));
-                if (less) { has1 = true; m1 = k; m1a = r.a; m1l = l; m1d = dr; }
-            }
-        }
-        if (!dr) break;                              // accepted packet closes the cluster
-    }
+    Pending m1;
+    boundary_hop1(ring, h1, tail, end, m1);
 
     // ---- (3) hop-2 events with b < end ------------------------------------------------
     h2 = scan_hop2(ring, h2, tail, h1, s.dl, end, acked, lost, at_live);
     out.s_end = h2;
-    bool has2 = false;
-    uint32_t m2 = 0; double m2b = 0.0, m2l = 0.0; bool m2d = false;
-    if (at_live) {
-        for (uint32_t k = h2; k != tail; k++) {
-            Rec r = ring.load(k);
-            bool dr = sgn(r.l);
-            if (!is_dead(r.a)) {
-                bool c1 = ((int32_t)(k - h1) < 0) || sgn(r.a);
-                if (!c1) break;                      // later hop-2 events are >= end + dl
-                double b = absd(r.a) + s.dl;
-                double l2 = absd(r.l) + s.dl;
-                if (b < end) {                       // straggler
-                    if (dr) lost++; else { acked++; out.extra = l2; out.has_extra = true; }
-                    ring.store_a(k, u2d(PCC_NEG_INF));
-                } else {
-                    bool less = !has2 || b < m2b || (b == m2b && (l2 < m2l || (l2 == m2l && !dr && m2d)));
-                    if (less) { has2 = true; m2 = k; m2b = b; m2l = l2; m2d = dr; }
-                }
-            }
-            if (!dr) break;
-        }
-    }
+    Pending m2;
+    m2.has = false; m2.idx = 0; m2.t = 0.0; m2.l = 0.0; m2.dropped = false;
+    if (at_live) boundary_hop2(ring, h1, h2, tail, s.dl, end, acked, lost, out.extra, out.has_extra, m2);
+    const bool has1 = m1.has, has2 = m2.has, m2d = m2.dropped;
+    const uint32_t m1i = m1.idx, m2i = m2.idx;
+    const double m1a = m1.t, m2b = m2.t, m2l = m2.l;
 
     // ---- (4) the event that crosses `end` ----------------------------------------------
     // candidates: pacing timer (t, 'S'), hop-1 (m1a, 'A', hop 1), hop-2 (m2b, 'A', hop 2)
@@ -402,11 +441,11 @@ PCC_HD void run_mi(EnvState &s, Ring &ring, Rng &rng, double dur, MiOut &out, bo
         PCC_SEND_ONE();
     } else if (which == 1) {
         s.cur_time = m1a;
-        if (m1 == h1) h1++; else ring.store_a(m1, negd(m1a));
+        if (m1i == h1) h1++; else ring.store_a(m1i, negd(m1a));
     } else {
         s.cur_time = m2b;
         if (m2d) lost++; else { acked++; out.extra = m2l; out.has_extra = true; }
-        if (m2 == h2) h2++; else ring.store_a(m2, u2d(PCC_NEG_INF));
+        if (m2i == h2) h2++; else ring.store_a(m2i, u2d(PCC_NEG_INF));
     }
 #undef PCC_SEND_ONE
     s.next_send = t;
@@ -488,6 +527,74 @@ PCC_HD double pw_sum(Reader &rd, int n)
         }
     }
 }
+
+// The same pairwise sum in PUSH form: the number of samples n is known in advance, the samples arrive one at a
+// time (the lane-per-env kernels read them tile by tile and cannot hand a pull-style reader to pw_sum).  The walk of
+// numpy's recursion is pw_sum's, turned inside out: `descend` opens the leftmost leaf of a subtree, `push` feeds the
+// current leaf (8 accumulators r[k % 8], the combination tree when the last full block of 8 is in, then the tail
+// sequentially), `leaf_done` folds finished subtrees.  Storage is a policy so that the scalar state stays in registers
+// on the GPU: `Acc` holds the 8 accumulators (double get(int), void set(int, double): a shared-memory column per
+// lane), `Stk` the recursion stack (int &rn(int), double &ls(int): caller-owned arrays, touched once per leaf).
+struct PwHostStack {
+    int right_n[PCC_PW_STACK]; double left_sum[PCC_PW_STACK];
+    PCC_HD int &rn(int i) { return right_n[i]; }
+    PCC_HD double &ls(int i) { return left_sum[i]; }
+};
+template <class Acc, class Stk = PwHostStack>
+struct PwStream {
+    Acc acc;
+    Stk stk;
+    int cur, k, nb;          // current leaf: size, samples consumed, size rounded down to a multiple of 8 (0 if < 8)
+    double res, total;
+    int sp;
+    uint32_t have_left;      // bit i: stack level i already holds its left sum
+    bool done;
+
+    PCC_HD void descend(int m)
+    {
+        while (m > 128) {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            stk.rn(sp) = m - n2; have_left &= ~(1u << sp); sp++;
+            m = n2;
+        }
+        cur = m; k = 0; nb = (m >= 8) ? m - (m % 8) : 0; res = 0.;
+    }
+    PCC_HD void begin(int n)
+    {
+        sp = 0; have_left = 0u; total = 0.0; res = 0.; cur = 0; k = 0; nb = 0;
+        done = n <= 0;
+        if (n > 0) descend(n);
+    }
+    PCC_HD void leaf_done()
+    {
+        double r = res;
+        for (;;) {
+            if (sp == 0) { total = r; done = true; return; }
+            if (!((have_left >> (sp - 1)) & 1u)) {
+                stk.ls(sp - 1) = r; have_left |= 1u << (sp - 1);
+                descend(stk.rn(sp - 1));             // the right sibling's leftmost leaf
+                return;
+            }
+            r = stk.ls(sp - 1) + r;
+            sp--;
+        }
+    }
+    PCC_HD void push(double x)
+    {
+        if (k < nb) {
+            const int j = k & 7;
+            if (k < 8) acc.set(j, x); else acc.set(j, acc.get(j) + x);
+            k++;
+            if (k == nb)
+                res = ((acc.get(0) + acc.get(1)) + (acc.get(2) + acc.get(3))) +
+                      ((acc.get(4) + acc.get(5)) + (acc.get(6) + acc.get(7)));
+        } else { res += x; k++; }
+        if (k == cur) leaf_done();
+    }
+    // np.mean of the n samples pushed: (0.0 + pairwise) / n
+    PCC_HD double mean(int n) const { double s = 0.0; s += total; return s / (double)n; }
+};
 
 // np.mean of the next n samples: (0.0 + pairwise) / n
 template <class Reader>

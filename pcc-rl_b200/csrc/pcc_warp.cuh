@@ -32,8 +32,9 @@ struct LeafScratch {
     int off[PCC_MAX_LEAVES];
     int cnt[PCC_MAX_LEAVES];
 };
-// ... followed by 65 (+1 pad) double2 of record staging for the single-env send phase (coop_send_chunks<32>)
-__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch) + 66 * 16; }
+// ... followed by the shared memory of the single-env send phase (SoloSendSmem; coop_send_chunks<32>: 66 double2)
+#define PCC_SEND_SMEM_BYTES ((sizeof(SoloSendSmem) > 66 * 16 ? sizeof(SoloSendSmem) : 66 * 16) + 15 & ~(size_t)15)
+__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch) + PCC_SEND_SMEM_BYTES; }
 
 struct ConsumeIn {
     double end, dl, tnext;
@@ -134,6 +135,7 @@ __device__ __forceinline__ void consume_scan_warp(const Grp<32> &g, double end, 
     int32_t acked = 0, lost = 0;
     for (;;) {
         unsigned bm[PCC_SCAN_W];
+        scan_prefetch(g, ring, h1, tail, true);
 #pragma unroll
         for (int w = 0; w < PCC_SCAN_W; w++) {
             bool valid;
@@ -154,6 +156,7 @@ __device__ __forceinline__ void consume_scan_warp(const Grp<32> &g, double end, 
     for (;;) {
         unsigned bm[PCC_SCAN_W], am[PCC_SCAN_W], lm[PCC_SCAN_W];
         double l2[PCC_SCAN_W];
+        scan_prefetch(g, ring, h2, tail, true);
 #pragma unroll
         for (int w = 0; w < PCC_SCAN_W; w++) {
             bool valid;
@@ -209,6 +212,7 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
     // ---- hop-1 events with a < end ----------------------------------------------------------
     for (;;) {
         unsigned bm[PCC_SCAN_W];
+        scan_prefetch(g, ring, h1, tail, true);
 #pragma unroll
         for (int w = 0; w < PCC_SCAN_W; w++) {
             bool valid;
@@ -240,6 +244,7 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
     for (;;) {
         unsigned bm[PCC_SCAN_W], am[PCC_SCAN_W], lm[PCC_SCAN_W];
         double l2[PCC_SCAN_W];
+        scan_prefetch(g, ring, h2, tail, true);
 #pragma unroll
         for (int w = 0; w < PCC_SCAN_W; w++) {
             bool valid;

@@ -159,3 +159,46 @@ def test_tail_drop_threshold_is_exact():
         for w in cands:
             assert (d_bw + w > max_qd) == (w > wf), (bw, queue, w, wf)
     assert L.twin_tail_drop_threshold(1.0, 0.5) == -1.0   # never admissible: every packet is tail-dropped
+
+
+def test_pw_stream_push_form_equals_pull_form():
+    """PwStream (the push-style pairwise sum of the lane-per-env kernels) == np_mean_stream / pw_sum (pinned to numpy
+    by tests/test_oracle_golden.py) for every sample count 1..3000: total, first half and second half."""
+    import ctypes as C
+    import twin_util
+    L = twin_util.lib()
+    L.twin_pw_stream_mismatches.argtypes = [C.POINTER(C.c_double), C.c_int]
+    rng = np.random.default_rng(5)
+    for scale in (1.0, 1e-3):
+        a = np.ascontiguousarray(rng.uniform(0.05, 1.3, 3000) * scale)
+        assert L.twin_pw_stream_mismatches(a.ctypes.data_as(C.POINTER(C.c_double)), 3000) == 0
+    # and against numpy itself
+    a = rng.uniform(0.05, 1.3, 20000)
+    for n in (1, 7, 8, 9, 127, 128, 129, 255, 256, 257, 1000, 4097, 20000):
+        assert L.twin_pw_stream_mismatches(a.ctypes.data_as(C.POINTER(C.c_double)), n) == 0
+
+
+def test_integer_loss_draw_equals_double_compare():
+    """loss_threshold / u53 (the integer form of `random.random() < lr` used by the packed kernels): same decision as
+    the binary64 compare for random and adversarial loss rates, incl. draws that land exactly on / next to the rate."""
+    import ctypes as C
+    import twin_util
+    L = twin_util.lib()
+    L.twin_loss_threshold_mismatches.restype = C.c_long
+    L.twin_loss_threshold_mismatches.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_uint32),
+                                                 C.POINTER(C.c_uint32), C.c_int]
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 2**32, 4000, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2**32, 4000, dtype=np.uint64).astype(np.uint32)
+    # draws equal to, just below and just above a handful of rates
+    k = rng.integers(0, 2**53, 200, dtype=np.uint64)
+    exact = (k.astype(np.float64) / 2.0**53)        # exact: k < 2^53
+    lr = np.concatenate([rng.uniform(0, 0.05, 300), rng.uniform(0, 1, 100), exact, np.nextafter(exact, 0), np.nextafter(exact, 1),
+                         [0.0, -0.0, -1.0, 1.0, 1.5, np.nan, 5e-324, 2.0**-53, 2.0**-54, 1 - 2.0**-53, 0.5]])
+    a2 = np.concatenate([a, (k >> np.uint64(26)).astype(np.uint32) << np.uint32(5)])
+    b2 = np.concatenate([b, (k & np.uint64((1 << 26) - 1)).astype(np.uint32) << np.uint32(6)])
+    lr = np.ascontiguousarray(lr)
+    bad = L.twin_loss_threshold_mismatches(lr.ctypes.data_as(C.POINTER(C.c_double)), len(lr),
+                                           np.ascontiguousarray(a2).ctypes.data_as(C.POINTER(C.c_uint32)),
+                                           np.ascontiguousarray(b2).ctypes.data_as(C.POINTER(C.c_uint32)), len(a2))
+    assert bad == 0

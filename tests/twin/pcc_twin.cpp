@@ -98,6 +98,50 @@ int twin_overflow(Twin *t) { return t->overflow; }
 uint32_t twin_inflight(Twin *t) { return t->s.tail - t->s.h2; }
 }
 
+// PwStream (push-style pairwise sum) against pw_sum (pull-style, the one the oracle tests pin to numpy): returns the
+// number of prefix lengths n in [1, n_max] whose total / first-half / second-half means differ in any bit.
+struct ArrReader { const double *a; int i; double next() { return a[i++]; } };
+struct ArrAcc { double r[8]; double get(int j) const { return r[j]; } void set(int j, double v) { r[j] = v; } };
+extern "C" int twin_pw_stream_mismatches(const double *a, int n_max)
+{
+    int bad = 0;
+    for (int n = 1; n <= n_max; n++) {
+        const int half = n / 2;
+        ArrReader r0{a, 0};
+        const double m_all = np_mean_stream(r0, n);
+        double m_lo = 0.0, m_hi = 0.0;
+        if (half >= 1) { ArrReader r1{a, 0}; m_lo = np_mean_stream(r1, half); m_hi = np_mean_stream(r1, n - half); }
+        PwStream<ArrAcc> t, h;
+        t.begin(n); h.begin(half >= 1 ? half : 0);
+        double s_lo = 0.0, s_hi = 0.0;
+        for (int i = 0; i < n; i++) {
+            t.push(a[i]);
+            if (half >= 1) {
+                if (i == half) { s_lo = h.mean(half); h.begin(n - half); }
+                h.push(a[i]);
+            }
+        }
+        if (half >= 1) s_hi = h.mean(n - half);
+        if (!t.done || (half >= 1 && !h.done)) { bad++; continue; }
+        const double tm = t.mean(n);
+        if (memcmp(&m_all, &tm, 8) != 0) bad++;
+        else if (half >= 1 && (memcmp(&m_lo, &s_lo, 8) != 0 || memcmp(&m_hi, &s_hi, 8) != 0)) bad++;
+    }
+    return bad;
+}
+
+// integer form of the loss draw against the double form, for loss rates `lr[i]` and word pairs (a[j], b[j])
+extern "C" long twin_loss_threshold_mismatches(const double *lr, int n_lr, const uint32_t *a, const uint32_t *b, int n_w)
+{
+    long bad = 0;
+    for (int i = 0; i < n_lr; i++) {
+        const uint64_t thr = loss_threshold(lr[i]);
+        for (int j = 0; j < n_w; j++)
+            if ((res53(a[j], b[j]) < lr[i]) != (u53(a[j], b[j]) < thr)) bad++;
+    }
+    return bad;
+}
+
 extern "C" double twin_tail_drop_threshold(double d_bw, double max_qd) { return pcc::tail_drop_threshold(d_bw, max_qd); }
 
 // ---- several senders on one bottleneck (pcc_multi_core.cuh), host build -------------------------------------
