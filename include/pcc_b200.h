@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PCC_ABI_VERSION 1
+#define PCC_ABI_VERSION 2
 
 /* error codes */
 #define PCC_OK 0
@@ -161,7 +161,8 @@ int pcc_step_host(pcc_handle h, const double *actions_host, double *obs_host, do
                   uint8_t *done_host, int32_t *counts_host, void *stream);
 
 /* On-device policy for pcc_rollout: the MLP of stable_solve.py:30-45 (obs -> h1 -> h2 -> 1, tanh hidden
- * layers, linear output = mean of the Gaussian action).  All pointers are device pointers to binary64,
+ * layers, linear output = mean of the Gaussian action) and, optionally, the value network of the same shape that
+ * PPO1 trains beside it (MlpPolicy: vf head; vw1 == NULL = none).  All pointers are device pointers to binary64,
  * row-major [out][in].  stochastic != 0 adds exp(log_std) * N(0,1) drawn from a Philox stream keyed by
  * (noise_seed; env, step). */
 typedef struct pcc_policy {
@@ -169,21 +170,26 @@ typedef struct pcc_policy {
     int32_t n_in, h1, h2, stochastic;
     double log_std;
     uint64_t noise_seed;
+    const double *vw1, *vb1, *vw2, *vb2, *vw3, *vb3;
 } pcc_policy;
 
-/* Fused rollout: n_steps monitor intervals for every env in ONE launch (what PPO1's
- * traj_segment_generator does around SimulatedNetworkEnv.step, stable_solve.py:52-58).  Each step is
- * exactly pcc_step followed, for finished envs, by pcc_reset with the next row of the parameter bank.
- *   actions_dev       double[n_steps][n_envs], or NULL to use `policy`
+/* Rollout: n_steps monitor intervals for every env without returning to the host -- what PPO1's
+ * traj_segment_generator does around SimulatedNetworkEnv.step (stable_solve.py:52-58: ob, ac, vpred, rew, new per
+ * step plus nextvpred).  Per step, enqueued back to back on `stream`: the policy / value kernel on the current
+ * observation, exactly pcc_step, and for finished envs exactly pcc_reset with the next row of the parameter bank.
+ *   actions_dev       double[n_steps][n_envs], or NULL to use `policy` (then actions_out_dev is required)
  *   reset_params_dev  double[n_episodes][5][n_envs]: bw, delay, queue, loss, start_rate of the
- *                     episodes each env starts DURING this rollout, in order (row 0 = its first reset)
+ *                     episodes each env starts DURING this rollout, in order (row 0 = its first reset);
+ *                     n_episodes == 0: no auto-reset
  *   obs_dev           double[n_steps][n_envs][history_len*n_features]  (optional) observation AFTER the
  *                     step -- for a finished env the first observation of its next episode
- *   actions_out_dev   double[n_steps][n_envs] (optional) the actions taken
- *   reward_dev, done_dev, counts_dev   [n_steps][n_envs] (counts optional, [..][3]) */
+ *   actions_out_dev   double[n_steps][n_envs] (optional with actions_dev) the actions taken
+ *   reward_dev, done_dev, counts_dev   [n_steps][n_envs] (counts optional, [..][3])
+ *   vpred_dev         double[n_steps + 1][n_envs] (optional, needs policy->vw1): row k = V(observation BEFORE step k),
+ *                     row n_steps = V(observation after the last step) */
 int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const pcc_policy *policy,
                 const double *reset_params_dev, int32_t n_episodes, double *obs_dev, double *actions_out_dev,
-                double *reward_dev, uint8_t *done_dev, int32_t *counts_dev, void *stream);
+                double *reward_dev, uint8_t *done_dev, int32_t *counts_dev, double *vpred_dev, void *stream);
 
 /* Synchronises `stream` and reports sticky device-side errors (PCC_EOVERFLOW). */
 int pcc_check(pcc_handle h, void *stream);

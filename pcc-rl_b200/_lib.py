@@ -5,7 +5,7 @@ import os
 
 from . import build as _build
 
-PCC_ABI_VERSION = 1
+PCC_ABI_VERSION = 2
 PCC_OK, PCC_EINVAL, PCC_ECUDA, PCC_EOVERFLOW, PCC_ENODEV = 0, -1, -2, -3, -4
 PCC_RNG_MT19937, PCC_RNG_PHILOX = 0, 1
 PCC_MAX_FEATURES = 12
@@ -27,7 +27,9 @@ class PccConfig(C.Structure):
 class PccPolicy(C.Structure):
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
                 ("w3", C.c_void_p), ("b3", C.c_void_p), ("n_in", C.c_int32), ("h1", C.c_int32),
-                ("h2", C.c_int32), ("stochastic", C.c_int32), ("log_std", C.c_double), ("noise_seed", C.c_uint64)]
+                ("h2", C.c_int32), ("stochastic", C.c_int32), ("log_std", C.c_double), ("noise_seed", C.c_uint64),
+                ("vw1", C.c_void_p), ("vb1", C.c_void_p), ("vw2", C.c_void_p), ("vb2", C.c_void_p),
+                ("vw3", C.c_void_p), ("vb3", C.c_void_p)]
 
 
 class PccVariant(C.Structure):
@@ -112,7 +114,7 @@ def load(rebuild_if_stale=True):
     L.pcc_reset.argtypes = [vp, u8p, dp, dp, vp, dp, dp, dp, vp]
     L.pcc_step.argtypes = [vp, dp, dp, dp, u8p, vp, dp, vp]
     L.pcc_step_host.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
-    L.pcc_rollout.argtypes = [vp, C.c_int32, dp, C.POINTER(PccPolicy), dp, C.c_int32, dp, dp, dp, u8p, vp, vp]
+    L.pcc_rollout.argtypes = [vp, C.c_int32, dp, C.POINTER(PccPolicy), dp, C.c_int32, dp, dp, dp, u8p, vp, dp, vp]
     L.pcc_check.argtypes = [vp, vp]
     L.pcc_multi_workspace_bytes.argtypes = [C.POINTER(PccConfig), C.c_int32, C.POINTER(C.c_uint64)]
     L.pcc_multi_create.argtypes = [C.POINTER(vp), C.POINTER(PccConfig), C.c_int32, vp]

@@ -197,13 +197,15 @@ class PccBatchEnv(object):
         return self.obs, self.reward, done, info
 
     def rollout(self, n_steps, actions=None, policy=None, want_obs=True, want_counts=True):
-        """n_steps monitor intervals for every env in ONE kernel launch (fused rollout), with in-kernel
-        auto-reset.  Equivalent, bit for bit, to n_steps calls of step().
+        """n_steps monitor intervals for every env without returning to the host: per step the policy / value
+        kernel, the regular env step and the auto-reset of finished envs are enqueued back to back on the stream.
+        Equivalent, bit for bit, to n_steps calls of step().
 
         actions: [n_steps, n_envs] float64 cuda tensor, or None to use `policy` = dict(w1, b1, w2, b2, w3,
         b3: float64 cuda tensors of the MLP obs -> h1 -> h2 -> 1 with tanh hidden layers; log_std, stochastic,
-        noise_seed optional).  Returns dict(obs [K,N,H*F] (observation after each step), actions [K,N],
-        reward [K,N], done [K,N] bool, counts [K,N,3])."""
+        noise_seed optional; vw1 ... vb3 optional: the value network of the same shape).  Returns dict(obs [K,N,H*F]
+        (observation after each step), actions [K,N], reward [K,N], done [K,N] bool, counts [K,N,3], and with a value
+        head vpred [K+1,N]: V(observation before step k), last row = V(observation after the last step))."""
         torch = self.torch
         K, n = int(n_steps), self.n_envs
         # parameters of the episodes that START during this rollout (host bookkeeping is deterministic)
@@ -225,33 +227,41 @@ class PccBatchEnv(object):
                    actions=torch.empty((K, n), **f64))
         out["obs"] = torch.empty((K, n, self.obs_dim), **f64) if want_obs else None
         out["counts"] = torch.empty((K, n, 3), dtype=torch.int32, device=self.device) if want_counts else None
-        act_ptr, pol_ref, keep = None, None, []
+        act_ptr, pol_ref, keep, vpred = None, None, [], None
         if actions is not None:
             a = torch.as_tensor(actions).to(self.device, torch.float64).reshape(K, n).contiguous()
             keep.append(a)
             act_ptr = a.data_ptr()
-        else:
+        if policy is not None:
             pol = _lib.PccPolicy()
-            ws = {k: policy[k].to(self.device, torch.float64).contiguous() for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
+            names = ["w1", "b1", "w2", "b2", "w3", "b3"]
+            if "vw1" in policy:
+                names += ["vw1", "vb1", "vw2", "vb2", "vw3", "vb3"]
+                vpred = torch.empty((K + 1, n), **f64)
+            ws = {k: policy[k].to(self.device, torch.float64).contiguous() for k in names}
             keep.append(ws)
             for k, v in ws.items():
                 setattr(pol, k, v.data_ptr())
             pol.n_in, pol.h1, pol.h2 = ws["w1"].shape[1], ws["w1"].shape[0], ws["w2"].shape[0]
             assert ws["w2"].shape[1] == pol.h1 and ws["w3"].numel() == pol.h2 and pol.n_in == self.obs_dim
+            if vpred is not None:
+                assert ws["vw1"].shape == ws["w1"].shape and ws["vw2"].shape == ws["w2"].shape and ws["vw3"].numel() == pol.h2
             pol.log_std = float(policy.get("log_std", 0.0))
             pol.stochastic = int(bool(policy.get("stochastic", False)))
             pol.noise_seed = int(policy.get("noise_seed", 0)) & 0xFFFFFFFFFFFFFFFF
             pol_ref = C.byref(pol)
         p = lambda t: t.data_ptr() if t is not None else None
-        _lib.check(self.L.pcc_rollout(self.h, K, act_ptr, pol_ref, bank_dev.data_ptr(), n_eps, p(out["obs"]),
-                                      out["actions"].data_ptr(), out["reward"].data_ptr(), out["done"].data_ptr(),
-                                      p(out["counts"]), self._stream()))
+        _lib.check(self.L.pcc_rollout(self.h, K, act_ptr, pol_ref, bank_dev.data_ptr() if n_eps > 0 else None, n_eps,
+                                      p(out["obs"]), out["actions"].data_ptr(), out["reward"].data_ptr(),
+                                      out["done"].data_ptr(), p(out["counts"]), p(vpred), self._stream()))
         self._keep = (bank_dev, keep)
         self._steps = (self._steps + K) % self.max_steps
         self._episode += n_resets
         if want_obs:
             self.obs.copy_(out["obs"][K - 1])
         out["done"] = out["done"].bool()
+        if vpred is not None:
+            out["vpred"] = vpred
         return out
 
     def step_device(self, actions_f64):

@@ -720,7 +720,7 @@ __device__ __forceinline__ void packed_emit(const DevState &p, double *rowbuf, b
     const int slot_new = (int)(head_step % (unsigned long long)H);
     double *__restrict__ hist = p.hist;
     if (HF <= 32) {
-        // one lane per element of the row; the history reads of four envs are in flight before their stores
+        // one lane per element of the row; the history reads of eight envs are in flight before their stores
         const int k = (int)lane;
         const int h = k / F, f = k - h * F;
         int sl = slot_new + 1 + h;
@@ -728,18 +728,18 @@ __device__ __forceinline__ void packed_emit(const DevState &p, double *rowbuf, b
         const bool act = k < HF, isnew = act && (h == H - 1);
         const int src = isnew ? 0 : sl * F + f;
 #pragma unroll 1
-        for (int j0 = 0; j0 < 32; j0 += 4) {
-            if (!((om >> j0) & 0xFu)) continue;                                      // warp-uniform
-            double v[4];
-            long long ej[4];
+        for (int j0 = 0; j0 < 32; j0 += 8) {
+            if (!((om >> j0) & 0xFFu)) continue;                                     // warp-uniform
+            double v[8];
+            long long ej[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 ej[u] = __shfl_sync(PCC_FULL, (long long)e, j0 + u);
                 v[u] = 0.0;
                 if (((om >> (j0 + u)) & 1u) && act && !isnew) v[u] = hist[(size_t)ej[u] * HF + src];
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 if (!((om >> (j0 + u)) & 1u) || !act) continue;
                 if (isnew) {
                     v[u] = rowbuf[(j0 + u) * PCC_MAX_FEATURES + f];
@@ -1015,179 +1015,117 @@ __global__ void pcc_schedule_kernel(const uint32_t *__restrict__ sorted_keys, in
 }
 
 // ---------------------------------------------------------------------------------------
-// Fused rollout: K monitor intervals per launch.  Every warp keeps its envs
-// for the whole rollout -- state in registers, in-kernel auto-reset from a pre-sampled parameter
-// bank, optional on-device policy (the MLP of stable_solve.py:30-45) -- so there is no per-MI grid
-// barrier and the per-step imbalance between envs averages out over the K steps.
+// Rollout: K monitor intervals per call with the policy, the value head and the auto-reset on
+// the device -- what PPO1's traj_segment_generator does around SimulatedNetworkEnv.step (stable_solve.py:30-58).
+// Round 1 fused the K steps into ONE persistent kernel; its work partition was fixed for the whole call, went stale
+// and the kernel ended up slower than the K launches it replaced.  The rollout is now a device-side SEQUENCE per step
+// -- policy/value kernel, (re-sort +) the regular step kernel, bank gather + masked reset -- enqueued back to back on
+// the caller's stream: nothing returns to the host between steps, and every step gets the step kernel's own freshly
+// balanced partition.
 // ---------------------------------------------------------------------------------------
 struct PolicyDev {
     const double *w1, *b1, *w2, *b2, *w3, *b3;   // row-major [out][in]; null w1 = no policy
+    const double *vw1, *vb1, *vw2, *vb2, *vw3, *vb3;   // value head of the same shape; null vw1 = none
     int32_t n_in, h1, h2;
     double log_std;
     unsigned long long noise_seed;
     int32_t stochastic;
 };
-struct RolloutArgs {
-    int32_t K;
-    const double *actions;       // [K][n] or null
-    PolicyDev pol;
-    const double *bank;          // [n_episodes][5][n]: bw, delay, queue, loss, start_rate
-    int32_t n_episodes;
-    double *obs;                 // [K][n][H*F] or null
-    double *act_out;             // [K][n] or null
-    double *reward;              // [K][n]
-    uint8_t *done;               // [K][n]
-    int32_t *counts;             // [K][n][3] or null
-};
 
 #define PCC_POLICY_MAXH 64
-// action = MLP(obs) [+ exp(log_std) * N(0,1)]: tanh hidden layers, linear output (MlpPolicy of PPO1)
+// obs -> tanh(W1 obs + b1) -> tanh(W2 . + b2) -> w3 . + b3   (MlpPolicy of PPO1: two tanh layers, linear output)
+__device__ __noinline__ double mlp_eval(const double *w1, const double *b1, const double *w2, const double *b2,
+                                        const double *w3, const double *b3, int n_in, int h1, int h2, const double *obs_row)
+{
+    double a1[PCC_POLICY_MAXH], a2[PCC_POLICY_MAXH];
+    for (int i = 0; i < h1; i++) {
+        double acc = b1[i];
+        for (int j = 0; j < n_in; j++) acc += w1[i * n_in + j] * obs_row[j];
+        a1[i] = tanh(acc);
+    }
+    for (int i = 0; i < h2; i++) {
+        double acc = b2[i];
+        for (int j = 0; j < h1; j++) acc += w2[i * h1 + j] * a1[j];
+        a2[i] = tanh(acc);
+    }
+    double out = b3[0];
+    for (int j = 0; j < h2; j++) out += w3[j] * a2[j];
+    return out;
+}
+
+// deterministic action from a history ring (rows oldest -> newest starting at slot_oldest): the flow monitor's agent
 __device__ __noinline__ double policy_action(PolicyDev pol, const double *hrow, int slot_oldest, int H, int F, int64_t e,
                                              unsigned long long t)
 {
-    double a1[PCC_POLICY_MAXH], a2[PCC_POLICY_MAXH];
     double obs_row[128];
-    for (int h = 0; h < H; h++) {          // oldest -> newest
+    for (int h = 0; h < H; h++) {
         int sl = slot_oldest + h;
         if (sl >= H) sl -= H;
         for (int f = 0; f < F; f++) obs_row[h * F + f] = hrow[sl * F + f];
     }
-    for (int i = 0; i < pol.h1; i++) {
-        double acc = pol.b1[i];
-        for (int j = 0; j < pol.n_in; j++) acc += pol.w1[i * pol.n_in + j] * obs_row[j];
-        a1[i] = tanh(acc);
-    }
-    for (int i = 0; i < pol.h2; i++) {
-        double acc = pol.b2[i];
-        for (int j = 0; j < pol.h1; j++) acc += pol.w2[i * pol.h1 + j] * a1[j];
-        a2[i] = tanh(acc);
-    }
-    double out = pol.b3[0];
-    for (int j = 0; j < pol.h2; j++) out += pol.w3[j] * a2[j];
-    if (pol.stochastic) {   // Box-Muller on a Philox block keyed by (noise_seed; env, step)
-        uint32_t c0 = (uint32_t)e, c1 = (uint32_t)(e >> 32), c2 = (uint32_t)t, c3 = 0x4e4f4953u;   // 'NOIS'
-        philox4x32_10(c0, c1, c2, c3, (uint32_t)pol.noise_seed, (uint32_t)(pol.noise_seed >> 32));
-        const double u1 = (res53(c0, c1) + 1.1102230246251565e-16), u2 = res53(c2, c3);
-        out += exp(pol.log_std) * sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-    }
-    return out;
+    (void)e; (void)t;
+    return mlp_eval(pol.w1, pol.b1, pol.w2, pol.b2, pol.w3, pol.b3, pol.n_in, pol.h1, pol.h2, obs_row);
 }
 
-// in-kernel reset of the lanes in `need` (network_sim.py:469-484).  Inlined: passing the env state by
-// reference to an out-of-line function would pin it to the stack for the whole rollout loop.
-__device__ __forceinline__ void rollout_reset(const DevState &p, bool need, int cnt, int64_t e, EnvState &s, PhiloxRng &rng,
-                                              const double *bank, int ep, WarpStage &dummy, bool &ovf)
+// One thread per env: action = pi(obs) [+ exp(log_std) * N(0,1), Box-Muller on a Philox block keyed by (noise_seed;
+// env, step t)], vpred = V(obs).  obs rows are the current observations, oldest -> newest.
+__global__ void pcc_policy_kernel(PolicyDev pol, int64_t n, const double *__restrict__ obs, unsigned long long t,
+                                  double *__restrict__ act_out, double *__restrict__ vpred_out)
 {
-    const Grp<32> g;
-    if (need) {
-        const size_t n = (size_t)p.n;
-        const double *b = bank + (size_t)ep * 5 * n;
-        const double bwv = b[0 * n + e], dlv = b[1 * n + e], qv = b[2 * n + e], lossv = b[3 * n + e], sr = b[4 * n + e];
-        s.d_bw = 1.0 / bwv; s.dl = dlv; s.lr = lossv; s.max_qd = (double)(long long)qv / bwv;
-        s.w_full = tail_drop_threshold(s.d_bw, s.max_qd);
-        s.qd = 0.0; s.t_upd = 0.0; s.rate = sr; s.cur_time = 0.0; s.next_send = 1.0 / sr;
-        s.run_dur = 3 * dlv; s.conn_min = 0.0;
-        s.h1 = s.tail; s.h2 = s.tail; s.steps = 0;
-        p.d_bw[e] = s.d_bw; p.bw[e] = bwv; p.dl[e] = s.dl; p.lr[e] = s.lr; p.max_qd[e] = s.max_qd; p.w_full[e] = s.w_full;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double row[128];
+    for (int j = 0; j < pol.n_in; j++) row[j] = obs[(size_t)e * pol.n_in + j];
+    if (act_out && pol.w1) {
+        double out = mlp_eval(pol.w1, pol.b1, pol.w2, pol.b2, pol.w3, pol.b3, pol.n_in, pol.h1, pol.h2, row);
+        if (pol.stochastic) {
+            uint32_t c0 = (uint32_t)e, c1 = (uint32_t)(e >> 32), c2 = (uint32_t)t, c3 = 0x4e4f4953u;   // 'NOIS'
+            philox4x32_10(c0, c1, c2, c3, (uint32_t)pol.noise_seed, (uint32_t)(pol.noise_seed >> 32));
+            const double u1 = (res53(c0, c1) + 1.1102230246251565e-16), u2 = res53(c2, c3);
+            out += exp(pol.log_std) * sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        }
+        act_out[e] = out;
     }
-    MiOut mo;
-    double a, li;
-    warp_mi<false, true>(g, p, need, cnt, e, s, rng, s.run_dur, nullptr, 0, dummy, mo, a, li);   // :478
-    ovf = mo.overflow;
-    warp_mi<false, true>(g, p, need, cnt, e, s, rng, s.run_dur, nullptr, 0, dummy, mo, a, li);   // :479
-    ovf = ovf || mo.overflow;
+    if (vpred_out && pol.vw1)
+        vpred_out[e] = mlp_eval(pol.vw1, pol.vb1, pol.vw2, pol.vb2, pol.vw3, pol.vb3, pol.n_in, pol.h1, pol.h2, row);
 }
 
-__global__ void __launch_bounds__(PCC_WARP_THREADS, PCC_WARP_MINBLOCKS)
-pcc_rollout_kernel(DevState p, WarpPartition part, unsigned long long head0, RolloutArgs a)
+// SenderHistory.as_array of every env (oldest -> newest) from the history ring: the rollout's first observation
+__global__ void pcc_obs_from_hist_kernel(DevState p, unsigned long long head, double *__restrict__ obs)
 {
-    extern __shared__ double dyn_smem[];      // per warp: warp_smem_bytes(part.wbuf)
-    __shared__ WarpStage sstage[1];
-    double *wsm = dyn_smem + (size_t)(threadIdx.x >> 5) * (warp_smem_bytes(part.wbuf) / 8);
-    const Grp<32> g;
-    const unsigned lane = threadIdx.x & 31u;
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head0 + (unsigned long long)a.K;
-    int64_t first;
-    int cnt;
-    if (part.starts) {
-        const int nw = *part.n_warps;
-        if (w >= nw) return;                       // whole warp
-        first = part.starts[w];
-        cnt = (int)(part.starts[w + 1] - first);
-    } else {
-        first = w * part.static_e;
-        if (first >= p.n) return;
-        cnt = (int)((p.n - first < part.static_e) ? (p.n - first) : part.static_e);
-    }
-    const bool owner = (int)lane < cnt;
-    const int64_t e = owner ? (part.perm ? (int64_t)part.perm[first + lane] : first + lane) : 0;
-    EnvState s;
-    load_env(p, e, s);
-    PhiloxRng rng;
-    rng.init(p.seed[e], p.draws[e]);
-    const int H = p.H, F = p.F, HF = H * F;
-    double *hrow = p.hist + (size_t)e * HF;
-    double ret_acc = p.ret_acc[e];
-    int ep = 0;
-    bool any_ovf = false;
-#pragma unroll 1
-    for (int k = 0; k < a.K; k++) {
-        const size_t kn = (size_t)k * (size_t)p.n + (size_t)e;
-        const int slot_new = (int)((head0 + (unsigned long long)k) % (unsigned long long)H);
-        // ---- action: given, or from the policy on the current observation -------------------
-        double act = 0.0;
-        if (owner) {
-            if (a.actions) act = a.actions[kn];
-            else act = policy_action(a.pol, hrow, slot_new, H, F, e, head0 + (unsigned long long)k);   // slot_new = oldest row now
-            if (a.act_out) a.act_out[kn] = act;
-            s.rate = apply_rate_delta(s.rate, act, p.c);                         // :412
-        }
-        StepOut o;
-        double avg_lat, lat_inc;
-        warp_mi<true, true>(g, p, owner, cnt, e, s, rng, s.run_dur, wsm, part.wbuf, sstage[0], o.mi, avg_lat, lat_inc, 0, nullptr,
-                            p.mean_scratch ? p.mean_scratch + (size_t)w * PCC_GSCRATCH : nullptr);   // :416
-        bool need_reset = false;
-        if (owner) {
-            mi_stats_finish(o.mi, p.c, avg_lat, lat_inc, s.conn_min, true, o.st);
-            s.steps += 1;                                                        // :419
-            if (o.st.avg_lat > 0.0) s.run_dur = 0.5 * o.st.avg_lat;              // :437-438
-            o.done = s.steps >= p.c.max_steps;                                   // :444
-            any_ovf = any_ovf || o.mi.overflow;
-            for (int f = 0; f < F; f++) hrow[slot_new * F + f] = metric_value(o.st, p.ids[f]);
-            a.reward[kn] = o.st.reward;
-            a.done[kn] = o.done ? 1 : 0;
-            ret_acc += o.st.reward;                                              // :443
-            if (o.done) { p.ret_last[e] = ret_acc; ret_acc = 0.0; }
-            if (a.counts) { a.counts[3 * kn + 0] = o.mi.sent; a.counts[3 * kn + 1] = o.mi.acked; a.counts[3 * kn + 2] = o.mi.lost; }
-            need_reset = o.done;
-        }
-        // ---- auto-reset with the next parameters of the bank (warp-uniform branch) ------------
-        if (__any_sync(PCC_FULL, need_reset)) {
-            if (need_reset && ep >= a.n_episodes) { atomicAdd(&p.meta[META_PART_ERR], 1ull); need_reset = false; }
-            bool ovf = false;
-            rollout_reset(p, need_reset, cnt, e, s, rng, a.bank, ep, sstage[0], ovf);
-            if (need_reset) {
-                any_ovf = any_ovf || ovf;
-                ep++;
-                for (int i = 0; i < HF; i++) hrow[i] = metric_empty(p.ids[i % F]);
-            }
-        }
-        // ---- observation after the step (and after a reset): oldest -> newest ----------------
-        if (owner && a.obs) {
-            double *ob = a.obs + kn * (size_t)HF;
-            for (int h = 0; h < H; h++) {
-                int sl = slot_new + 1 + h;
-                if (sl >= H) sl -= H;
-                for (int f = 0; f < F; f++) ob[h * F + f] = hrow[sl * F + f];
-            }
+    const int HF = p.H * p.F;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n * HF) return;
+    const int64_t e = i / HF;
+    const int k = (int)(i - e * HF), h = k / p.F, f = k - h * p.F;
+    int sl = (int)(head % (unsigned long long)p.H) + h;     // the slot the next step will overwrite is the oldest
+    if (sl >= p.H) sl -= p.H;
+    obs[i] = p.hist[(size_t)e * HF + sl * p.F + f];
+}
+
+// Auto-reset of a rollout, part 1: for every env that finished its episode in this step (done != 0) fetch the link
+// parameters of its next episode from the bank [n_episodes][5][n] (row = resets of this env so far in this rollout)
+__global__ void pcc_bank_gather_kernel(DevState p, const uint8_t *__restrict__ done, const double *__restrict__ bank,
+                                       int32_t n_episodes, int32_t *__restrict__ ep, uint8_t *__restrict__ mask,
+                                       double *__restrict__ bw, double *__restrict__ dl, long long *__restrict__ queue,
+                                       double *__restrict__ loss, double *__restrict__ rate)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    uint8_t m = 0;
+    if (done[e]) {
+        const int j = ep[e];
+        if (j >= n_episodes) atomicAdd(&p.meta[META_PART_ERR], 1ull);   // the bank is too short: reported by pcc_check
+        else {
+            const size_t n = (size_t)p.n;
+            const double *b = bank + (size_t)j * 5 * n;
+            bw[e] = b[0 * n + e]; dl[e] = b[1 * n + e]; queue[e] = (long long)b[2 * n + e];
+            loss[e] = b[3 * n + e]; rate[e] = b[4 * n + e];
+            ep[e] = j + 1;
+            m = 1;
         }
     }
-    if (!owner) return;
-    store_env_dynamic(p, e, s);
-    p.draws[e] = rng.draws;
-    p.ret_acc[e] = ret_acc;
-    if (any_ovf) flag_overflow(p, e);
+    mask[e] = m;
 }
 
 template <int E>
@@ -1206,6 +1144,7 @@ pcc_reset_warp_kernel(DevState p, const uint8_t *__restrict__ mask, const double
     bool owner = lane < (unsigned)E && slot < p.n;
     const int64_t e = owner ? slot : 0;
     if (mask && !mask[e]) owner = false;
+    if (!__any_sync(PCC_FULL, owner)) return;   // nothing to reset here (the per-step masked reset of a rollout)
     EnvState s;
     const double bwv = bw[e], dlv = delay[e], sr = start_rate[e];
     // reset_env of pcc_core.cuh (network_sim.py:454-484)
@@ -1452,6 +1391,11 @@ struct pcc_handle_s {
     uint32_t *sched;          // launch order of the work units
     SchedCost sched_cost;
     int reb_parity;
+    // scratch of pcc_rollout: current observations, parameters / mask / episode index of the per-step masked reset
+    double *ro_obs, *ro_par;      // [n][H*F]; [4][n] bw, delay, loss, start_rate
+    long long *ro_queue;
+    int32_t *ro_ep;
+    uint8_t *ro_mask;
     // staging for pcc_step_host
     double *st_actions, *st_obs, *st_reward;
     uint8_t *st_done;
@@ -1734,6 +1678,7 @@ void pcc_destroy(pcc_handle h)
     cudaFree(h->st_done); cudaFree(h->st_counts);
     cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->perm); cudaFree(h->sort_tmp);
     cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps); cudaFree(h->sent_tmp); cudaFree(h->d.mean_scratch); cudaFree(h->n_solo_dev); cudaFree(h->sched);
+    cudaFree(h->ro_obs); cudaFree(h->ro_par); cudaFree(h->ro_queue); cudaFree(h->ro_ep); cudaFree(h->ro_mask);
     delete h;
 }
 
@@ -1934,44 +1879,78 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
 
 int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const pcc_policy *policy,
                 const double *reset_params_dev, int32_t n_episodes, double *obs_dev, double *actions_out_dev,
-                double *reward_dev, uint8_t *done_dev, int32_t *counts_dev, void *stream)
+                double *reward_dev, uint8_t *done_dev, int32_t *counts_dev, double *vpred_dev, void *stream)
 {
     if (!h || !reward_dev || !done_dev) return fail(PCC_EINVAL, "null pointer");
     if (n_steps < 1) return fail(PCC_EINVAL, "n_steps must be positive");
-    if (!actions_dev && !(policy && policy->w1)) return fail(PCC_EINVAL, "pcc_rollout needs actions or a policy");
-    if (!h->epw) return fail(PCC_EINVAL, "pcc_rollout needs the warp execution mode (Philox streams)");
+    const bool use_policy = !actions_dev;
+    if (use_policy && !(policy && policy->w1)) return fail(PCC_EINVAL, "pcc_rollout needs actions or a policy");
+    if (use_policy && !actions_out_dev) return fail(PCC_EINVAL, "pcc_rollout with a policy needs actions_out_dev");
+    if (vpred_dev && !(policy && policy->vw1)) return fail(PCC_EINVAL, "vpred_dev needs a policy with a value head");
+    if (h->cfg.rng_kind != PCC_RNG_PHILOX) return fail(PCC_EINVAL, "pcc_rollout needs Philox streams");
     if (n_episodes < 0 || (n_episodes > 0 && !reset_params_dev)) return fail(PCC_EINVAL, "bad reset parameter bank");
-    if (policy && policy->w1 &&
-        (policy->n_in != h->cfg.history_len * h->cfg.n_features || policy->h1 < 1 || policy->h1 > PCC_POLICY_MAXH ||
-         policy->h2 < 1 || policy->h2 > PCC_POLICY_MAXH || h->cfg.history_len * h->cfg.n_features > 128))
+    const int HF = h->cfg.history_len * h->cfg.n_features;
+    if (policy && (policy->w1 || policy->vw1) &&
+        (policy->n_in != HF || policy->h1 < 1 || policy->h1 > PCC_POLICY_MAXH || policy->h2 < 1 ||
+         policy->h2 > PCC_POLICY_MAXH || HF > 128))
         return fail(PCC_EINVAL, "policy shape does not fit (n_in = history_len * n_features <= 128, hidden <= 64)");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    WarpPartition part{nullptr, nullptr, nullptr, h->epw, h->wbuf, 0};
-    const int wpb = h->warp_threads / 32;
-    const size_t dyn = (size_t)wpb * warp_smem_bytes(h->wbuf);
-    int64_t nwarps = (h->cfg.n_envs + h->epw - 1) / h->epw;
-    if (h->rebalance_every > 0) {
-        int rc = rebalance(h, st);
+    const size_t n = (size_t)h->cfg.n_envs;
+    if (!h->ro_obs) {
+        CUDA_TRY(cudaMalloc(&h->ro_obs, 8 * n * (size_t)HF));
+        CUDA_TRY(cudaMalloc(&h->ro_par, 8 * n * 4));
+        CUDA_TRY(cudaMalloc(&h->ro_queue, 8 * n));
+        CUDA_TRY(cudaMalloc(&h->ro_ep, 4 * n));
+        CUDA_TRY(cudaMalloc(&h->ro_mask, n));
+    }
+    PolicyDev pol;
+    memset(&pol, 0, sizeof(pol));
+    if (policy) {
+        pol.w1 = use_policy ? policy->w1 : nullptr; pol.b1 = policy->b1; pol.w2 = policy->w2; pol.b2 = policy->b2;
+        pol.w3 = policy->w3; pol.b3 = policy->b3;
+        pol.vw1 = vpred_dev ? policy->vw1 : nullptr; pol.vb1 = policy->vb1; pol.vw2 = policy->vw2; pol.vb2 = policy->vb2;
+        pol.vw3 = policy->vw3; pol.vb3 = policy->vb3;
+        pol.n_in = policy->n_in; pol.h1 = policy->h1; pol.h2 = policy->h2;
+        pol.log_std = policy->log_std; pol.noise_seed = policy->noise_seed; pol.stochastic = policy->stochastic;
+    }
+    const bool eval = pol.w1 || pol.vw1;
+    const unsigned eg = (unsigned)((n + 127) / 128);
+    if (eval) {   // the observation the first action is computed from
+        pcc_obs_from_hist_kernel<<<(unsigned)((n * HF + 255) / 256), 256, 0, st>>>(h->d, h->head, h->ro_obs);
+        h->launches++;
+    }
+    if (n_episodes > 0) CUDA_TRY(cudaMemsetAsync(h->ro_ep, 0, 4 * n, st));
+    double *bw = h->ro_par, *dl = h->ro_par + n, *loss = h->ro_par + 2 * n, *rate = h->ro_par + 3 * n;
+    for (int32_t k = 0; k < n_steps; k++) {
+        const size_t kn = (size_t)k * n;
+        const double *act = actions_dev ? actions_dev + kn : actions_out_dev + kn;
+        if (eval) {
+            pcc_policy_kernel<<<eg, 128, 0, st>>>(pol, (int64_t)n, h->ro_obs, h->head, pol.w1 ? actions_out_dev + kn : nullptr,
+                                                 pol.vw1 ? vpred_dev + kn : nullptr);
+            h->launches++;
+        }
+        if (actions_dev && actions_out_dev)
+            CUDA_TRY(cudaMemcpyAsync(actions_out_dev + kn, actions_dev + kn, 8 * n, cudaMemcpyDeviceToDevice, st));
+        int rc = pcc_step(h, act, h->ro_obs, reward_dev + kn, done_dev + kn, counts_dev ? counts_dev + 3 * kn : nullptr,
+                          nullptr, stream);
         if (rc) return rc;
-        part.perm = h->perm; part.starts = h->starts; part.n_warps = h->n_warps;
-        nwarps = h->max_warps;
-        h->rebalance_now = true;    // costs will have drifted by the end of the rollout
+        if (n_episodes > 0) {
+            // finished envs start their next episode with the next row of the bank (network_sim.py:469-484)
+            pcc_bank_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d, done_dev + kn, reset_params_dev, n_episodes,
+                                                                             h->ro_ep, h->ro_mask, bw, dl, h->ro_queue, loss, rate);
+            h->launches++;
+            const bool reb = h->rebalance_now;
+            rc = pcc_reset(h, h->ro_mask, bw, dl, (const int64_t *)h->ro_queue, loss, rate, h->ro_obs, stream);
+            if (rc) return rc;
+            if (!h->packed) h->rebalance_now = reb;   // a stale partition is only slower; the periodic rebalance picks the resets up
+        }
+        if (obs_dev) CUDA_TRY(cudaMemcpyAsync(obs_dev + kn * HF, h->ro_obs, 8 * n * (size_t)HF, cudaMemcpyDeviceToDevice, st));
     }
-    RolloutArgs a;
-    memset(&a, 0, sizeof(a));
-    a.K = n_steps; a.actions = actions_dev; a.bank = reset_params_dev; a.n_episodes = n_episodes;
-    a.obs = obs_dev; a.act_out = actions_out_dev; a.reward = reward_dev; a.done = done_dev; a.counts = counts_dev;
-    if (policy && policy->w1 && !actions_dev) {
-        a.pol.w1 = policy->w1; a.pol.b1 = policy->b1; a.pol.w2 = policy->w2; a.pol.b2 = policy->b2;
-        a.pol.w3 = policy->w3; a.pol.b3 = policy->b3; a.pol.n_in = policy->n_in; a.pol.h1 = policy->h1; a.pol.h2 = policy->h2;
-        a.pol.log_std = policy->log_std; a.pol.noise_seed = policy->noise_seed; a.pol.stochastic = policy->stochastic;
+    if (pol.vw1) {   // V(observation after the last step): PPO1's nextvpred (before the (1 - new) factor)
+        pcc_policy_kernel<<<eg, 128, 0, st>>>(pol, (int64_t)n, h->ro_obs, h->head, nullptr, vpred_dev + (size_t)n_steps * n);
+        h->launches++;
     }
-    CUDA_TRY(cudaFuncSetAttribute(pcc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    const unsigned wgrid = (unsigned)((nwarps + wpb - 1) / wpb);
-    pcc_rollout_kernel<<<wgrid, h->warp_threads, dyn, st>>>(h->d, part, h->head, a);
-    h->head += (unsigned long long)n_steps;
-    h->launches++;
     CUDA_TRY(cudaGetLastError());
     return PCC_OK;
 }

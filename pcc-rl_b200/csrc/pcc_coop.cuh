@@ -795,9 +795,14 @@ __device__ __noinline__ void means_groups_from_buf(const Grp<G> &g, bool on, con
         r += __shfl_xor_sync(PCC_FULL, r, 2);    // ((r0+r1)+(r2+r3)) ((r4+r5)+(r6+r7))
         r += __shfl_xor_sync(PCC_FULL, r, 4);
         if (G > 8) r = g.bcast(r, 0);
-        double res;
-        if (c >= 8) { res = r; for (int k = nb; k < c; k++) res += p[k]; }
-        else { res = 0.; for (int k = 0; k < c; k++) res += p[k]; }
+        // the (up to 7) tail samples: loaded together, added in order
+        const int t0 = (c >= 8) ? nb : 0;
+        double tv[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) tv[k] = (t0 + k < c) ? p[t0 + k] : 0.0;
+        double res = (c >= 8) ? r : 0.;
+#pragma unroll
+        for (int k = 0; k < 7; k++) if (t0 + k < c) res += tv[k];
         if (active) {
             consumed += c;
             m.res = res;

@@ -144,6 +144,30 @@ struct LocalStack {
     __device__ __forceinline__ double &ls(int i) { return left_sum[i]; }
 };
 
+// Ring view of one lane for the MI-boundary analysis: records inside the lane's current tile window come from shared
+// memory (the record the scan stopped on is almost always the only one needed), the rest from global memory; flag
+// stores go to both so that the window stays consistent.
+struct TileRing {
+    DevRing g;
+    double2 *row;          // the lane's tile row
+    uint32_t w0;           // ring position of row[0]
+    uint32_t n;            // valid records in the row
+    __device__ __forceinline__ uint32_t capacity() const { return g.capacity(); }
+    __device__ __forceinline__ Rec load(uint32_t i) const
+    {
+        const uint32_t d = i - w0;
+        if (d < n) { const double2 v = row[d]; Rec r; r.a = v.x; r.l = v.y; return r; }
+        return g.load(i);
+    }
+    __device__ __forceinline__ void store_a(uint32_t i, double a)
+    {
+        const uint32_t d = i - w0;
+        if (d < n) row[d].x = a;
+        g.store_a(i, a);
+    }
+    __device__ __forceinline__ void prefetch(uint32_t) const {}
+};
+
 struct PackedOut {
     int32_t sent, acked, lost;
     double start, end;
@@ -239,6 +263,7 @@ __device__ __forceinline__ void packed_mi(const RingSet &rs, PackedSmem &sm, boo
 
     PCC_PTICK(1);
     // ---- phase B1: hop-1 events with a < end (scan_hop1 of pcc_core.cuh, from the tile) ----------------------
+    TileRing tring{ring, &sm.tile[lane][0], 0u, 0u};
     {
         bool scanning = owner && (h1 != tail);
         while (__any_sync(PCC_FULL, scanning)) {
@@ -246,6 +271,7 @@ __device__ __forceinline__ void packed_mi(const RingSet &rs, PackedSmem &sm, boo
             if (scanning) {
                 const uint32_t left = tail - h1;
                 const int avail = left < (uint32_t)PCC_TILE_R ? (int)left : PCC_TILE_R;
+                tring.w0 = h1; tring.n = (uint32_t)avail;
                 int k = 0;
                 for (; k < avail; k++) {
                     const double a = sm.tile[lane][k].x;
@@ -259,20 +285,24 @@ __device__ __forceinline__ void packed_mi(const RingSet &rs, PackedSmem &sm, boo
     }
     Pending m1;
     m1.has = false; m1.idx = 0; m1.t = 0.0; m1.l = 0.0; m1.dropped = false;
-    if (owner) boundary_hop1(ring, h1, tail, end, m1);
+    if (owner) boundary_hop1(tring, h1, tail, end, m1);
     __syncwarp();                                    // straggler flags are read by the hop-2 fill
 
     PCC_PTICK(2);
     // ---- phase B2: hop-2 events with b < end (scan_hop2) ---------------------------------------------------
     const uint32_t s_begin = h2;
     bool at_live = false;
+    tring.n = 0u;
+    int b2_rounds = 0;
     {
         bool scanning = owner && (h2 != tail);
         while (__any_sync(PCC_FULL, scanning)) {
             tile_fill(rs, sm, e, h2, tail, scanning);
+            b2_rounds++;
             if (scanning) {
                 const uint32_t left = tail - h2;
                 const int avail = left < (uint32_t)PCC_TILE_R ? (int)left : PCC_TILE_R;
+                tring.w0 = h2; tring.n = (uint32_t)avail;
                 int k = 0;
                 for (; k < avail; k++) {
                     const double2 r = sm.tile[lane][k];
@@ -295,7 +325,7 @@ __device__ __forceinline__ void packed_mi(const RingSet &rs, PackedSmem &sm, boo
     bool has_extra = false;
     Pending m2;
     m2.has = false; m2.idx = 0; m2.t = 0.0; m2.l = 0.0; m2.dropped = false;
-    if (owner && at_live) boundary_hop2(ring, h1, h2, tail, s.dl, end, acked, lost, extra, has_extra, m2);
+    if (owner && at_live) boundary_hop2(tring, h1, h2, tail, s.dl, end, acked, lost, extra, has_extra, m2);
 
     PCC_PTICK(3);
     // ---- the event that crosses `end` (run_mi phase 4) ---------------------------------------------------------
@@ -310,11 +340,11 @@ __device__ __forceinline__ void packed_mi(const RingSet &rs, PackedSmem &sm, boo
             PCC_PACKED_SEND(d, if ((uint32_t)(tail - h2) >= rs.cap) ovf = true; else { ring.store(tail, Rec{rec_.x, rec_.y}); tail++; });
         } else if (which == 1) {
             s.cur_time = m1.t;
-            if (m1.idx == h1) h1++; else ring.store_a(m1.idx, negd(m1.t));
+            if (m1.idx == h1) h1++; else tring.store_a(m1.idx, negd(m1.t));
         } else {
             s.cur_time = m2.t;
             if (m2.dropped) lost++; else { acked++; extra = m2.l; has_extra = true; }
-            if (m2.idx == h2) h2++; else ring.store_a(m2.idx, u2d(PCC_NEG_INF));
+            if (m2.idx == h2) h2++; else tring.store_a(m2.idx, u2d(PCC_NEG_INF));
         }
     }
 #undef PCC_PACKED_SEND
@@ -351,8 +381,11 @@ __device__ __forceinline__ void packed_mi(const RingSet &rs, PackedSmem &sm, boo
         }
         uint32_t i = s_begin;
         bool reading = (n > 0) && (i != s_end);
+        // the hop-2 scan took a single tile round: every lane's row still holds its records from s_begin on
+        bool reuse = b2_rounds == 1;
         while (__any_sync(PCC_FULL, reading)) {
-            tile_fill(rs, sm, e, i, s_end, reading);
+            if (!reuse) tile_fill(rs, sm, e, i, s_end, reading);
+            reuse = false;
             if (reading) {
                 const uint32_t left = s_end - i;
                 const int avail = left < (uint32_t)PCC_TILE_R ? (int)left : PCC_TILE_R;

@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.pcc_abi_version() == 1
+    assert L.pcc_abi_version() == lib.PCC_ABI_VERSION == 2
 
 
 def test_config_struct_layout_and_defaults():
