@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the batched MI simulator on N B200s, next to the CPU oracle.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3|config2|config4|config5|flows]
 
-One "step" = one monitor interval for every env of the batch (one pcc_step launch), auto-reset
-included (a 400-step episode ends inside the default window, so the amortised reset cost is
-in the number).  Workloads (BASELINE.json `configs`):
-    config2: 4 096 envs per GPU,  default (ICML'19) link-parameter ranges, history_len 10   [default]
-    config3: 65 536 envs per GPU, same ranges, fresh parameters at every per-env reset
+One "step" = one monitor interval for every env of the batch (one pcc_step call), auto-reset
+included at its natural frequency when K >= 400 (the window then covers a whole 400-step episode).
+For a shorter K the window is centred on the middle of an episode and the boundary step (reset kernel +
+fresh link parameters for every env) is timed separately and reported as config.episode_boundary.
+Workloads (BASELINE.json `configs`):
+    config3: 65 536 envs per GPU (524 288 on 8), default (ICML'19) ranges, fresh parameters at every reset   [default]
+    config2: 4 096 envs per GPU, same ranges, history_len 10 (also reported as a sub-key of the default line)
+    config4: the closed-loop rollout (policy + value head on the device, 8 192 steps by default; also a sub-key)
 Weak scaling: every rank owns --envs envs (global ids are contiguous, parameters and RNG streams
 are functions of the global id); no data-path collective; one all-gather of episode returns.
 
@@ -37,7 +40,7 @@ WORKLOADS = {
     "config2": dict(envs=4096, desc="4 096 envs on 1xB200, link params sampled from ICML'19 ranges, history_len=10"),
     "config3": dict(envs=65536, desc="65 536 envs on 1xB200, per-reset randomized bw/lat/queue/loss, 1 sender per env"),
     "config4": dict(envs=65536, desc="65 536 envs per GPU (524 288 on 8), PPO-style rollout end to end: on-device MLP policy "
-                                     "30-32-16-1 + env step fused (pcc_rollout, 64 MIs per launch), NCCL gather of episode returns"),
+                                     "30-32-16-1 + value head + env step + auto-reset (pcc_rollout), NCCL gather of episode returns"),
 }
 WORKLOADS["flows"] = dict(envs=1 << 20, desc="MI-sample ingestion (SURVEY 8f rank 4): 1 Mi live flows per GPU, one MI record per flow "
                                              "per step (~150 RTT samples each), history_len=10, 3 features")
@@ -49,17 +52,20 @@ ACTION_SIGMA = 1.0   # a ~ N(0,1), BASELINE.md §3
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=None, help="default 400 (config4: 8192)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (overrides the workload's)")
     ap.add_argument("--seed", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--ring-capacity", type=int, default=None, help="experiment: override the safe ring capacity")
     ap.add_argument("--only-device-pass", action="store_true", help="experiment: skip the b2b / e2e / cpu passes")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 8192 if a.workload == "config4" else 400
+    return a
 
 
 class ClockSampler(object):
@@ -121,16 +127,30 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-def run_reference_arm(args, rank, world):
-    """--impl reference: the CPU restatement of the reference (oracle/, the Python reference itself cannot
-    travel to the GPU box) on all host threads, same workload, same metric.  Rank 0 only."""
-    if rank != 0:
-        return
+REF_CHUNK = 100     # env-steps per process and "step" of the reference arm
+
+
+def time_python_reference(steps, warmup, seed, n_procs=None):
+    """The UNMODIFIED Python reference on this box's host cores (oracle/ref_timing.py): one SimulatedNetworkEnv per
+    process, `steps` x REF_CHUNK timed env-steps each (bounded), all cores and one core.  None if no reference tree."""
+    import ref_timing
+    root = ref_timing.find_reference_root()
+    if root is None:
+        return None
+    cores = n_procs or os.cpu_count() or 1
+    timed = int(min(max(steps, 1) * REF_CHUNK, 30000))
+    warm = int(min(max(warmup, 0) * REF_CHUNK, 2000))
+    allc = ref_timing.time_reference(cores, warm, timed, seed=seed, root=root)
+    one = ref_timing.time_reference(1, warm, min(timed, 6000), seed=seed, root=root)
+    return dict(value=float(sum(allc["per_process"])), cores=cores, single_core=one["value"],
+                bound_by_slowest_process=allc["value"], seconds=allc["seconds"], env_steps_per_process=timed,
+                root=root)
+
+
+def time_c_port(args, n, steps, warmup):
+    """The C restatement of the reference (oracle/) on all host threads over the arm's env batch."""
     import oracle
-    if args.workload == "flows":
-        return run_reference_arm_flows(args, oracle)
     from pcc_rl_b200 import sample_link_params
-    n = (args.envs or WORKLOADS[args.workload]["envs"]) * max(1, args.gpus)   # the whole job's env batch
     cores = os.cpu_count() or 1
     seeds = (np.uint64(args.seed) + np.arange(n, dtype=np.uint64))
     ob = oracle.OracleBatch(seeds, n_threads=cores)
@@ -147,22 +167,54 @@ def run_reference_arm(args, rank, world):
             episode += 1
             ob.reset(sample_link_params(args.seed, episode, np.arange(n), n))
             steps_in_ep = 0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         one()
     dt = time.perf_counter() - t0
-    v = n * args.steps / dt
+    return dict(value=n * steps / dt, cores=cores, seconds=dt, envs=n, steps=steps)
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, same metric.
+    If a reference tree is present (PCC_REFERENCE_ROOT, baseline/_ref staged by __graft_entry__.build(), /root/reference)
+    the line's value is the UNMODIFIED Python SimulatedNetworkEnv, one process per core, a bounded sample per step
+    (REF_CHUNK env-steps per process); the C restatement (oracle/) over the arm's env batch is reported beside it.
+    Without a tree the C restatement is the value and the line says reference_absent.  Rank 0 only."""
+    if rank != 0:
+        return
+    import oracle
+    if args.workload == "flows":
+        return run_reference_arm_flows(args, oracle)
+    wl = args.workload if args.workload in ("config2", "config3", "config4") else "config3"
+    n = (args.envs or WORKLOADS[wl]["envs"]) * max(1, args.gpus)   # the whole job's env batch
+    ks = min(args.steps, 40)                                      # bounded sample of the C restatement
+    port = time_c_port(args, n, ks, min(args.warmup, 5))
+    ref = time_python_reference(args.steps, args.warmup, args.seed)
+    port_desc = ("%d envs x %d steps on %d host threads, C restatement of the Python reference (oracle/)"
+                 % (n, ks, port["cores"]))
+    if ref is not None:
+        v, secs = ref["value"], ref["seconds"]
+        cpu = {"value": v, "unit": "env-steps/s", "cores": ref["cores"], "kind": "reference",
+               "sample": "unmodified SimulatedNetworkEnv (%s), one process per host core, %d env-steps per process incl. "
+                         "resets, default link-parameter ranges, actions N(0,1); sum of the per-process rates"
+                         % (ref["root"], ref["env_steps_per_process"]),
+               "single_core": ref["single_core"], "bound_by_slowest_process": ref["bound_by_slowest_process"],
+               "port": {"value": port["value"], "cores": port["cores"], "sample": port_desc}}
+    else:
+        v, secs = port["value"], port["seconds"]
+        cpu = {"value": v, "unit": "env-steps/s", "cores": port["cores"], "kind": "port", "reference_absent": True,
+               "sample": port_desc + "; no reference tree on this box (the unmodified Python reference measured "
+                                     "1.3-2.1k env-steps/s per core in the build container, BASELINE.md section 2)"}
     line = {"impl": "reference", "metric": "env-steps/sec (batched MI sim)", "value": v, "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "envs": n,
-                       "actions": "N(0,1)", "auto_reset": True},
-            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": "%d envs x %d steps, all host threads (C restatement of the Python reference; "
-                                       "the unmodified Python reference measured 1.3-1.5k env-steps/s on one core, "
-                                       "BASELINE.md §2)" % (n, args.steps)},
+            "config": {"workload": wl + ": " + WORKLOADS[wl]["desc"], "envs_per_gpu": n // max(1, args.gpus),
+                       "global_envs": n, "actions": "N(0,1)", "auto_reset": True,
+                       "reference_step": "%d env-steps of every host process" % REF_CHUNK if ref is not None else
+                                         "one MI of every env of the batch"},
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -288,51 +340,24 @@ def run_config5(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
 
 def run_config4(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
     """BASELINE config 4: K-step rollout (default 8 192 = PPO1's timesteps_per_actorbatch, stable_solve.py:52) with the
-    policy on the device; `value` = env-steps/s of the whole rollout incl. policy, auto-resets and the return gather."""
-    K, RK = args.steps, 64
-    env = pcc_rl_b200.PccBatchEnv(n_envs=n, device=dev, seed=args.seed, global_offset=rank * n, n_global=n_global)
-    env.reset()
-    g = torch.Generator(device=dev)
-    g.manual_seed(args.seed + 7)    # same random-init policy on every rank
-    r = lambda *sh, sc: torch.randn(*sh, generator=g, device=dev, dtype=torch.float64) * sc
-    pol = dict(w1=r(32, 30, sc=0.2), b1=r(32, sc=0.05), w2=r(16, 32, sc=0.2), b2=r(16, sc=0.05), w3=r(1, 16, sc=0.5),
-               b3=r(1, sc=0.05), stochastic=True, log_std=-0.7, noise_seed=args.seed + rank)
-    for _ in range(max(1, args.warmup // RK)):
-        env.rollout(RK, policy=pol, want_obs=False, want_counts=False)
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize(dev)
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = env.launches
-    t0 = time.perf_counter()
-    s.record()
-    finished, steps_done = [], 0
-    while steps_done < K:
-        k = min(RK, K - steps_done)
-        out = env.rollout(k, policy=pol, want_obs=False, want_counts=False)
-        steps_done += k
-        if bool(out["done"].any()):
-            finished.append(env.column("last_episode_return")[out["done"].any(0)])
-    e.record()
-    rets = torch.cat(finished) if finished else torch.zeros(0, dtype=torch.float64, device=dev)
-    stats = D.gather_episode_returns(rets)          # NCCL all-gather of [count, sum, sum^2]
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize(dev)
-    wall = D.max_over_ranks(time.perf_counter() - t0, dev)
-    dev_ms = D.max_over_ranks(s.elapsed_time(e), dev)
-    env.check()
+    policy and the value head on the device; `value` = env-steps/s of the whole rollout incl. policy, auto-resets and the
+    return gather."""
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+    roll = run_rollout(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global, args.steps, barrier, lambda k, w: 0)
     if rank == 0:
         print(json.dumps({
-            "metric": "env-steps/sec (batched MI sim)", "value": n_global * K / wall, "unit": "env-steps/s",
-            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * wall / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "metric": "env-steps/sec (batched MI sim)", "value": roll["value"], "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": roll["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config4: " + WORKLOADS["config4"]["desc"], "envs_per_gpu": n, "global_envs": n_global,
-                       "policy": "random-init MLP 30-32-16-1 (tanh), stochastic", "steps_per_launch": RK},
-            "device_ms_per_step": dev_ms / K, "gpu_launches": int(env.launches - launches0),
-            "e2e": {"value": n_global * K / wall, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "policy": roll["policy"]},
+            "device_ms_per_step": roll["device_ms_per_step"], "gpu_launches": roll["gpu_launches"],
+            "e2e": {"value": roll["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "closed loop on the device: nothing crosses PCIe per step"},
-            "episode_returns": {"count": stats["count"], "mean": stats["mean"]}}))
+            "episode_returns": roll["episode_returns"], "note": roll["note"]}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -506,55 +531,95 @@ def main():
         run_config5(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global)
         return
 
-    def make_env():
-        return pcc_rl_b200.PccBatchEnv(n_envs=n, device=dev, seed=args.seed, global_offset=rank * n,
-                                       n_global=n_global, auto_reset=True, ring_capacity=args.ring_capacity)
+    MAX_STEPS = 400
+
+    def make_env(ne=n):
+        return pcc_rl_b200.PccBatchEnv(n_envs=ne, device=dev, seed=args.seed, global_offset=rank * ne,
+                                       n_global=ne * world, auto_reset=True, ring_capacity=args.ring_capacity)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(args.seed + 1 + rank)
-    # pre-generate the actions (the policy is outside the path): [W+K, n] float64 on the device
-    actions = torch.randn((W + K, n), generator=gen, device=dev, dtype=torch.float64) * ACTION_SIGMA
+    def preroll(k, w):
+        """Untimed steps before the warm-up.  K >= 400: none -- the window covers a whole episode and its boundary at
+        the natural frequency.  K < 400: the window is centred on the middle of the episode (early steps are lighter
+        than late ones: the rates random-walk apart); the boundary step is then timed separately (episode_boundary)."""
+        return 0 if k >= MAX_STEPS else max(0, MAX_STEPS // 2 - w - k // 2)
+
+    def make_actions(ne, rows, seed):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        return torch.randn((rows, ne), generator=gen, device=dev, dtype=torch.float64) * ACTION_SIGMA
+
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    # ---------------- pass 1: device-resident inputs, per-step CUDA-event brackets ----------------
-    env = make_env()
-    env.reset()
-    tot = torch.zeros(3, dtype=torch.int64, device=dev)
-    finished = []
-    for t in range(W):
-        env.step(actions[t])
-    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
-    barrier()
-    launches0 = env.launches
-    sampler.start()
-    wall0 = time.perf_counter()
-    for t in range(K):
-        if flush is not None:
-            flush.fill_(t & 0xFF)
-        ev_s[t].record()
-        obs, rew, done, info = env.step(actions[W + t])
-        ev_e[t].record()
-        tot += info["counts"].sum(0)
-        if bool(env._steps.max() == 0):  # a synchronized auto-reset just happened
+    def device_pass(ne, k, w, sample_clocks):
+        """Device-resident inputs, per-step CUDA-event brackets, L2 flushed between steps (outside the brackets)."""
+        env = make_env(ne)
+        env.reset()
+        pre = preroll(k, w)
+        acts = make_actions(ne, pre + w + k, args.seed + 1 + rank)
+        for t in range(pre + w):
+            env.step(acts[t])
+        ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
+        ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
+        sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+        barrier()
+        launches0 = env.launches
+        if sample_clocks:
+            sampler.start()
+        wall0 = time.perf_counter()
+        tot = torch.zeros(3, dtype=torch.int64, device=dev)
+        finished = []
+        for t in range(k):
+            if flush is not None:
+                flush.fill_(t & 0xFF)
+            ev_s[t].record()
+            obs, rew, done, info = env.step(acts[pre + w + t])
+            ev_e[t].record()
+            tot += info["counts"].sum(0)
+            if int(env._steps.max()) == 0:     # host bookkeeping: a synchronized auto-reset just happened
+                finished.append(env.column("last_episode_return"))
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sample_clocks else None
+        launches = env.launches - launches0
+        env.check()
+        boundary_ms = None
+        if not finished and sample_clocks:
+            # the episode boundary is outside the window: walk to it untimed and time that one step (reset kernel +
+            # parameter upload for every env + the step itself)
+            ag = make_actions(ne, 1, args.seed + 99)[0]
+            while int(env._steps.max()) < MAX_STEPS - 1:
+                env.step(ag)
+            torch.cuda.synchronize(dev)
+            bs, be = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            bs.record()
+            env.step(ag)
+            be.record()
+            torch.cuda.synchronize(dev)
+            boundary_ms = D.max_over_ranks(bs.elapsed_time(be), dev)
             finished.append(env.column("last_episode_return"))
-    barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-    launches = env.launches - launches0
-    env.check()
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))
-    dev_ms = D.max_over_ranks(dev_ms, dev)
-    sent, acked, lost = [int(x) for x in tot.cpu().tolist()]
-    g_sent, g_acked = D.sum_over_ranks(sent, dev), D.sum_over_ranks(acked, dev)
-    rets = torch.cat(finished) if finished else torch.zeros(0, dtype=torch.float64, device=dev)
-    ret_stats = D.gather_episode_returns(rets)   # the path's only collective (NCCL all-gather, a few bytes)
+            env.check()
+        per_step = [a.elapsed_time(b) for a, b in zip(ev_s, ev_e)]
+        dev_ms = D.max_over_ranks(sum(per_step), dev)
+        sent, acked, _lost = [int(x) for x in tot.cpu().tolist()]
+        rets = torch.cat(finished) if finished else torch.zeros(0, dtype=torch.float64, device=dev)
+        out = dict(dev_ms=dev_ms, wall=wall, clocks=clocks, launches=int(launches), g_sent=D.sum_over_ranks(sent, dev),
+                   g_acked=D.sum_over_ranks(acked, dev), rets=rets, reset_step_ms=max(per_step),
+                   median_step_ms=float(np.median(per_step)), boundary_inside=boundary_ms is None and bool(finished),
+                   boundary_ms=boundary_ms)
+        env.close()
+        del env, acts
+        torch.cuda.empty_cache()
+        return out
+
+    # ---------------- pass 1: the headline device pass ----------------
+    p1 = device_pass(n, K, W, True)
+    ret_stats = D.gather_episode_returns(p1["rets"])   # the path's only collective (NCCL all-gather, a few bytes)
+    dev_ms, g_sent, g_acked, clocks = p1["dev_ms"], p1["g_sent"], p1["g_acked"], p1["clocks"]
     value = n_global * K / (dev_ms * 1e-3)
     if args.only_device_pass:
         if rank == 0:
@@ -563,76 +628,102 @@ def main():
         return
 
     # ---------------- pass 2: back to back, no flush, one bracket around all K steps ----------------
-    del env
     env = make_env()
     env.reset()
+    acts = make_actions(n, W + K, args.seed + 1 + rank)
     for t in range(W):
-        env.step(actions[t])
+        env.step(acts[t])
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for t in range(K):
-        env.step(actions[W + t])
+        env.step(acts[W + t])
     e.record()
     barrier()
     b2b_ms = D.max_over_ranks(s.elapsed_time(e), dev)
     env.check()
-
-    # ---------------- pass 2b: fused rollout, 64 monitor intervals per launch ----------------
+    env.close()
     del env
-    env = make_env()
-    env.reset()
-    RK = 64
-    n_roll = max(1, K // RK)
-    for t in range(W):
-        env.step(actions[t])
-    ract = actions[W:W + RK]
-    if ract.shape[0] < RK:
-        ract = torch.randn((RK, n), generator=gen, device=dev, dtype=torch.float64) * ACTION_SIGMA
-    barrier()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(n_roll):
-        env.rollout(RK, actions=ract, want_obs=False, want_counts=False)
-    e.record()
-    barrier()
-    roll_ms = D.max_over_ranks(s.elapsed_time(e), dev)
-    env.check()
+    torch.cuda.empty_cache()
 
-    # ---------------- pass 3: end to end through host buffers (pcc_step_host) ----------------
-    del env
+    # ---------------- pass 3: end to end through host buffers ----------------
+    # pinned HOST actions in, obs / reward / done out, every step; (a) two steps in flight through
+    # pcc_step_host_submit / _wait (the download of step k overlaps step k + 1), (b) the synchronous pcc_step_host
     env = make_env()
     env.reset()
     hf = env.obs_dim
+    pre3 = preroll(K, W)
+    for t in range(pre3):
+        env.step(acts[t % (W + K)])
     h_act = torch.empty((W + K, n), dtype=torch.float64).pin_memory()
-    h_act.copy_(actions.cpu())
-    h_obs = torch.empty((n, hf), dtype=torch.float64).pin_memory()
-    h_rew = torch.empty(n, dtype=torch.float64).pin_memory()
-    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    a_np, o_np, r_np, d_np = h_act.numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy()
+    h_act.copy_(acts.cpu())
+    bufs = [dict(o=torch.empty((n, hf), dtype=torch.float64).pin_memory(), r=torch.empty(n, dtype=torch.float64).pin_memory(),
+                 d=torch.empty(n, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+    a_np = h_act.numpy()
+    nb = [{k: v.numpy() for k, v in b.items()} for b in bufs]
 
-    def host_step(t):
-        env.step_host(a_np[t], o_np, r_np, d_np)
-        if env._steps[0] >= env.max_steps:      # the caller resets finished envs, as PPO does
-            env.reset()
-    for t in range(W):
-        host_step(t)
+    def e2e_run(first, count, pipelined):
+        acc, tk = 0.0, [None, None]
+        for t in range(first, first + count):
+            sl = t & 1
+            if pipelined:
+                if tk[sl] is not None:
+                    env.step_host_wait(tk[sl])
+                    acc += float(nb[sl]["r"][0])           # the result is really read on the host
+                tk[sl] = env.step_host_submit(a_np[t], nb[sl]["o"], nb[sl]["r"], nb[sl]["d"])
+            else:
+                env.step_host(a_np[t], nb[sl]["o"], nb[sl]["r"], nb[sl]["d"])
+                acc += float(nb[sl]["r"][0])
+            if env._steps[0] >= env.max_steps:             # the caller resets finished envs, as PPO does
+                for q in (0, 1):
+                    if tk[q] is not None:
+                        env.step_host_wait(tk[q]); acc += float(nb[q]["r"][0]); tk[q] = None
+                env.reset()
+        for q in (0, 1):
+            if tk[q] is not None:
+                env.step_host_wait(tk[q]); acc += float(nb[q]["r"][0])
+        return acc
+
+    e2e_run(0, W, True)
     barrier()
     t0 = time.perf_counter()
-    ret_acc = 0.0
-    for t in range(K):
-        host_step(W + t)
-        ret_acc += float(r_np[0])               # the result is really read on the host
+    e2e_run(W, K, True)
     barrier()
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    ks = min(K, 50)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(W, ks, False)
+    barrier()
+    e2e_sync_s = D.max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = n_global * K / e2e_s
     env.check()
-    del env
+    env.close()
+    del env, acts
+    torch.cuda.empty_cache()
+
+    # ---------------- sub-key: the closed-loop rollout of config 4 (policy + value head on the device) ----------------
+    roll = run_rollout(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global, max(64, min(K, 512)), barrier, preroll)
+
+    # ---------------- sub-key: BASELINE config 2 (4 096 envs per GPU) ----------------
+    c2 = None
+    if args.workload == "config3" and n > 4096:
+        k2 = min(K, 100)
+        q = device_pass(4096, k2, 10, False)
+        b2 = algorithmic_bytes(4096 * world * k2, q["g_sent"], q["g_acked"])
+        c2 = {"workload": "config2: " + WORKLOADS["config2"]["desc"], "value": 4096 * world * k2 / (q["dev_ms"] * 1e-3),
+              "unit": "env-steps/s", "ms_per_step": q["dev_ms"] / k2, "steps": k2,
+              "roofline_frac": b2 / (q["dev_ms"] * 1e-3) / 1e9 / world / measured_peak_gbs()[0],
+              "boundary_inside": q["boundary_inside"]}
+        r2 = run_rollout(args, pcc_rl_b200, D, torch, dev, rank, world, 4096, 4096 * world, max(64, min(K, 256)), barrier, preroll)
+        c2["rollout"] = {k: r2[k] for k in ("value", "ms_per_step", "device_ms_per_step", "steps", "gpu_launches")}
 
     if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return
     peak, peak_kind = measured_peak_gbs()
-    traffic, traffic_src, kernel_name = None, None, "pcc_step_*"
+    traffic, traffic_src, kernel_name = None, None, "pcc_step_packed_kernel" if n > 16384 else "pcc_step_warp_kernel"
     try:   # dram bytes per launch of the dominant kernel, from the committed ncu capture of this workload
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)[args.workload]
@@ -649,18 +740,25 @@ def main():
         "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "envs_per_gpu": n,
                    "global_envs": n_global, "history_len": 10, "features": 3, "rng": "philox4x32-10",
                    "actions": "N(0,1) pre-generated on device", "auto_reset": True,
+                   "episode_boundary": ("inside the timed window (that step took %.3f ms, the median step %.3f ms)"
+                                        % (p1["reset_step_ms"], p1["median_step_ms"])) if p1["boundary_inside"] else
+                                       ("outside the %d-step window (steps %d.. of a 400-step episode); timed separately: the "
+                                        "boundary step takes %.3f ms, the median step %.3f ms -> %.1f M env-steps/s over a "
+                                        "whole episode" % (K, preroll(K, W) + W, p1["boundary_ms"] or 0.0, p1["median_step_ms"],
+                                                           n_global * 400 / (399 * p1["median_step_ms"] + (p1["boundary_ms"] or 0.0)) / 1e3)),
                    "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB write outside the event brackets)",
                    "parallelism": "env-batch sharding x%d, no data-path collective" % world},
         "back_to_back": {"value": n_global * K / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K,
                          "note": "K steps enqueued back to back, one event bracket, warm L2"},
-        "rollout": {"value": n_global * RK * n_roll / (roll_ms * 1e-3), "ms_per_step": roll_ms / (RK * n_roll),
-                    "steps_per_launch": RK, "launches": n_roll,
-                    "note": "pcc_rollout: 64 MIs per launch with in-kernel auto-reset, same actions; bit-identical to 64 steps"},
+        "rollout": roll,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 8 * n,
                 "d2h_bytes_per_step": n * (8 * hf + 8 + 1), "ms_per_step": 1e3 * e2e_s / K,
-                "api": "PccBatchEnv.step_host -> pcc_step_host (pinned host buffers, synchronous)"},
-        "gpu_launches": int(launches),
-        "wall_s_timed_region": wall,
+                "api": "PccBatchEnv.step_host_submit / step_host_wait -> pcc_step_host_submit / _wait: pinned host buffers, "
+                       "two steps in flight (the download of step k overlaps the upload and kernel of step k + 1)",
+                "sync": {"value": n_global * ks / e2e_sync_s, "ms_per_step": 1e3 * e2e_sync_s / ks, "steps": ks,
+                         "api": "PccBatchEnv.step_host -> pcc_step_host (one step in flight, synchronous)"}},
+        "gpu_launches": p1["launches"],
+        "wall_s_timed_region": p1["wall"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
@@ -670,22 +768,82 @@ def main():
         "clocks": clocks,
         "episode_returns": {"count": ret_stats["count"], "mean": ret_stats["mean"]},
     }
+    if c2 is not None:
+        line["config2"] = c2
     if not args.no_cpu_baseline:
+        ref = time_python_reference(min(K, 60), min(W, 5), args.seed)
+        ns, ks2 = min(n, 4096), 100
         import oracle
         from pcc_rl_b200 import sample_link_params
         cores = os.cpu_count() or 1
-        ns, ks = min(n, 4096), 100
-        p = sample_link_params(args.seed, 1, np.arange(ns), n_global)
-        acts = np.random.default_rng(args.seed + 1).normal(0, ACTION_SIGMA, (ks, ns))
-        r = oracle.batch_run(p["bw"], p["lat"], p["queue"], p["loss"], p["start_rate"],
-                             np.uint64(args.seed) + np.arange(ns, dtype=np.uint64), ks, actions=acts, n_threads=cores)
-        line["cpu_baseline"] = {"value": ns * ks / r["seconds"], "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": "%d envs x (reset + %d steps) of the same workload on %d host threads; "
-                                          "C restatement of the reference (oracle/), the Python reference itself "
-                                          "measured 1.3-1.5k env-steps/s on one core (BASELINE.md)" % (ns, ks, cores)}
+        pp = sample_link_params(args.seed, 1, np.arange(ns), n_global)
+        pacts = np.random.default_rng(args.seed + 1).normal(0, ACTION_SIGMA, (ks2, ns))
+        r = oracle.batch_run(pp["bw"], pp["lat"], pp["queue"], pp["loss"], pp["start_rate"],
+                             np.uint64(args.seed) + np.arange(ns, dtype=np.uint64), ks2, actions=pacts, n_threads=cores)
+        port = {"value": ns * ks2 / r["seconds"], "cores": cores,
+                "sample": "%d envs x (reset + %d steps) of the same workload on %d host threads; C restatement of the "
+                          "reference (oracle/)" % (ns, ks2, cores)}
+        if ref is not None:
+            line["cpu_baseline"] = {"value": ref["value"], "unit": "env-steps/s", "cores": ref["cores"], "kind": "reference",
+                                    "sample": "unmodified Python SimulatedNetworkEnv (%s), one process per host core, %d "
+                                              "env-steps per process incl. resets, default ranges, actions N(0,1); sum of "
+                                              "the per-process rates" % (ref["root"], ref["env_steps_per_process"]),
+                                    "single_core": ref["single_core"], "port": port}
+        else:
+            line["cpu_baseline"] = dict(port, unit="env-steps/s", kind="port", reference_absent=True)
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def run_rollout(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global, K, barrier, preroll):
+    """The closed loop of BASELINE config 4 on every rank: K monitor intervals with the MLP policy 30-32-16-1 and the
+    value network of the same shape on the device (PPO1's ob / ac / vpred / rew / new segment, stable_solve.py:30-58),
+    in-sequence auto-reset, nothing crossing PCIe per step, and the NCCL gather of the finished episodes' returns."""
+    RK = 256
+    env = pcc_rl_b200.PccBatchEnv(n_envs=n, device=dev, seed=args.seed, global_offset=rank * n, n_global=n_global)
+    env.reset()
+    g = torch.Generator(device=dev)
+    g.manual_seed(args.seed + 7)    # same random-init networks on every rank
+    r = lambda *sh, sc: torch.randn(*sh, generator=g, device=dev, dtype=torch.float64) * sc
+    pol = dict(w1=r(32, 30, sc=0.2), b1=r(32, sc=0.05), w2=r(16, 32, sc=0.2), b2=r(16, sc=0.05), w3=r(1, 16, sc=0.5),
+               b3=r(1, sc=0.05), vw1=r(32, 30, sc=0.2), vb1=r(32, sc=0.05), vw2=r(16, 32, sc=0.2), vb2=r(16, sc=0.05),
+               vw3=r(1, 16, sc=0.5), vb3=r(1, sc=0.05), stochastic=True, log_std=-0.7, noise_seed=args.seed + rank)
+    pre = preroll(K, 16) + 16                       # includes the warm-up launches of every kernel of the sequence
+    done_pre = 0
+    while done_pre < pre:
+        k = min(RK, pre - done_pre)
+        env.rollout(k, policy=pol, want_obs=False, want_counts=False)
+        done_pre += k
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = env.launches
+    t0 = time.perf_counter()
+    s.record()
+    finished, steps_done = [], 0
+    while steps_done < K:
+        k = min(RK, K - steps_done)
+        crosses = bool(((env._steps + k) // env.max_steps).max() > 0)       # host bookkeeping, no device sync
+        env.rollout(k, policy=pol, want_obs=False, want_counts=False)
+        steps_done += k
+        if crosses:
+            finished.append(env.column("last_episode_return"))
+    e.record()
+    rets = torch.cat(finished) if finished else torch.zeros(0, dtype=torch.float64, device=dev)
+    stats = D.gather_episode_returns(rets)          # NCCL all-gather of [count, sum, sum^2]
+    barrier()
+    wall = D.max_over_ranks(time.perf_counter() - t0, dev)
+    dev_ms = D.max_over_ranks(s.elapsed_time(e), dev)
+    launches = int(env.launches - launches0)
+    env.check()
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    return {"value": n_global * K / wall, "unit": "env-steps/s", "ms_per_step": 1e3 * wall / K, "device_ms_per_step": dev_ms / K,
+            "steps": K, "gpu_launches": launches, "policy": "random-init MLP 30-32-16-1 (tanh), stochastic, + value head",
+            "episode_returns": {"count": stats["count"], "mean": stats["mean"]},
+            "note": "pcc_rollout: per step policy / value kernel + step kernel + bank gather + masked reset, enqueued on the "
+                    "device; wall clock incl. the NCCL gather of episode returns; nothing crosses PCIe per step"}
 
 
 if __name__ == "__main__":

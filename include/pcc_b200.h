@@ -160,6 +160,16 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
 int pcc_step_host(pcc_handle h, const double *actions_host, double *obs_host, double *reward_host,
                   uint8_t *done_host, int32_t *counts_host, void *stream);
 
+/* The same, split in two so that a caller can keep two steps in flight (e.g. two half-batches of a vector env, or
+ * actions that do not depend on the previous observation): submit enqueues upload, step and download -- the download
+ * runs on a stream of the handle's own, from one of two device staging slots, so it overlaps the NEXT submission's
+ * upload and kernel -- and returns a ticket; wait blocks until that step's host buffers are complete.  At most two
+ * tickets may be outstanding; each needs its own host buffers.  pcc_step_host == submit + wait. */
+int pcc_step_host_submit(pcc_handle h, const double *actions_host, double *obs_host, double *reward_host,
+                         uint8_t *done_host, int32_t *counts_host, double *info_host /* optional, [n][PCC_INFO_WIDTH] */,
+                         void *stream, int64_t *ticket);
+int pcc_step_host_wait(pcc_handle h, int64_t ticket);
+
 /* On-device policy for pcc_rollout: the MLP of stable_solve.py:30-45 (obs -> h1 -> h2 -> 1, tanh hidden
  * layers, linear output = mean of the Gaussian action) and, optionally, the value network of the same shape that
  * PPO1 trains beside it (MlpPolicy: vf head; vw1 == NULL = none).  All pointers are device pointers to binary64,

@@ -66,7 +66,7 @@ class PccError(RuntimeError):
 # every symbol include/pcc_b200.h declares
 EXPORTS = ["pcc_default_consts", "pcc_default_config", "pcc_ring_capacity_for", "pcc_workspace_bytes",
            "pcc_create", "pcc_destroy", "pcc_attach", "pcc_seed", "pcc_get_mt_state", "pcc_set_mt_state",
-           "pcc_reset", "pcc_step", "pcc_step_host", "pcc_rollout", "pcc_check", "pcc_get_column", "pcc_launch_count",
+           "pcc_reset", "pcc_step", "pcc_step_host", "pcc_step_host_submit", "pcc_step_host_wait", "pcc_rollout", "pcc_check", "pcc_get_column", "pcc_launch_count",
            "pcc_last_error", "pcc_abi_version", "pcc_multi_workspace_bytes", "pcc_multi_create", "pcc_multi_destroy",
            "pcc_multi_seed", "pcc_multi_reset", "pcc_multi_step", "pcc_multi_check",
            "pcc_default_variant", "pcc_multi_set_variant", "pcc_multi_step_cwnd",
@@ -114,6 +114,8 @@ def load(rebuild_if_stale=True):
     L.pcc_reset.argtypes = [vp, u8p, dp, dp, vp, dp, dp, dp, vp]
     L.pcc_step.argtypes = [vp, dp, dp, dp, u8p, vp, dp, vp]
     L.pcc_step_host.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
+    L.pcc_step_host_submit.argtypes = [vp, dp, dp, dp, u8p, vp, dp, vp, C.POINTER(C.c_int64)]
+    L.pcc_step_host_wait.argtypes = [vp, C.c_int64]
     L.pcc_rollout.argtypes = [vp, C.c_int32, dp, C.POINTER(PccPolicy), dp, C.c_int32, dp, dp, dp, u8p, vp, dp, vp]
     L.pcc_check.argtypes = [vp, vp]
     L.pcc_multi_workspace_bytes.argtypes = [C.POINTER(PccConfig), C.c_int32, C.POINTER(C.c_uint64)]

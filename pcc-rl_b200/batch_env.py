@@ -136,38 +136,78 @@ class PccBatchEnv(object):
 
     def reset(self, mask=None, params=None):
         """Starts a new episode for every env (or those in the boolean numpy `mask`).  `params` may
-        give explicit link parameters: dict of arrays bw, lat, queue, loss, start_rate (length n_envs)."""
+        give explicit link parameters: dict of arrays bw, lat, queue, loss, start_rate (length n_envs).
+        Sampled parameters are prepared ahead of time (see _prefetch_start), so an episode boundary
+        costs the reset kernel and five small uploads, not a host-side sampling pass."""
         torch = self.torch
         sel = np.ones(self.n_envs, dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
+        if mask is not None and sel.all():
+            mask = None
+        pinned = None
         if params is None:
-            params = self._sample(sel)
+            pinned = self._prefetch_take(sel)
+            params = pinned[0] if pinned is not None else self._sample(sel)
         if self.params is None:
             self.params = {k: np.array(v, copy=True) for k, v in params.items()}
         else:
             for k in self.params:
                 self.params[k][sel] = np.asarray(params[k])[sel]
         m = None if mask is None else self._dev(sel.astype(np.uint8), torch.uint8)
-        bw = self._dev(params["bw"], torch.float64)
-        lat = self._dev(params["lat"], torch.float64)
-        q = self._dev(params["queue"], torch.int64)
-        loss = self._dev(params["loss"], torch.float64)
-        rate = self._dev(params["start_rate"], torch.float64)
+        if pinned is not None:      # page-locked staging: asynchronous uploads on the current stream
+            bw, lat, q, loss, rate = (pinned[1][k].to(self.device, non_blocking=True)
+                                      for k in ("bw", "lat", "queue", "loss", "start_rate"))
+        else:
+            bw = self._dev(params["bw"], torch.float64)
+            lat = self._dev(params["lat"], torch.float64)
+            q = self._dev(params["queue"], torch.int64)
+            loss = self._dev(params["loss"], torch.float64)
+            rate = self._dev(params["start_rate"], torch.float64)
         _lib.check(self.L.pcc_reset(self.h, m.data_ptr() if m is not None else None, bw.data_ptr(), lat.data_ptr(),
                                     q.data_ptr(), loss.data_ptr(), rate.data_ptr(), self.obs.data_ptr(),
                                     self._stream()))
         # the parameter tensors must outlive the asynchronous kernel
-        self._keep = (m, bw, lat, q, loss, rate)
+        self._keep = (m, bw, lat, q, loss, rate, pinned)
         self._steps[sel] = 0
         self._episode[sel] += 1
+        if self.auto_reset:
+            self._prefetch_start()
         return self.obs
+
+    # -- parameters of the NEXT episode, sampled by a host thread while the current episode runs ------------------
+    def _prefetch_start(self):
+        import threading
+        torch = self.torch
+        episodes = self._episode.copy()
+        box = {}
+
+        def work():
+            p = self._sample_for(np.ones(self.n_envs, dtype=bool), episodes)
+            box["pin"] = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in p.items()}
+            box["host"] = p
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        self._pref = (th, episodes, box)
+
+    def _prefetch_take(self, sel):
+        pref, self._pref = getattr(self, "_pref", None), None
+        if pref is None:
+            return None
+        th, episodes, box = pref
+        th.join()
+        if "host" not in box or not np.array_equal(episodes[sel], self._episode[sel]):
+            return None
+        return box["host"], box["pin"]
 
     def _sample(self, sel):
         """Reference-formula link parameters as a function of (seed, episode, global env id)."""
+        return self._sample_for(sel, self._episode)
+
+    def _sample_for(self, sel, episode):
         out = {k: np.zeros(self.n_envs, dtype=np.int64 if k == "queue" else np.float64)
                for k in ("bw", "lat", "queue", "loss", "start_rate")}
         idx = np.nonzero(sel)[0]
-        for ep in np.unique(self._episode[idx]):
-            ii = idx[self._episode[idx] == ep]
+        for ep in np.unique(episode[idx]):
+            ii = idx[episode[idx] == ep]
             p = sample_link_params(self.seed_base, int(ep), self._global_ids[ii], self.n_global, self.ranges)
             for k in out:
                 out[k][ii] = p[k]
@@ -214,10 +254,7 @@ class PccBatchEnv(object):
         bank = np.zeros((max(n_eps, 1), 5, n))
         for j in range(n_eps):
             sel = n_resets > j
-            saved = self._episode.copy()
-            self._episode = saved + j
-            pj = self._sample(sel)
-            self._episode = saved
+            pj = self._sample_for(sel, self._episode + j)
             for r, k in enumerate(("bw", "lat", "queue", "loss", "start_rate")):
                 bank[j, r, sel] = pj[k][sel]
                 self.params[k][sel] = pj[k][sel]
@@ -279,6 +316,20 @@ class PccBatchEnv(object):
         _lib.check(self.L.pcc_step_host(self.h, p(actions_np), p(obs_np), p(reward_np), p(done_np),
                                         p(counts_np) if counts_np is not None else None, self._stream()))
         self._steps += 1
+
+    def step_host_submit(self, actions_np, obs_np, reward_np, done_np, counts_np=None):
+        """step_host split in two (pcc_step_host_submit / _wait): returns a ticket at once; the host buffers of a
+        ticket are complete after step_host_wait(ticket).  Two tickets may be in flight, each with its own buffers."""
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        t = C.c_int64()
+        _lib.check(self.L.pcc_step_host_submit(self.h, p(actions_np), p(obs_np), p(reward_np), p(done_np),
+                                               p(counts_np) if counts_np is not None else None, None, self._stream(),
+                                               C.byref(t)))
+        self._steps += 1
+        return t.value
+
+    def step_host_wait(self, ticket):
+        _lib.check(self.L.pcc_step_host_wait(self.h, int(ticket)))
 
     # -- observation / action space metadata (network_sim.py:376-388) -------------------------
     @property

@@ -362,7 +362,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
                                         PhiloxRng &rng, double dur, double *buf, int wbuf, WarpStage &stage, MiOut &mo,
                                         double &avg_lat, double &lat_inc, int32_t sent_before = 0,
                                         long long *prof = nullptr, double *gscratch = nullptr, PairOffer *offer = nullptr,
-                                        bool pair = PAIR, int bar0 = 1)
+                                        bool pair = PAIR, int bar0 = 1, uint32_t *mt = nullptr)
 {
     const unsigned lane = g.gl;
     const double end = s.cur_time + dur;            // network_sim.py:124
@@ -418,7 +418,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
             coop_send_chunks(g, true, sb, r0, bseed, bdraws, bend, binv, stage2, bt, bq, btu, btail, bh2, bsent, bovf);
 #else
             group_send_chunks(g, true, sb, r0, bseed, bdraws, bend, binv, *reinterpret_cast<SoloSendSmem *>(stage2), bt, bq,
-                              btu, btail, bh2, bsent, bovf);
+                              btu, btail, bh2, bsent, bovf, mt);
 #endif
             if (owner) {
                 c.t = bt; c.q = bq; c.tu = btu; c.tail = btail; c.sent += bsent; c.ovf = c.ovf || bovf;
@@ -515,7 +515,10 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
     if (owner) {
         if (which == 0) {
             s.cur_time = c.t;
-            lane_send_one(c, s, ring, s.h2, p.cap, inv_rate, rng.next());
+            double u;
+            if (mt != nullptr) { Mt19937Rng mr; mr.init(mt); u = mr.next(); }
+            else u = rng.next();
+            lane_send_one(c, s, ring, s.h2, p.cap, inv_rate, u);
         } else {
             s.cur_time = ct;
         }
@@ -672,6 +675,7 @@ struct PackedPartition {
     int32_t wbuf;             // staging capacity (samples) of a solo warp
 };
 #define PCC_PACKED_THREADS 128
+#define PCC_MT_WBUF 4096           // staging capacity (samples) of the MT19937 solo warp
 #ifndef PCC_PACKED_SOLO_WBUF
 #define PCC_PACKED_SOLO_WBUF 1024
 #endif
@@ -945,6 +949,34 @@ pcc_step_packed_kernel(DevState p, PackedPartition part, unsigned long long head
         q[9] = (double)(tend - prof[0]); q[10] = (double)gt0; q[11] = (double)gt1;
     }
 #endif
+}
+
+// MT19937 fidelity mode (the drop-in SimulatedNetworkEnv: CPython's generator, one env per call): one warp per env on the
+// cooperative single-env path, the loss draws of a chunk tempered in parallel from the generator state.  Round 1 ran this
+// mode on the scalar one-thread kernel (~300 us per step of dependent ring loads).
+__global__ void __launch_bounds__(32)
+pcc_step_solo_mt_kernel(DevState p, int wbuf, unsigned long long head_step, const double *__restrict__ actions,
+                        double *__restrict__ obs, double *__restrict__ reward, uint8_t *__restrict__ done,
+                        int32_t *__restrict__ counts, double *__restrict__ info)
+{
+    extern __shared__ double dyn_smem[];      // warp_smem_bytes(wbuf)
+    const Grp<32> g;
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t e = (int64_t)blockIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[META_HEAD] = head_step + 1ull;
+    const bool owner = lane == 0;
+    EnvState s;
+    load_env(p, e, s);
+    PhiloxRng rng;
+    rng.seed = 0ull; rng.draws = 0ull; rng.w2 = 0u; rng.w3 = 0u;
+    s.rate = apply_rate_delta(s.rate, actions[e], p.c);                              // :412
+    MiOut mo;
+    double avg_lat, lat_inc;
+    warp_mi<true, true, false>(g, p, owner, 1, e, s, rng, s.run_dur, dyn_smem, wbuf, *reinterpret_cast<WarpStage *>(dyn_smem),
+                               mo, avg_lat, lat_inc, 0, nullptr, p.mean_scratch ? p.mean_scratch + (size_t)e * PCC_GSCRATCH : nullptr,
+                               nullptr, false, 1, p.mt + (size_t)e * 625);           // :416
+    __syncwarp();
+    packed_emit(p, dyn_smem, owner, e, s, mo, avg_lat, lat_inc, p.draws[e], head_step, obs, reward, done, counts, info);
 }
 
 // predicted packets of the step about to run (its action applied): the sort key of the packed partition
@@ -1375,6 +1407,7 @@ struct pcc_handle_s {
     unsigned long long *cost64, *cum_excl, *target;
     int32_t *starts, *n_warps, *sent_tmp;
     bool split;
+    bool mt_scalar;           // MT19937 mode on the scalar one-thread kernel (PCC_B200_MODE=scalar) instead of the solo warp
     bool scalar_sorted;
     int wbuf, warp_threads;   // warp kernel: staging capacity per warp, threads per block
     bool pair;                // small batches: worker + helper warp per partition slot (pcc_step_warp_kernel<false, 1>)
@@ -1396,10 +1429,15 @@ struct pcc_handle_s {
     long long *ro_queue;
     int32_t *ro_ep;
     uint8_t *ro_mask;
-    // staging for pcc_step_host
-    double *st_actions, *st_obs, *st_reward;
-    uint8_t *st_done;
-    int32_t *st_counts;
+    // staging for pcc_step_host / pcc_step_host_submit: two slots, device -> host copies on a stream of their own
+    double *st_actions[2], *st_obs[2], *st_reward[2], *st_info[2];
+    uint8_t *st_done[2];
+    int32_t *st_counts[2];
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_step[2], ev_copy[2];
+    int64_t tickets;          // steps submitted through the host path so far
+    bool host_small;          // the last submission took the single-stream path (see pcc_step_host_submit)
+    cudaStream_t host_stream;
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -1548,7 +1586,13 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
     } else if (!grp) {
         h->group = small_batch ? 32 : 8;
     }
-    if (cfg->rng_kind != PCC_RNG_PHILOX) { h->group = 0; h->epw = 0; h->packed = false; }   // MT19937 (fidelity mode): scalar kernels
+    if (cfg->rng_kind != PCC_RNG_PHILOX) {   // MT19937 (fidelity mode): one warp per env (pcc_step_solo_mt_kernel)
+        h->group = 0; h->epw = 0; h->packed = false;
+        h->mt_scalar = mode && !strcmp(mode, "scalar");
+        cudaError_t ce = cudaFuncSetAttribute(pcc_step_solo_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)warp_smem_bytes(PCC_MT_WBUF));
+        if (ce != cudaSuccess) h->mt_scalar = true;
+    }
     {
         const char *wb = getenv("PCC_B200_WBUF");
         h->wbuf = wb ? atoi(wb) : (small_batch ? 4096 : 512);   // big batches: small shared buffer -> 16 warps/SM; heavy MIs stage to global scratch
@@ -1674,8 +1718,12 @@ void pcc_destroy(pcc_handle h)
 {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_reward);
-    cudaFree(h->st_done); cudaFree(h->st_counts);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(h->st_actions[i]); cudaFree(h->st_obs[i]);      // st_obs heads the slot's single staging block
+        if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
+        if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->perm); cudaFree(h->sort_tmp);
     cudaFree(h->cost64); cudaFree(h->cum_excl); cudaFree(h->target); cudaFree(h->starts); cudaFree(h->n_warps); cudaFree(h->sent_tmp); cudaFree(h->d.mean_scratch); cudaFree(h->n_solo_dev); cudaFree(h->sched);
     cudaFree(h->ro_obs); cudaFree(h->ro_par); cudaFree(h->ro_queue); cudaFree(h->ro_ep); cudaFree(h->ro_mask);
@@ -1868,9 +1916,12 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
     else if (h->cfg.rng_kind == PCC_RNG_PHILOX)
         pcc_step_kernel<PCC_RNG_PHILOX><<<grid_for(h), h->block, 0, st>>>(
             h->d, scalar_perm, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
-    else
+    else if (h->mt_scalar)
         pcc_step_kernel<PCC_RNG_MT19937><<<grid_for(h), h->block, 0, st>>>(
             h->d, nullptr, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
+    else
+        pcc_step_solo_mt_kernel<<<(unsigned)h->cfg.n_envs, 32, warp_smem_bytes(PCC_MT_WBUF), st>>>(
+            h->d, PCC_MT_WBUF, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
     h->head++;
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1955,30 +2006,93 @@ int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const 
     return PCC_OK;
 }
 
-int pcc_step_host(pcc_handle h, const double *actions_host, double *obs_host, double *reward_host,
-                  uint8_t *done_host, int32_t *counts_host, void *stream)
+// Device staging of one slot: ONE allocation laid out [obs | reward | info | counts | done] so that a caller whose host
+// buffers have the same layout (the drop-in single env) gets its results with a single copy.
+struct StageLayout { size_t obs, reward, info, counts, done, total; };
+static StageLayout stage_layout(size_t n, size_t hf)
+{
+    StageLayout L;
+    L.obs = 0; L.reward = 8 * n * hf; L.info = L.reward + 8 * n; L.counts = L.info + 8 * n * PCC_INFO_WIDTH;
+    L.done = L.counts + 12 * n; L.total = L.done + n;
+    return L;
+}
+#define PCC_HOST_SMALL_BYTES (64u << 10)   // below this a step's results are latency-, not bandwidth-bound
+
+int pcc_step_host_submit(pcc_handle h, const double *actions_host, double *obs_host, double *reward_host,
+                         uint8_t *done_host, int32_t *counts_host, double *info_host, void *stream, int64_t *ticket)
 {
     if (!h || !actions_host || !obs_host || !reward_host || !done_host) return fail(PCC_EINVAL, "null pointer");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)h->cfg.n_envs, hf = (size_t)h->cfg.history_len * h->cfg.n_features;
-    if (!h->st_actions) {
-        CUDA_TRY(cudaMalloc(&h->st_actions, 8 * n));
-        CUDA_TRY(cudaMalloc(&h->st_obs, 8 * n * hf));
-        CUDA_TRY(cudaMalloc(&h->st_reward, 8 * n));
-        CUDA_TRY(cudaMalloc(&h->st_done, n));
-        CUDA_TRY(cudaMalloc(&h->st_counts, 12 * n));
+    const StageLayout SL = stage_layout(n, hf);
+    if (!h->copy_stream) {
+        for (int i = 0; i < 2; i++) {
+            char *blk = nullptr;
+            CUDA_TRY(cudaMalloc(&h->st_actions[i], 8 * n));
+            CUDA_TRY(cudaMalloc(&blk, (SL.total + 255) & ~(size_t)255));
+            h->st_obs[i] = (double *)(blk + SL.obs); h->st_reward[i] = (double *)(blk + SL.reward);
+            h->st_info[i] = (double *)(blk + SL.info); h->st_counts[i] = (int32_t *)(blk + SL.counts);
+            h->st_done[i] = (uint8_t *)(blk + SL.done);
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     }
-    CUDA_TRY(cudaMemcpyAsync(h->st_actions, actions_host, 8 * n, cudaMemcpyHostToDevice, st));
-    int rc = pcc_step(h, h->st_actions, h->st_obs, h->st_reward, h->st_done,
-                      counts_host ? h->st_counts : nullptr, nullptr, stream);
+    const int slot = (int)(h->tickets & 1);
+    const bool small = SL.total <= PCC_HOST_SMALL_BYTES;
+    // small batches: everything on the caller's stream (no cross-stream events: each costs microseconds that a 30 us
+    // step notices); big ones: results travel on the copy stream so that the next submission does not queue behind them
+    cudaStream_t cs = small ? st : h->copy_stream;
+    // the slot's previous occupant (two submissions ago) must have left for the host before the kernel overwrites it
+    if (!small && h->tickets >= 2) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_copy[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(h->st_actions[slot], actions_host, 8 * n, cudaMemcpyHostToDevice, st));
+    int rc = pcc_step(h, h->st_actions[slot], h->st_obs[slot], h->st_reward[slot], h->st_done[slot],
+                      counts_host ? h->st_counts[slot] : nullptr, info_host ? h->st_info[slot] : nullptr, stream);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(obs_host, h->st_obs, 8 * n * hf, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(reward_host, h->st_reward, 8 * n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(done_host, h->st_done, n, cudaMemcpyDeviceToHost, st));
-    if (counts_host) CUDA_TRY(cudaMemcpyAsync(counts_host, h->st_counts, 12 * n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!small) {
+        CUDA_TRY(cudaEventRecord(h->ev_step[slot], st));
+        CUDA_TRY(cudaStreamWaitEvent(cs, h->ev_step[slot], 0));
+    }
+    char *host0 = (char *)obs_host;
+    const bool one_block = info_host && counts_host && (char *)reward_host == host0 + SL.reward &&
+                           (char *)info_host == host0 + SL.info && (char *)counts_host == host0 + SL.counts &&
+                           (char *)done_host == host0 + SL.done;
+    if (one_block) {
+        CUDA_TRY(cudaMemcpyAsync(host0, h->st_obs[slot], SL.total, cudaMemcpyDeviceToHost, cs));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(reward_host, h->st_reward[slot], 8 * n, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(done_host, h->st_done[slot], n, cudaMemcpyDeviceToHost, cs));
+        if (counts_host) CUDA_TRY(cudaMemcpyAsync(counts_host, h->st_counts[slot], 12 * n, cudaMemcpyDeviceToHost, cs));
+        if (info_host) CUDA_TRY(cudaMemcpyAsync(info_host, h->st_info[slot], 8 * n * PCC_INFO_WIDTH, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(obs_host, h->st_obs[slot], 8 * n * hf, cudaMemcpyDeviceToHost, cs));
+    }
+    if (!small) CUDA_TRY(cudaEventRecord(h->ev_copy[slot], cs));
+    h->host_small = small;
+    h->host_stream = st;
+    if (ticket) *ticket = h->tickets;
+    h->tickets++;
     return PCC_OK;
+}
+
+int pcc_step_host_wait(pcc_handle h, int64_t ticket)
+{
+    if (!h) return fail(PCC_EINVAL, "null handle");
+    if (ticket < 0 || ticket >= h->tickets) return fail(PCC_EINVAL, "unknown ticket");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->host_small) { CUDA_TRY(cudaStreamSynchronize(h->host_stream)); return PCC_OK; }
+    if (ticket + 2 < h->tickets) return PCC_OK;          // its slot has been reused: those copies finished long ago
+    CUDA_TRY(cudaEventSynchronize(h->ev_copy[ticket & 1]));
+    return PCC_OK;
+}
+
+int pcc_step_host(pcc_handle h, const double *actions_host, double *obs_host, double *reward_host,
+                  uint8_t *done_host, int32_t *counts_host, void *stream)
+{
+    int64_t t = 0;
+    int rc = pcc_step_host_submit(h, actions_host, obs_host, reward_host, done_host, counts_host, nullptr, stream, &t);
+    if (rc) return rc;
+    return pcc_step_host_wait(h, t);
 }
 
 int pcc_check(pcc_handle h, void *stream)

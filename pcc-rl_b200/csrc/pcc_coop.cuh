@@ -254,6 +254,77 @@ struct SoloSendSmem {
     double xs[64];         // x of the packets that reach the queue, compact; overwritten in place by y
 };
 
+// CPython's MT19937 (state mt[0..623] + position mt[624], laid out like random.getstate()[1]) as the
+// source of a chunk's loss draws, by a whole warp: draw k of the chunk is genrand_res53 of the stream words at positions
+// pos + 2k and pos + 2k + 1 -- tempering is per word, so the draws of a chunk are independent of each other; the
+// block regeneration (the "twist") runs in three phases of 32-wide steps whose reads all precede their writes.
+// Exactly `cnt` draws are consumed, which is why the caller counts the chunk's packets first.
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+__device__ __forceinline__ void mt_twist_warp(uint32_t *mt)
+{
+    const int lane = (int)(threadIdx.x & 31u);
+    for (int base = 0; base < 227; base += 32) {            // mt[kk] = mt[kk + 397] ^ f(mt[kk], mt[kk + 1]), old values
+        const int kk = base + lane;
+        const bool on = kk < 227;
+        uint32_t a = 0, b = 0, c = 0;
+        if (on) { a = mt[kk]; b = mt[kk + 1]; c = mt[kk + 397]; }
+        __syncwarp();
+        if (on) { const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu); mt[kk] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        __syncwarp();
+    }
+    for (int base = 227; base < 623; base += 32) {          // mt[kk] = NEW mt[kk - 227] ^ f(old mt[kk], old mt[kk + 1])
+        const int kk = base + lane;
+        const bool on = kk < 623;
+        uint32_t a = 0, b = 0, c = 0;
+        if (on) { a = mt[kk]; b = mt[kk + 1]; c = mt[kk - 227]; }
+        __syncwarp();
+        if (on) { const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu); mt[kk] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        const uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    __syncwarp();
+}
+// bit k of the result: draw k (k < cnt <= 64) of the chunk is < lr.  `tailbuf`: 128 words of shared scratch.
+__device__ __forceinline__ uint64_t mt_chunk_mask(uint32_t *mt, int cnt, uint64_t thr, uint32_t *tailbuf)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t pos = mt[624];
+    const bool cross = pos + 2u * (uint32_t)cnt > 624u;     // the chunk runs past the current block: regenerate
+    if (cross) {
+        const uint32_t ntail = 624u - pos;                   // < 128: the words of the old block still to be used
+        for (uint32_t i = lane; i < ntail; i += 32u) tailbuf[i] = mt[pos + i];
+        __syncwarp();
+        mt_twist_warp(mt);
+    }
+    unsigned m[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int k = (int)lane + 32 * u;
+        bool d = false;
+        if (k < cnt) {
+            const uint32_t i0 = pos + 2u * (uint32_t)k, i1 = i0 + 1u;
+            const uint32_t w0 = i0 < 624u ? (cross ? tailbuf[i0 - pos] : mt[i0]) : mt[i0 - 624u];
+            const uint32_t w1 = i1 < 624u ? (cross ? tailbuf[i1 - pos] : mt[i1]) : mt[i1 - 624u];
+            d = u53(mt_temper(w0), mt_temper(w1)) < thr;    // genrand_res53: a = first word >> 5, b = second >> 6
+        }
+        m[u] = __ballot_sync(PCC_FULL, d);
+    }
+    __syncwarp();
+    if (lane == 0 && cnt > 0) mt[624] = cross ? pos + 2u * (uint32_t)cnt - 624u : pos + 2u * (uint32_t)cnt;
+    __syncwarp();
+    return (uint64_t)m[0] | ((uint64_t)m[1] << 32);
+}
+
 template <int G>
 struct GroupSmemV2 {
     static constexpr bool kSendV2 = true;
@@ -265,8 +336,9 @@ template <int G, class Ring>
 __device__ __forceinline__ void group_send_chunks(const Grp<G> &g, bool alive, const EnvState &s, Ring &ring, uint64_t seed,
                                                   uint64_t &draws, double end, double inv_rate, SoloSendSmem &sm, double &t,
                                                   double &qd, double &t_upd, uint32_t &tail, uint32_t h2, int32_t &sent,
-                                                  bool &ovf)
+                                                  bool &ovf, uint32_t *mt = nullptr)
 {
+    // mt != nullptr (G == 32 only): the loss draws come from CPython's MT19937 state at `mt` instead of the Philox stream
     constexpr int NB = 32 / G;          // Philox blocks per lane and chunk
     constexpr int PPL = 64 / G;         // packets per lane and chunk
     const uint32_t cap = ring.capacity();
@@ -291,18 +363,8 @@ __device__ __forceinline__ void group_send_chunks(const Grp<G> &g, bool alive, c
     int b = 0;
     double q = qd, tu = t_upd;
     while (__any_sync(PCC_FULL, more)) {
-        const unsigned off = (unsigned)(draws & 1ull);
+        const unsigned off = (G == 32 && mt != nullptr) ? 0u : (unsigned)(draws & 1ull);
         const int navail = 64 - (int)off;
-        // S1: bit k of dm = packet k of the chunk is randomly dropped (:73)
-        unsigned be = 0u, bo = 0u;
-#pragma unroll
-        for (int j = 0; j < NB; j++) {
-            uint32_t c0, c1, c2, c3;
-            philox_block(seed, (draws >> 1) + (uint64_t)(j * G) + g.gl, c0, c1, c2, c3);
-            be |= g.ballot(u53(c0, c1) < thr) << (j * G);
-            bo |= g.ballot(u53(c2, c3) < thr) << (j * G);
-        }
-        const uint64_t dm = interleave_bits(be, bo) >> off;
         // S2: packets of this chunk that are sent in this MI (send times increase: a prefix)
         double tk[PPL];
         int cnt = 0;
@@ -316,6 +378,21 @@ __device__ __forceinline__ void group_send_chunks(const Grp<G> &g, bool alive, c
         if (more && (uint32_t)(tail - h2) + (uint32_t)cnt > cap) { ovf = true; fits = false; }   // fatal, reported by the host
         const bool work = more && fits;
         if (!work) cnt = 0;
+        // S1: bit k of dm = packet k of the chunk is randomly dropped (:73)
+        uint64_t dm;
+        if (G == 32 && mt != nullptr) {
+            dm = mt_chunk_mask(mt, cnt, thr, reinterpret_cast<uint32_t *>(&sm.xs[0]));   // xs is free until S3
+        } else {
+            unsigned be = 0u, bo = 0u;
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                uint32_t c0, c1, c2, c3;
+                philox_block(seed, (draws >> 1) + (uint64_t)(j * G) + g.gl, c0, c1, c2, c3);
+                be |= g.ballot(u53(c0, c1) < thr) << (j * G);
+                bo |= g.ballot(u53(c2, c3) < thr) << (j * G);
+            }
+            dm = interleave_bits(be, bo) >> off;
+        }
         const double t_after = sm.ts[b][navail];
         const bool next = work && (cnt == navail) && (t_after < end);
         const uint64_t sentm = (cnt >= 64) ? ~0ull : ((1ull << cnt) - 1ull);
@@ -336,25 +413,42 @@ __device__ __forceinline__ void group_send_chunks(const Grp<G> &g, bool alive, c
         double state = q;
         {
             const int niter = timer ? (next ? 64 : 0) : cnt_nd;
-            int kmax = (g.gl < 2) ? niter : 0;
+            int kmax = (g.gl < 2) ? niter : 0, kmin = (g.gl < 2 && niter > 0) ? niter : 64;   // idle lanes do not shorten the fast part
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(PCC_FULL, kmax, o); kmax = v > kmax ? v : kmax; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const int v = __shfl_xor_sync(PCC_FULL, kmax, o), u = __shfl_xor_sync(PCC_FULL, kmin, o);
+                kmax = v > kmax ? v : kmax;
+                kmin = u < kmin ? u : kmin;
+            }
             if (g.gl < 2) {
                 double *io = timer ? &sm.ts[b ^ 1][1] : &sm.xs[0];
                 if (timer) { state = t_after; if (next) sm.ts[b ^ 1][0] = t_after; }
+                const double state0 = state;
+                // [0, kmin): every WORKING chain and timer lane of the warp is inside its range -- no predicates on the
+                // chain (a lane with nothing to do computes on scratch values and restores its state afterwards)
 #pragma unroll 4
-                for (int k = 0; k < kmax; ++k) {
-                    const bool on = k < niter;
-                    const double x = io[k];
-                    const double y = state - x;                               // :66-67 | t + 1/rate
-                    if (on) io[k] = y;
+                for (int k = 0; k < kmin; ++k) {
+                    const double y = state - io[k];                           // :66-67 | t + 1/rate
+                    io[k] = y;
                     const double cpos = r_dbw + y;                            // :82 if 0 < y <= w_full
                     const bool pos = y > 0.0;
                     const bool fullp = y > r_wfull;                           // :77-79 (tail_drop_threshold)
+                    const double qn = fullp ? y : cpos;
+                    state = pos ? qn : k0;
+                }
+#pragma unroll 2
+                for (int k = kmin; k < kmax; ++k) {
+                    const bool on = k < niter;
+                    const double y = state - io[k];
+                    if (on) io[k] = y;
+                    const double cpos = r_dbw + y;
+                    const bool pos = y > 0.0;
+                    const bool fullp = y > r_wfull;
                     double qn = fullp ? y : cpos;
                     qn = pos ? qn : k0;
                     state = on ? qn : state;
                 }
+                if (niter == 0) state = state0;
             }
         }
         __syncwarp();
@@ -605,7 +699,7 @@ __device__ __forceinline__ void run_mi_coop(const Grp<G> &g, bool alive, EnvStat
             else { qd += s.d_bw; dropped = false; }
         }
         Rec r; r.a = t + ll; r.l = dropped ? negd(ll) : ll;
-        if ((uint32_t)(tail - h2) >= cap) ovf = true;
+        if ((uint32_t)(tail - out.s_begin) >= cap) ovf = true;   // s_begin, not the advanced h2: consumed records may be re-read for the means
         else { if (alive && g.gl == 0) ring.store(tail, r); tail++; }
         t = t + inv_rate;
     } else if (which == 1) {
@@ -763,29 +857,33 @@ struct LocalPwStack {
     __device__ __forceinline__ int &rn(int i) { return right_n[i]; }
     __device__ __forceinline__ double &ls(int i) { return left_sum[i]; }
 };
-template <int G>
-__device__ __noinline__ void means_groups_from_buf(const Grp<G> &g, bool on, const double *a, int n, bool need_increase,
-                                                   double &avg_lat, double &lat_increase)
+// numpy's pairwise sum of a[0..n) per 8-lane subgroup, the four subgroups of the warp in lock step on four DIFFERENT
+// arrays (four envs of a quad warp; or the three sums -- all, first half, second half -- of one env of a solo warp).
+// Warp-uniform call; subgroups with !on idle along.
+__device__ __noinline__ double pw_sum_subgroups(bool on, const double *a, int n)
 {
-    static_assert(G >= 8, "8 lanes hold numpy's 8 accumulators");
-    const int half = n / 2;
-    const int njobs = on ? ((need_increase && half >= 1) ? 3 : 1) : 0;
+    const unsigned lane = threadIdx.x & 31u;
+    const int j = (int)(lane & 7u);
     int rn[PCC_PW_STACK];
     double ls[PCC_PW_STACK];
     PwStream<NoAcc, LocalPwStack> m;
     m.stk.right_n = rn; m.stk.left_sum = ls;
-    int job = 0, joff = 0, consumed = 0;
-    double sum0 = 0.0, sum1 = 0.0, sum2 = 0.0;
-    bool active = njobs > 0;
+    bool active = on && n > 0;
+    int consumed = 0;
+    double total = 0.0;
     m.begin(active ? n : 0);
-    const int j = (int)(g.gl & 7u);
     while (__any_sync(PCC_FULL, active)) {
         const int c = active ? m.cur : 0;
-        const double *p = a + joff + consumed;
+        const double *p = a + consumed;
         const int nb = c - (c % 8);
         int nbmax = nb;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(PCC_FULL, nbmax, o); nbmax = v > nbmax ? v : nbmax; }
+        // the (up to 7) tail samples: loaded together with the blocks, added in order at the end
+        const int t0 = (c >= 8) ? nb : 0;
+        double tv[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) tv[k] = (t0 + k < c) ? p[t0 + k] : 0.0;
         double r = 0.0;
         if (c >= 8) r = p[j];
 #pragma unroll 8
@@ -794,12 +892,6 @@ __device__ __noinline__ void means_groups_from_buf(const Grp<G> &g, bool on, con
         r += __shfl_xor_sync(PCC_FULL, r, 1);    // (r0+r1) (r2+r3) (r4+r5) (r6+r7)
         r += __shfl_xor_sync(PCC_FULL, r, 2);    // ((r0+r1)+(r2+r3)) ((r4+r5)+(r6+r7))
         r += __shfl_xor_sync(PCC_FULL, r, 4);
-        if (G > 8) r = g.bcast(r, 0);
-        // the (up to 7) tail samples: loaded together, added in order
-        const int t0 = (c >= 8) ? nb : 0;
-        double tv[7];
-#pragma unroll
-        for (int k = 0; k < 7; k++) tv[k] = (t0 + k < c) ? p[t0 + k] : 0.0;
         double res = (c >= 8) ? r : 0.;
 #pragma unroll
         for (int k = 0; k < 7; k++) if (t0 + k < c) res += tv[k];
@@ -807,30 +899,64 @@ __device__ __noinline__ void means_groups_from_buf(const Grp<G> &g, bool on, con
             consumed += c;
             m.res = res;
             m.leaf_done();
-            if (m.done) {
-                if (job == 0) sum0 = m.total; else if (job == 1) sum1 = m.total; else sum2 = m.total;
-                job++;
-                if (job < njobs) {
-                    joff = (job == 2) ? half : 0;
-                    consumed = 0;
-                    m.begin(job == 1 ? half : n - half);
-                } else active = false;
-            }
+            if (m.done) { total = m.total; active = false; }
         }
+    }
+    __syncwarp();
+    return total;
+}
+
+// np.mean of n > 128 staged samples a[0..n) per group of a quad warp: three lock-step sweeps (all, first half, second
+// half).  Warp-uniform call; `on` selects the groups that take part.
+template <int G>
+__device__ __forceinline__ void means_groups_from_buf(const Grp<G> &g, bool on, const double *a, int n, bool need_increase,
+                                                      double &avg_lat, double &lat_increase)
+{
+    static_assert(G == 8, "one env per 8-lane subgroup");
+    const int half = n / 2;
+    const bool inc = on && need_increase && half >= 1;
+    const double sum0 = pw_sum_subgroups(on, a, n);
+    double sum1 = 0.0, sum2 = 0.0;
+    if (__any_sync(PCC_FULL, inc)) {
+        sum1 = pw_sum_subgroups(inc, a, half);
+        sum2 = pw_sum_subgroups(inc, a + half, n - half);
     }
     if (on) {
         double sum = 0.0;
         sum += sum0;
         avg_lat = sum / (double)n;                                              // sender_obs.py:119-122
         lat_increase = 0.0;
-        if (njobs == 3) {                                                       // :138-142
+        if (inc) {                                                              // :138-142
             double s1 = 0.0, s2 = 0.0;
             s1 += sum1;
             s2 += sum2;
             lat_increase = s2 / (double)(n - half) - s1 / (double)half;
         }
     }
-    __syncwarp();
+}
+
+// The same for ONE env owned by the whole warp (solo): its three sums run side by side on three subgroups.
+__device__ __forceinline__ void means_solo_from_buf(const double *a, int n, bool need_increase, double &avg_lat,
+                                                    double &lat_increase)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int sub = (int)(lane >> 3), half = n / 2;
+    const bool inc = need_increase && half >= 1;
+    const double *pa = (sub == 2) ? a + half : a;
+    const int cnt = (sub == 0) ? n : (sub == 1) ? half : (sub == 2) ? n - half : 0;
+    const bool on = sub == 0 || (inc && sub < 3);
+    const double sres = pw_sum_subgroups(on, pa, cnt);
+    const double tot = __shfl_sync(PCC_FULL, sres, 0), f1 = __shfl_sync(PCC_FULL, sres, 8), f2 = __shfl_sync(PCC_FULL, sres, 16);
+    double sum = 0.0;
+    sum += tot;
+    avg_lat = sum / (double)n;                                                  // sender_obs.py:119-122
+    lat_increase = 0.0;
+    if (inc) {                                                                  // :138-142
+        double s1 = 0.0, s2 = 0.0;
+        s1 += f1;
+        s2 += f2;
+        lat_increase = s2 / (double)(n - half) - s1 / (double)half;
+    }
 }
 
 // avg latency (sender_obs.py:119-122) and latency increase (:138-142) of the MI
@@ -842,7 +968,7 @@ __device__ __forceinline__ void mi_means_coop(const Grp<G> &g, bool alive, const
     int n = alive ? o.acked : 0;
     avg_lat = 0.0;
     lat_increase = 0.0;
-    if (gbuf != nullptr) {   // warp-uniform: staged samples of MIs with more than one leaf
+    if constexpr (G == 8) if (gbuf != nullptr) {   // warp-uniform: staged samples of MIs with more than one leaf
         const bool use_g = n > PCC_LEAF && n <= gcap;
         if (__any_sync(PCC_FULL, use_g)) means_groups_from_buf(g, use_g, gbuf, n, need_increase, avg_lat, lat_increase);
         if (use_g) n = 0;    // done

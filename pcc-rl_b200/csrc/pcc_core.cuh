@@ -408,8 +408,10 @@ PCC_HD void run_mi(EnvState &s, Ring &ring, Rng &rng, double dur, MiOut &out, bo
     // ring must hold  in-flight at MI start + packets sent in the MI.  The host sizes it from
     // the declared parameter ranges (1.5 * max_rate * max RTT); exceeding it is a fatal,
     // reported error -- the packet is counted but its record is lost.
+    // (capacity is measured from the MI-START hop-2 cursor out.s_begin: with `prescan` the cursor has already moved,
+    // but the records it passed are re-read for the means at the end of the MI and must not be overwritten)
     while (t < end) {
-        if ((uint32_t)(tail - h2) >= cap) { out.overflow = true; tail--; }
+        if ((uint32_t)(tail - out.s_begin) >= cap) { out.overflow = true; tail--; }
         PCC_SEND_ONE();
     }
 
@@ -437,7 +439,7 @@ PCC_HD void run_mi(EnvState &s, Ring &ring, Rng &rng, double dur, MiOut &out, bo
     else which = 0;
     if (which == 0) {
         s.cur_time = t;
-        if ((uint32_t)(tail - h2) >= cap) { out.overflow = true; tail--; }
+        if ((uint32_t)(tail - out.s_begin) >= cap) { out.overflow = true; tail--; }
         PCC_SEND_ONE();
     } else if (which == 1) {
         s.cur_time = m1a;

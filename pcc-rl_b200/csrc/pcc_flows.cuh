@@ -645,6 +645,9 @@ pcc_flows_long_kernel(FlowsDev p, BatchDev b, uint32_t batch_no, double *__restr
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int H = p.H, F = p.F, HF = H * F;
+    // the batch counter travels with the workspace: a handle attached to it later (checkpoint / resume) continues the
+    // numbering, so the per-flow stamps of earlier batches can never equal a new batch's number
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta[2] = (unsigned long long)batch_no;
     for (long long base = warp * 32; base < b.R; base += nwarps * 32) {
         const long long mine = base + lane;
         bool is_long = false;
@@ -949,6 +952,11 @@ static int flows_build(pcc_flows_handle *out, const pcc_flows_config *cfg, void 
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "flows init: %s", cudaGetErrorString(e)); }
         h->launches++;
+    } else {
+        unsigned long long bn = 0;
+        cudaError_t e = cudaMemcpy(&bn, d.meta + 2, 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "flows attach: %s", cudaGetErrorString(e)); }
+        h->batch_no = (uint32_t)bn;
     }
     *out = h;
     return PCC_OK;

@@ -337,7 +337,7 @@ __device__ __forceinline__ void packed_mi(const RingSet &rs, PackedSmem &sm, boo
         if (which == 0) {
             s.cur_time = t;
             const bool d = rng.next();
-            PCC_PACKED_SEND(d, if ((uint32_t)(tail - h2) >= rs.cap) ovf = true; else { ring.store(tail, Rec{rec_.x, rec_.y}); tail++; });
+            PCC_PACKED_SEND(d, if ((uint32_t)(tail - s_begin) >= rs.cap) ovf = true; else { ring.store(tail, Rec{rec_.x, rec_.y}); tail++; });   /* s_begin, not h2: the consumed records are re-read for the means */
         } else if (which == 1) {
             s.cur_time = m1.t;
             if (m1.idx == h1) h1++; else tring.store_a(m1.idx, negd(m1.t));

@@ -490,7 +490,12 @@ __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut
         }
         __syncwarp();
     } else if (n <= wbuf) {
+#ifdef PCC_MEANS_V1
         means_from_smem(buf, ls, n, need_increase, avg_lat, lat_increase);
+#else
+        (void)ls;
+        means_solo_from_buf(buf, n, need_increase, avg_lat, lat_increase);
+#endif
     } else {
         mi_means_stream(co, ring, dl, smem_buf, need_increase, avg_lat, lat_increase);
     }

@@ -241,6 +241,7 @@ def configure(agent_factory=None, history_len=10, features=sender_obs.DEFAULT_FE
     _agent_factory, _history_len, _features, MAX_FLOWS = agent_factory, history_len, features, max_flows
     _monitor = None
     PccGymDriver.flow_lookup = {}
+    PccGymDriver.next_slot = 0
 
 
 def _get_monitor():
@@ -252,13 +253,21 @@ def _get_monitor():
 
 class PccGymDriver(object):
     flow_lookup = {}
+    next_slot = 0          # slots are handed out once and never shared: a flow id keeps its slot across re-inits
 
     def __init__(self, flow_id):
         self.id = flow_id
         self.mon = _get_monitor()
-        self.slot = len(PccGymDriver.flow_lookup)
-        if self.slot >= self.mon.n_flows:
-            raise RuntimeError("more than %d flows: raise max_flows in configure()" % self.mon.n_flows)
+        prev = PccGymDriver.flow_lookup.get(flow_id)
+        if prev is not None:
+            # init(flow_id) for an id that exists (loaded_client.py:173-175 replaces the dict entry): same GPU slot, fresh
+            # history -- and, like the reference's module-level _conn_min_latencies, the flow's connection-min entry stays
+            self.slot, mode = prev.slot, _lib.PCC_FLOW_RESET_CLIENT
+        else:
+            self.slot, mode = PccGymDriver.next_slot, _lib.PCC_FLOW_RESET_NEW
+            if self.slot >= self.mon.n_flows:
+                raise RuntimeError("more than %d flows: raise max_flows in configure()" % self.mon.n_flows)
+            PccGymDriver.next_slot += 1
         self.rate = random.uniform(RESET_RATE_MIN, RESET_RATE_MAX)      # :51
         self.history_len = self.mon.history_len
         self.features = self.mon.features
@@ -266,7 +275,7 @@ class PccGymDriver(object):
         self.agent = _agent_factory() if _agent_factory is not None else None
         self._sel = np.zeros(self.mon.n_flows, dtype=np.uint8)
         self._sel[self.slot] = 1
-        self.mon.reset(mask=self._sel, mode=_lib.PCC_FLOW_RESET_NEW)
+        self.mon.reset(mask=self._sel, mode=mode)
         self.mon.set_rates(rate=self.rate, mask=self._sel)
         PccGymDriver.flow_lookup[flow_id] = self
 

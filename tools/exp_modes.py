@@ -46,5 +46,6 @@ def run(n, setting, K=60, W=30, seed=100):
 
 if __name__ == "__main__":
     n = int(sys.argv[1])
+    W = int(os.environ.get("EXP_WARMUP", "30"))      # the timed window starts at this step of the episode
     for s in sys.argv[2:]:
-        run(n, s)
+        run(n, s, W=W)

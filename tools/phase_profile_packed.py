@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pcc_rl_b200
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60      # the profile is taken at the last 3 of these steps of the episode
 env = pcc_rl_b200.PccBatchEnv(n_envs=n, seed=100, want_info=True, auto_reset=False)
 env.reset()
 g = torch.Generator(device=env.device); g.manual_seed(101)
