@@ -221,8 +221,12 @@ class PccBatchEnv(object):
         if not torch.is_tensor(a):
             a = torch.as_tensor(np.asarray(a, dtype=np.float64))
         a = a.reshape(self.n_envs)
-        self._actions.copy_(a, non_blocking=True)
-        _lib.check(self.L.pcc_step(self.h, self._actions.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+        if a.dtype == torch.float64 and a.device == self.device and a.is_contiguous():
+            self._keep_actions = a            # already where the kernel reads it: no staging copy
+        else:
+            self._actions.copy_(a, non_blocking=True)
+            a = self._actions
+        _lib.check(self.L.pcc_step(self.h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
                                    self.done.data_ptr(), self.counts.data_ptr(),
                                    self.info.data_ptr() if self.info is not None else None, self._stream()))
         self._steps += 1

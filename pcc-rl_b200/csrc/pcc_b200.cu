@@ -797,11 +797,21 @@ pcc_step_packed_kernel(DevState p, PackedPartition part, unsigned long long head
     const int nqw = (n_quad + 3) / 4;                                                 // quad warps
     int64_t pos_packed = (int64_t)n_solo + 4 * (int64_t)nqw;                          // first sorted position of the packed part
     if (pos_packed > p.n) pos_packed = p.n;
-    // launch order: the unit this warp runs (pcc_schedule_kernel: longest estimated run time first, whatever its role)
-    if (w >= part.counts[2]) return;                                                  // whole warp
-    const uint32_t unit = part.sched[w];
-    const int role = (int)(unit >> 28);
-    const int64_t uj = (int64_t)(unit & 0x0fffffffu);
+    // launch order: the unit this warp runs.  Default: role order -- solo, quad, lanes, each heaviest first --, computed
+    // here; with a schedule (pcc_schedule_kernel: longest estimated run time first across the roles) looked up
+    int role;
+    int64_t uj;
+    if (part.sched != nullptr) {
+        if (w >= part.counts[2]) return;                                              // whole warp
+        const uint32_t unit = part.sched[w];
+        role = (int)(unit >> 28);
+        uj = (int64_t)(unit & 0x0fffffffu);
+    } else {
+        const int nqw_eff = (int)((pos_packed - n_solo + 3) / 4);
+        if (w < n_solo) { role = 0; uj = w; }
+        else if (w < (int64_t)n_solo + nqw_eff) { role = 1; uj = w - n_solo; }
+        else { role = 2; uj = w - n_solo - nqw_eff; }
+    }
     if (role == 1) {
         // ---- four envs of similar (medium / heavy) work, 8 lanes each: the group-cooperative MI of pcc_coop.cuh with the
         // second-generation send phase; the four chain lanes share one instruction stream
@@ -1099,10 +1109,43 @@ __device__ __noinline__ double policy_action(PolicyDev pol, const double *hrow, 
     return mlp_eval(pol.w1, pol.b1, pol.w2, pol.b2, pol.w3, pol.b3, pol.n_in, pol.h1, pol.h2, obs_row);
 }
 
-// One thread per env: action = pi(obs) [+ exp(log_std) * N(0,1), Box-Muller on a Philox block keyed by (noise_seed;
-// env, step t)], vpred = V(obs).  obs rows are the current observations, oldest -> newest.
-__global__ void pcc_policy_kernel(PolicyDev pol, int64_t n, const double *__restrict__ obs, unsigned long long t,
-                                  double *__restrict__ act_out, double *__restrict__ vpred_out)
+// The same network by a whole warp for ONE env: lane i owns hidden unit i (and i + 32), the inputs of a layer travel by
+// shuffle, every sum runs over j ascending from the bias (the order of mlp_eval).  ~80 dependent steps instead of ~1 500.
+__device__ __forceinline__ double mlp_eval_warp(const double *__restrict__ w1, const double *__restrict__ b1,
+                                                const double *__restrict__ w2, const double *__restrict__ b2,
+                                                const double *__restrict__ w3, const double *__restrict__ b3, int n_in, int h1,
+                                                int h2, const double (&x)[4])
+{
+    const int lane = (int)(threadIdx.x & 31u);
+    double a1[2], a2[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {                       // layer 1: units lane, lane + 32
+        const int i = lane + 32 * u;
+        double acc = (i < h1) ? b1[i] : 0.0;
+        for (int j = 0; j < n_in; j++) {
+            const double xj = __shfl_sync(PCC_FULL, (j >> 5) == 0 ? x[0] : (j >> 5) == 1 ? x[1] : (j >> 5) == 2 ? x[2] : x[3], j & 31);
+            if (i < h1) acc += w1[i * n_in + j] * xj;
+        }
+        a1[u] = (i < h1) ? tanh(acc) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {                       // layer 2
+        const int i = lane + 32 * u;
+        double acc = (i < h2) ? b2[i] : 0.0;
+        for (int j = 0; j < h1; j++) {
+            const double aj = __shfl_sync(PCC_FULL, (j >> 5) ? a1[1] : a1[0], j & 31);
+            if (i < h2) acc += w2[i * h1 + j] * aj;
+        }
+        a2[u] = (i < h2) ? tanh(acc) : 0.0;
+    }
+    double out = b3[0];                                  // output: the same ascending sum on every lane
+    for (int j = 0; j < h2; j++) out += w3[j] * __shfl_sync(PCC_FULL, (j >> 5) ? a2[1] : a2[0], j & 31);
+    return out;
+}
+
+// One THREAD per env (big batches: every weight load is a warp-wide broadcast, all lanes busy)
+__global__ void pcc_policy_thread_kernel(PolicyDev pol, int64_t n, const double *__restrict__ obs, unsigned long long t,
+                                         double *__restrict__ act_out, double *__restrict__ vpred_out)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -1120,6 +1163,35 @@ __global__ void pcc_policy_kernel(PolicyDev pol, int64_t n, const double *__rest
     }
     if (vpred_out && pol.vw1)
         vpred_out[e] = mlp_eval(pol.vw1, pol.vb1, pol.vw2, pol.vb2, pol.vw3, pol.vb3, pol.n_in, pol.h1, pol.h2, row);
+}
+
+// One WARP per env (small batches: latency): action = pi(obs) [+ exp(log_std) * N(0,1), Box-Muller on a Philox block
+// keyed by (noise_seed; env, step t)], vpred = V(obs).  obs rows are the current observations, oldest -> newest.  Both
+// kernels sum in the same order, so a batch gives the same actions whichever runs.
+__global__ void __launch_bounds__(128)
+pcc_policy_kernel(PolicyDev pol, int64_t n, const double *__restrict__ obs, unsigned long long t,
+                  double *__restrict__ act_out, double *__restrict__ vpred_out)
+{
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= n) return;                                  // whole warp
+    const int lane = (int)(threadIdx.x & 31u);
+    double x[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) x[u] = (lane + 32 * u < pol.n_in) ? obs[(size_t)e * pol.n_in + lane + 32 * u] : 0.0;
+    if (act_out && pol.w1) {
+        double out = mlp_eval_warp(pol.w1, pol.b1, pol.w2, pol.b2, pol.w3, pol.b3, pol.n_in, pol.h1, pol.h2, x);
+        if (pol.stochastic) {
+            uint32_t c0 = (uint32_t)e, c1 = (uint32_t)(e >> 32), c2 = (uint32_t)t, c3 = 0x4e4f4953u;   // 'NOIS'
+            philox4x32_10(c0, c1, c2, c3, (uint32_t)pol.noise_seed, (uint32_t)(pol.noise_seed >> 32));
+            const double u1 = (res53(c0, c1) + 1.1102230246251565e-16), u2 = res53(c2, c3);
+            out += exp(pol.log_std) * sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        }
+        if (lane == 0) act_out[e] = out;
+    }
+    if (vpred_out && pol.vw1) {
+        const double v = mlp_eval_warp(pol.vw1, pol.vb1, pol.vw2, pol.vb2, pol.vw3, pol.vb3, pol.n_in, pol.h1, pol.h2, x);
+        if (lane == 0) vpred_out[e] = v;
+    }
 }
 
 // SenderHistory.as_array of every env (oldest -> newest) from the history ring: the rollout's first observation
@@ -1421,8 +1493,10 @@ struct pcc_handle_s {
     int quad_packets;         // predicted packets above which an env is run by 8 lanes (four envs per warp)
     int n_solo_cap, n_quad_cap;
     int32_t *n_solo_dev;      // [2][4] device counters (solo, quad, units), alternating between rebalances
-    uint32_t *sched;          // launch order of the work units
+    uint32_t *sched;          // launch order of the work units (experiment: PCC_B200_SCHED_COST=solo;quad;lanes cycles per packet)
     SchedCost sched_cost;
+    bool use_sched;
+    int64_t uniform_steps;    // steps every env has taken since a reset of ALL envs, or -1 when the envs may differ
     int reb_parity;
     // scratch of pcc_rollout: current observations, parameters / mask / episode index of the per-step masked reset
     double *ro_obs, *ro_par;      // [n][H*F]; [4][n] bw, delay, loss, start_rate
@@ -1663,7 +1737,7 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         h->split = sp ? atoi(sp) != 0 : false;   // two-kernel variant: measured slower, kept for experiments
         if (h->packed) {
             const char *pe = getenv("PCC_B200_PACKED_EVERY"), *so = getenv("PCC_B200_SOLO");
-            h->packed_every = pe ? atoi(pe) : 1;
+            h->packed_every = pe ? atoi(pe) : 4;   // measured: 1: 0.62, 3-4: 0.59, 8: 0.62, 16: 0.71 ms per step (predictions age slowly, the sort is not free)
             if (h->packed_every < 1) h->packed_every = 1;
             const char *qu = getenv("PCC_B200_QUAD");
             h->solo_packets = so ? atoi(so) : 1200;
@@ -1681,7 +1755,8 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
             if (ce == cudaSuccess) ce = cudaMalloc(&h->sched, sizeof(uint32_t) * (size_t)(h->n_solo_cap + (h->n_quad_cap + 3) / 4 + (n + 31) / 32 + 8));
             // estimated cycles per packet of a unit's heaviest env, per role (B200, 65 536 envs, profiles/r02_phase_profile_packed.txt)
             const char *cs = getenv("PCC_B200_SCHED_COST");
-            h->sched_cost = SchedCost{1e9f, 1e5f, 1.0f};   // role order; a merged order (225;755;2900) measured no better
+            h->sched_cost = SchedCost{225.0f, 755.0f, 2900.0f};
+            h->use_sched = cs != nullptr;    // default: role order (a merged longest-first order measured no better)
             if (cs && sscanf(cs, "%f;%f;%f", &h->sched_cost.solo, &h->sched_cost.quad, &h->sched_cost.lanes) != 3)
                 sscanf(cs, "%f,%f,%f", &h->sched_cost.solo, &h->sched_cost.quad, &h->sched_cost.lanes);
             if (ce == cudaSuccess)
@@ -1700,6 +1775,7 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
         cudaError_t e = cudaMemcpy(&head, d.meta + META_HEAD, 8, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "attach: %s", cudaGetErrorString(e)); }
         h->head = head;
+        h->uniform_steps = -1;    // an adopted workspace: the envs may be anywhere in their episodes
     }
     *out = h;
     return PCC_OK;
@@ -1784,6 +1860,7 @@ int pcc_reset(pcc_handle h, const uint8_t *mask_dev, const double *bw_dev, const
 #define PCC_RESET_WARP(E_) pcc_reset_warp_kernel<E_><<<wgrid, PCC_WARP_THREADS, 0, st>>>( \
         h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rate_dev, obs_dev)
     h->rebalance_now = true;
+    h->uniform_steps = mask_dev ? -1 : 0;
     if (h->epw == 4) PCC_RESET_WARP(4);
     else if (h->epw == 8) PCC_RESET_WARP(8);
     else if (h->epw == 16) PCC_RESET_WARP(16);
@@ -1853,15 +1930,19 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
                 h->n_solo_dev + 4 * h->reb_parity, h->n_solo_dev + 4 * (h->reb_parity ^ 1));
             CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp, h->sort_tmp_bytes, h->sort_keys_in,
                                                                h->sort_keys_out, h->sort_vals_in, h->perm, (int)n, 0, 16, st));
-            const int64_t max_units = (int64_t)h->n_solo_cap + (h->n_quad_cap + 3) / 4 + (n + 31) / 32;
-            pcc_schedule_kernel<<<(unsigned)((max_units + 255) / 256), 256, 0, st>>>(
-                h->sort_keys_out, n, h->n_solo_dev + 4 * h->reb_parity, h->n_solo_cap, h->n_quad_cap, h->sched_cost, h->sched);
+            if (h->use_sched) {
+                const int64_t max_units = (int64_t)h->n_solo_cap + (h->n_quad_cap + 3) / 4 + (n + 31) / 32;
+                pcc_schedule_kernel<<<(unsigned)((max_units + 255) / 256), 256, 0, st>>>(
+                    h->sort_keys_out, n, h->n_solo_dev + 4 * h->reb_parity, h->n_solo_cap, h->n_quad_cap, h->sched_cost, h->sched);
+                h->launches++;
+            }
             h->rebalance_now = false;
             h->steps_since_rebalance = 0;
-            h->launches += 3;
+            h->launches += 2;
         }
         h->steps_since_rebalance++;
-        PackedPartition pp{h->perm, h->sched, h->n_solo_dev + 4 * h->reb_parity, h->n_solo_cap, h->n_quad_cap, PCC_PACKED_SOLO_WBUF};
+        PackedPartition pp{h->perm, h->use_sched ? h->sched : nullptr, h->n_solo_dev + 4 * h->reb_parity, h->n_solo_cap,
+                           h->n_quad_cap, PCC_PACKED_SOLO_WBUF};
         const int wpb = PCC_PACKED_THREADS / 32;
         const int64_t nwarps = (int64_t)h->n_solo_cap + (h->n_quad_cap + 3) / 4 + (n + 31) / 32;
         pcc_step_packed_kernel<<<(unsigned)((nwarps + wpb - 1) / wpb), PCC_PACKED_THREADS, wpb * packed_warp_smem_bytes(), st>>>(
@@ -1924,6 +2005,7 @@ int pcc_step(pcc_handle h, const double *actions_dev, double *obs_dev, double *r
             h->d, PCC_MT_WBUF, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev, info_dev);
     h->head++;
     h->launches++;
+    if (h->uniform_steps >= 0) h->uniform_steps++;
     CUDA_TRY(cudaGetLastError());
     return PCC_OK;
 }
@@ -1966,7 +2048,8 @@ int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const 
         pol.log_std = policy->log_std; pol.noise_seed = policy->noise_seed; pol.stochastic = policy->stochastic;
     }
     const bool eval = pol.w1 || pol.vw1;
-    const unsigned eg = (unsigned)((n + 127) / 128);
+    const unsigned eg = (unsigned)((n * 32 + 127) / 128);   // one warp per env ...
+    const bool per_thread = n >= 16384;                     // ... or one thread per env when there are enough envs to fill the GPU that way
     if (eval) {   // the observation the first action is computed from
         pcc_obs_from_hist_kernel<<<(unsigned)((n * HF + 255) / 256), 256, 0, st>>>(h->d, h->head, h->ro_obs);
         h->launches++;
@@ -1977,8 +2060,12 @@ int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const 
         const size_t kn = (size_t)k * n;
         const double *act = actions_dev ? actions_dev + kn : actions_out_dev + kn;
         if (eval) {
-            pcc_policy_kernel<<<eg, 128, 0, st>>>(pol, (int64_t)n, h->ro_obs, h->head, pol.w1 ? actions_out_dev + kn : nullptr,
-                                                 pol.vw1 ? vpred_dev + kn : nullptr);
+            if (per_thread)
+                pcc_policy_thread_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(pol, (int64_t)n, h->ro_obs, h->head,
+                    pol.w1 ? actions_out_dev + kn : nullptr, pol.vw1 ? vpred_dev + kn : nullptr);
+            else
+                pcc_policy_kernel<<<eg, 128, 0, st>>>(pol, (int64_t)n, h->ro_obs, h->head, pol.w1 ? actions_out_dev + kn : nullptr,
+                                                     pol.vw1 ? vpred_dev + kn : nullptr);
             h->launches++;
         }
         if (actions_dev && actions_out_dev)
@@ -1986,7 +2073,11 @@ int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const 
         int rc = pcc_step(h, act, h->ro_obs, reward_dev + kn, done_dev + kn, counts_dev ? counts_dev + 3 * kn : nullptr,
                           nullptr, stream);
         if (rc) return rc;
-        if (n_episodes > 0) {
+        // when every env has taken the same number of steps (the usual case: all reset together) the host knows at
+        // which step the episodes end and skips the two launches everywhere else
+        const bool may_finish = h->uniform_steps < 0 || h->uniform_steps >= (int64_t)h->cfg.consts.max_steps;
+        if (n_episodes > 0 && may_finish) {
+            const bool all_finish = h->uniform_steps >= 0;
             // finished envs start their next episode with the next row of the bank (network_sim.py:469-484)
             pcc_bank_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d, done_dev + kn, reset_params_dev, n_episodes,
                                                                              h->ro_ep, h->ro_mask, bw, dl, h->ro_queue, loss, rate);
@@ -1994,12 +2085,17 @@ int pcc_rollout(pcc_handle h, int32_t n_steps, const double *actions_dev, const 
             const bool reb = h->rebalance_now;
             rc = pcc_reset(h, h->ro_mask, bw, dl, (const int64_t *)h->ro_queue, loss, rate, h->ro_obs, stream);
             if (rc) return rc;
-            if (!h->packed) h->rebalance_now = reb;   // a stale partition is only slower; the periodic rebalance picks the resets up
+            if (!h->packed && !all_finish) h->rebalance_now = reb;   // a stale partition is only slower; the periodic rebalance picks the resets up
+            if (all_finish) h->uniform_steps = 0;            // the masked reset just reset every env
         }
         if (obs_dev) CUDA_TRY(cudaMemcpyAsync(obs_dev + kn * HF, h->ro_obs, 8 * n * (size_t)HF, cudaMemcpyDeviceToDevice, st));
     }
     if (pol.vw1) {   // V(observation after the last step): PPO1's nextvpred (before the (1 - new) factor)
-        pcc_policy_kernel<<<eg, 128, 0, st>>>(pol, (int64_t)n, h->ro_obs, h->head, nullptr, vpred_dev + (size_t)n_steps * n);
+        if (per_thread)
+            pcc_policy_thread_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(pol, (int64_t)n, h->ro_obs, h->head, nullptr,
+                                                                           vpred_dev + (size_t)n_steps * n);
+        else
+            pcc_policy_kernel<<<eg, 128, 0, st>>>(pol, (int64_t)n, h->ro_obs, h->head, nullptr, vpred_dev + (size_t)n_steps * n);
         h->launches++;
     }
     CUDA_TRY(cudaGetLastError());
