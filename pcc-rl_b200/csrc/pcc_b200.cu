@@ -194,16 +194,27 @@ __device__ __forceinline__ void coop_emit(const Grp<G> &g, const DevState &p, in
     const int slot_new = (int)(head_step % (unsigned long long)H);
     double *hrow = p.hist + (size_t)e * HF;
     double *ob = obs + (size_t)e * HF;
-    for (int k = (int)g.gl; k < HF; k += G) {
-        const int h = k / F, f = k - h * F;
-        double v;
-        if (h == H - 1) v = metric_value(st, p.ids[f]);
-        else {
-            int slot = slot_new + 1 + h;
-            if (slot >= H) slot -= H;
-            v = hrow[slot * F + f];
+    for (int base = (int)g.gl; base < HF; base += 4 * G) {     // four history reads in flight before their stores
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = base + u * G;
+            v[u] = 0.0;
+            if (k < HF) {
+                const int h = k / F, f = k - h * F;
+                if (h == H - 1) v[u] = metric_value(st, p.ids[f]);
+                else {
+                    int slot = slot_new + 1 + h;
+                    if (slot >= H) slot -= H;
+                    v[u] = hrow[slot * F + f];
+                }
+            }
         }
-        ob[k] = v;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = base + u * G;
+            if (k < HF) ob[k] = v[u];
+        }
     }
     g.gsync();
     if ((int)g.gl < F) hrow[slot_new * F + (int)g.gl] = metric_value(st, p.ids[g.gl]);
@@ -824,6 +835,11 @@ pcc_step_packed_kernel(DevState p, PackedPartition part, unsigned long long head
         GroupSmemV2<8> &sm = reinterpret_cast<GroupSmemV2<8> *>(wsm)[grp];
         EnvState s;
         load_env(p, e, s);
+        {   // what the epilogue reads (history row, episode return) travels to L2 while the MI runs
+            const int HFq = p.H * p.F;
+            if (g.gl * 16 < (unsigned)HFq) prefetch_l2_line(p.hist + (size_t)e * HFq + g.gl * 16);
+            if (g.gl == 7) prefetch_l2_line(p.ret_acc + e);
+        }
         DevRing ring{p.rings + (size_t)e * p.cap, p.cap - 1u};
         const uint64_t seed = p.seed[e];
         uint64_t draws = p.draws[e];
@@ -930,6 +946,13 @@ pcc_step_packed_kernel(DevState p, PackedPartition part, unsigned long long head
     const int64_t e = owner ? (int64_t)part.perm[first + lane] : 0;
     EnvState s;
     load_env(p, e, s);
+    if (owner) {   // what the epilogue reads travels to L2 while the MI runs
+        const int HFp = p.H * p.F;
+        prefetch_l2_line(p.hist + (size_t)e * HFp);
+        prefetch_l2_line(p.hist + (size_t)e * HFp + 16);
+        if (HFp > 32) prefetch_l2_line(p.hist + (size_t)e * HFp + 32);
+        prefetch_l2_line(p.ret_acc + e);
+    }
     s.rate = apply_rate_delta(s.rate, actions[e], p.c);                              // :412
     LaneDraws rng;
     rng.init(p.seed[e], p.draws[e], s.lr);
@@ -1740,10 +1763,10 @@ static int build_handle(pcc_handle *out, const pcc_config *cfg, void *state_dev,
             h->packed_every = pe ? atoi(pe) : 4;   // measured: 1: 0.62, 3-4: 0.59, 8: 0.62, 16: 0.71 ms per step (predictions age slowly, the sort is not free)
             if (h->packed_every < 1) h->packed_every = 1;
             const char *qu = getenv("PCC_B200_QUAD");
-            h->solo_packets = so ? atoi(so) : 1200;
+            h->solo_packets = so ? atoi(so) : 1600;
             if (h->solo_packets < 32) h->solo_packets = 32;
             if (h->solo_packets > 65534) h->solo_packets = 65534;
-            h->quad_packets = qu ? atoi(qu) : 192;
+            h->quad_packets = qu ? atoi(qu) : 128;
             if (h->quad_packets < 8) h->quad_packets = 8;
             if (h->quad_packets > h->solo_packets) h->quad_packets = h->solo_packets;
             h->n_solo_cap = (int)(n / 32 > 64 ? n / 32 : 64);
