@@ -596,10 +596,13 @@ def main():
                 env.step(ag)
             torch.cuda.synchronize(dev)
             bs, be = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tb0 = time.perf_counter()
             bs.record()
             env.step(ag)
             be.record()
             torch.cuda.synchronize(dev)
+            if os.environ.get("PCC_BENCH_DEBUG"):
+                sys.stderr.write("boundary: wall %.2f ms, events %.2f ms\n" % (1e3 * (time.perf_counter() - tb0), bs.elapsed_time(be)))
             boundary_ms = D.max_over_ranks(bs.elapsed_time(be), dev)
             finished.append(env.column("last_episode_return"))
             env.check()
@@ -742,10 +745,10 @@ def main():
                    "actions": "N(0,1) pre-generated on device", "auto_reset": True,
                    "episode_boundary": ("inside the timed window (that step took %.3f ms, the median step %.3f ms)"
                                         % (p1["reset_step_ms"], p1["median_step_ms"])) if p1["boundary_inside"] else
-                                       ("outside the %d-step window (steps %d.. of a 400-step episode); timed separately: the "
-                                        "boundary step takes %.3f ms, the median step %.3f ms -> %.1f M env-steps/s over a "
-                                        "whole episode" % (K, preroll(K, W) + W, p1["boundary_ms"] or 0.0, p1["median_step_ms"],
-                                                           n_global * 400 / (399 * p1["median_step_ms"] + (p1["boundary_ms"] or 0.0)) / 1e3)),
+                                       ("outside the %d-step window (steps %d.. of a 400-step episode, median step %.3f ms); the "
+                                        "boundary step, walked to and timed separately incl. the host-side reset preparation, "
+                                        "took %.1f ms; a run with --steps 400 covers a whole episode with the boundary inside"
+                                        % (K, preroll(K, W) + W, p1["median_step_ms"], p1["boundary_ms"] or 0.0)),
                    "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB write outside the event brackets)",
                    "parallelism": "env-batch sharding x%d, no data-path collective" % world},
         "back_to_back": {"value": n_global * K / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K,

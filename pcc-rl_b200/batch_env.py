@@ -177,12 +177,23 @@ class PccBatchEnv(object):
     def _prefetch_start(self):
         import threading
         torch = self.torch
+        if getattr(self, "_pin_sets", None) is None:
+            # two alternating sets of page-locked staging buffers, allocated ONCE: the sampling thread must not make
+            # CUDA calls (a cudaHostAlloc there waits for the whole queued stream to drain and stalls the boundary)
+            mk = lambda dt: torch.empty(self.n_envs, dtype=dt).pin_memory()
+            self._pin_sets = [{k: mk(torch.int64 if k == "queue" else torch.float64)
+                               for k in ("bw", "lat", "queue", "loss", "start_rate")} for _ in range(2)]
+            self._pin_next = 0
+        pin = self._pin_sets[self._pin_next]
+        self._pin_next ^= 1
         episodes = self._episode.copy()
         box = {}
 
         def work():
             p = self._sample_for(np.ones(self.n_envs, dtype=bool), episodes)
-            box["pin"] = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in p.items()}
+            for k, v in p.items():
+                np.copyto(pin[k].numpy(), v)
+            box["pin"] = pin
             box["host"] = p
         th = threading.Thread(target=work, daemon=True)
         th.start()

@@ -1103,18 +1103,20 @@ __device__ __noinline__ double mlp_eval(const double *w1, const double *b1, cons
                                         const double *w3, const double *b3, int n_in, int h1, int h2, const double *obs_row)
 {
     double a1[PCC_POLICY_MAXH], a2[PCC_POLICY_MAXH];
+    // explicit fma(): the policy networks are not part of the bit-exact simulator path (-fmad=false is for that), and a
+    // fused multiply-add halves their binary64 instruction count; both evaluation kernels fuse the same way
     for (int i = 0; i < h1; i++) {
         double acc = b1[i];
-        for (int j = 0; j < n_in; j++) acc += w1[i * n_in + j] * obs_row[j];
+        for (int j = 0; j < n_in; j++) acc = fma(w1[i * n_in + j], obs_row[j], acc);
         a1[i] = tanh(acc);
     }
     for (int i = 0; i < h2; i++) {
         double acc = b2[i];
-        for (int j = 0; j < h1; j++) acc += w2[i * h1 + j] * a1[j];
+        for (int j = 0; j < h1; j++) acc = fma(w2[i * h1 + j], a1[j], acc);
         a2[i] = tanh(acc);
     }
     double out = b3[0];
-    for (int j = 0; j < h2; j++) out += w3[j] * a2[j];
+    for (int j = 0; j < h2; j++) out = fma(w3[j], a2[j], out);
     return out;
 }
 
@@ -1147,7 +1149,7 @@ __device__ __forceinline__ double mlp_eval_warp(const double *__restrict__ w1, c
         double acc = (i < h1) ? b1[i] : 0.0;
         for (int j = 0; j < n_in; j++) {
             const double xj = __shfl_sync(PCC_FULL, (j >> 5) == 0 ? x[0] : (j >> 5) == 1 ? x[1] : (j >> 5) == 2 ? x[2] : x[3], j & 31);
-            if (i < h1) acc += w1[i * n_in + j] * xj;
+            if (i < h1) acc = fma(w1[i * n_in + j], xj, acc);
         }
         a1[u] = (i < h1) ? tanh(acc) : 0.0;
     }
@@ -1157,12 +1159,12 @@ __device__ __forceinline__ double mlp_eval_warp(const double *__restrict__ w1, c
         double acc = (i < h2) ? b2[i] : 0.0;
         for (int j = 0; j < h1; j++) {
             const double aj = __shfl_sync(PCC_FULL, (j >> 5) ? a1[1] : a1[0], j & 31);
-            if (i < h2) acc += w2[i * h1 + j] * aj;
+            if (i < h2) acc = fma(w2[i * h1 + j], aj, acc);
         }
         a2[u] = (i < h2) ? tanh(acc) : 0.0;
     }
     double out = b3[0];                                  // output: the same ascending sum on every lane
-    for (int j = 0; j < h2; j++) out += w3[j] * __shfl_sync(PCC_FULL, (j >> 5) ? a2[1] : a2[0], j & 31);
+    for (int j = 0; j < h2; j++) out = fma(w3[j], __shfl_sync(PCC_FULL, (j >> 5) ? a2[1] : a2[0], j & 31), out);
     return out;
 }
 
