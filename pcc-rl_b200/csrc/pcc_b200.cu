@@ -424,7 +424,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
             DevRing r0{p.rings + (size_t)be0 * p.cap, p.cap - 1u};
             int32_t bsent = 0;
             bool bovf = false;
-            double2 *stage2 = reinterpret_cast<double2 *>(reinterpret_cast<char *>(buf) + (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch));
+            double2 *stage2 = reinterpret_cast<double2 *>(reinterpret_cast<char *>(buf) + (size_t)(wbuf + 32) * 8);
 #ifdef PCC_SOLO_V1
             coop_send_chunks(g, true, sb, r0, bseed, bdraws, bend, binv, stage2, bt, bq, btu, btail, bh2, bsent, bovf);
 #else
@@ -510,7 +510,7 @@ __device__ __forceinline__ void warp_mi(const Grp<32> &g, const DevState &p, boo
 #ifdef PCC_PROFILE
         const long long tc1 = clock64();
 #endif
-        if (WANT_MEANS) mi_means_warp(g, co, rj, in.dl, sbuf_j, in.wbuf, reinterpret_cast<LeafScratch *>(buf + wbuf + 32), buf,
+        if (WANT_MEANS) mi_means_warp(g, co, rj, in.dl, sbuf_j, in.wbuf, buf,
                                       p.need_inc != 0, a, li);
 #ifdef PCC_PROFILE
         if (prof && (int)lane == j) { prof[2] = tc1 - tc0; prof[3] = clock64() - tc1; }
@@ -688,7 +688,7 @@ struct PackedPartition {
 #define PCC_PACKED_THREADS 128
 #define PCC_MT_WBUF 4096           // staging capacity (samples) of the MT19937 solo warp
 #ifndef PCC_PACKED_SOLO_WBUF
-#define PCC_PACKED_SOLO_WBUF 1024
+#define PCC_PACKED_SOLO_WBUF 1280
 #endif
 __host__ __device__ inline size_t packed_warp_smem_bytes()
 {

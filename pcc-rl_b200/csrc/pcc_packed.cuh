@@ -1,7 +1,7 @@
 // pcc_packed.cuh -- "a lane owns an env": the packed execution of the monitor interval.
 //
 // A warp owns 32 envs of SIMILAR predicted work (the host sorts the batch by predicted packets every step, see
-// pcc_b200.cu: rebalance_packed), one per lane.  Every phase of pcc_core.cuh::run_mi runs per lane -- the scalar code
+// pcc_b200.cu: pcc_cost_packed_kernel + a 16-bit radix sort), one per lane.  Every phase of pcc_core.cuh::run_mi runs per lane -- the scalar code
 // the host twin proves against the heap oracle -- so all 32 lanes are busy with useful work:
 //
 //   phase A   sends with t < end: pacing timer, Philox loss draw (compared as a 53-bit integer against a per-env

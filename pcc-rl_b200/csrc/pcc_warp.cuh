@@ -23,18 +23,12 @@
 
 namespace pcc {
 
-// Per-warp shared memory (dynamic): [wbuf + 32] doubles of acked-latency staging, then a LeafScratch.
-// wbuf is a launch parameter (1024 for big batches, 4096 when the batch is small and occupancy
-// is not the limit); MIs with more acks than wbuf re-read the ring (streaming path).
-#define PCC_MAX_LEAVES 160
-struct LeafScratch {
-    double sum[PCC_MAX_LEAVES];
-    int off[PCC_MAX_LEAVES];
-    int cnt[PCC_MAX_LEAVES];
-};
-// ... followed by the shared memory of the single-env send phase (SoloSendSmem; coop_send_chunks<32>: 66 double2)
-#define PCC_SEND_SMEM_BYTES ((sizeof(SoloSendSmem) > 66 * 16 ? sizeof(SoloSendSmem) : 66 * 16) + 15 & ~(size_t)15)
-__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + sizeof(LeafScratch) + PCC_SEND_SMEM_BYTES; }
+// Per-warp shared memory (dynamic): [wbuf + 32] doubles of acked-latency staging, followed by the shared memory of the
+// single-env send phase (SoloSendSmem).  wbuf is a launch parameter (512-1024 for big batches, 4096 when the batch is
+// small and occupancy is not the limit); MIs with more acks than wbuf stage in the warp's global scratch, and beyond
+// that re-read the ring (streaming path).
+#define PCC_SEND_SMEM_BYTES ((sizeof(SoloSendSmem) + 15) & ~(size_t)15)
+__host__ __device__ inline size_t warp_smem_bytes(int wbuf) { return (size_t)(wbuf + 32) * 8 + PCC_SEND_SMEM_BYTES; }
 
 struct ConsumeIn {
     double end, dl, tnext;
@@ -319,105 +313,8 @@ __device__ __forceinline__ void consume_mi_warp(const Grp<32> &g, const ConsumeI
     out.acked = acked; out.lost = lost;
 }
 
-// ---- np.mean for 128 < n <= capacity: all samples are staged (shared memory, or the warp's global scratch) ----
-// numpy's pairwise recursion (n > 128: n2 = n/2 rounded down to a multiple of 8; sum(left) + sum(right))
-// bottoms out in leaves of 65..128 elements.  List the leaves left to right ...
-__device__ __forceinline__ int enum_leaves(int base, int n, int *off, int *cnt, int at)
-{
-    int so[16], sn[16], sp = 0;
-    so[0] = base; sn[0] = n; sp = 1;
-    while (sp) {
-        --sp;
-        const int o = so[sp], m = sn[sp];
-        if (m <= PCC_LEAF) { if (at < PCC_MAX_LEAVES) { off[at] = o; cnt[at] = m; } ++at; }
-        else {
-            int n2 = m / 2;
-            n2 -= n2 % 8;
-            so[sp] = o + n2; sn[sp] = m - n2; ++sp;   // right (popped second)
-            so[sp] = o; sn[sp] = n2; ++sp;            // left  (popped first)
-        }
-    }
-    return at;
-}
-// ... and fold the leaf sums back in the recursion's order (iterative post-order).
-__device__ __forceinline__ double fold_leaves(int n, const double *sums, int &idx)
-{
-    int right_n[16];
-    double left_sum[16];
-    bool have_left[16];
-    int sp = 0;
-    int cur = n;
-    for (;;) {
-        while (cur > PCC_LEAF) {
-            int n2 = cur / 2;
-            n2 -= n2 % 8;
-            right_n[sp] = cur - n2; have_left[sp] = false; sp++;
-            cur = n2;
-        }
-        double res = sums[idx++];
-        for (;;) {
-            if (sp == 0) return res;
-            if (!have_left[sp - 1]) {
-                left_sum[sp - 1] = res; have_left[sp - 1] = true;
-                cur = right_n[sp - 1];
-                break;
-            }
-            res = left_sum[sp - 1] + res;
-            sp--;
-        }
-    }
-}
-
-// Leaves are independent: four at a time, one per 8-lane subgroup (numpy's 8 accumulators + xor tree).
-__device__ __noinline__ void means_from_smem(const double *buf, LeafScratch *ls, int n, bool need_increase,
-                                             double &avg_lat, double &lat_increase)
-{
-    const unsigned lane = threadIdx.x & 31u;
-    const int half = n / 2;
-    int L = 0;
-    if (lane == 0) {
-        L = enum_leaves(0, n, ls->off, ls->cnt, 0);
-        if (need_increase && half >= 1) {
-            L = enum_leaves(0, half, ls->off, ls->cnt, L);
-            L = enum_leaves(half, n - half, ls->off, ls->cnt, L);
-        }
-    }
-    L = __shfl_sync(PCC_FULL, L, 0);
-    __syncwarp();
-    const int sg = (int)(lane >> 3), j = (int)(lane & 7u);
-    for (int base = 0; base < L; base += 4) {          // warp-uniform
-        const int li = base + sg;
-        const bool on = li < L;
-        const int c = on ? ls->cnt[li] : 0;
-        const double *a = buf + (on ? ls->off[li] : 0);
-        const int nb = c - (c % 8);
-        double r = 0.0;
-        if (c >= 8) {
-            r = a[j];
-            for (int k = 8; k < nb; k += 8) r += a[k + j];
-        }
-        r += __shfl_xor_sync(PCC_FULL, r, 1);
-        r += __shfl_xor_sync(PCC_FULL, r, 2);
-        r += __shfl_xor_sync(PCC_FULL, r, 4);
-        double res;
-        if (c >= 8) { res = r; for (int k = nb; k < c; k++) res += a[k]; }
-        else { res = 0.; for (int k = 0; k < c; k++) res += a[k]; }
-        if (on && j == 0) ls->sum[li] = res;
-    }
-    __syncwarp();
-    int idx = 0;
-    double sum = 0.0;
-    sum += fold_leaves(n, ls->sum, idx);
-    avg_lat = sum / (double)n;                                              // sender_obs.py:119-122
-    lat_increase = 0.0;
-    if (need_increase && half >= 1) {                                       // :138-142
-        double s1 = 0.0, s2 = 0.0;
-        s1 += fold_leaves(half, ls->sum, idx);
-        s2 += fold_leaves(n - half, ls->sum, idx);
-        lat_increase = s2 / (double)(n - half) - s1 / (double)half;
-    }
-    __syncwarp();
-}
+// (np.mean for 128 < n <= staging capacity: means_solo_from_buf in pcc_coop.cuh -- the three sums of the env side by
+// side on three 8-lane subgroups, each walking the leaves of numpy's recursion)
 
 // n > wbuf (very rare): streaming re-read of the ring
 template <class Ring>
@@ -449,7 +346,7 @@ __device__ __noinline__ void mi_means_stream(ConsumeOut co, Ring ring, double dl
 // avg latency (sender_obs.py:119-122) and latency increase (:138-142) of one env's MI, warp-wide
 template <class Ring>
 __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut &co, Ring &ring, double dl,
-                                              double *buf, int wbuf, LeafScratch *ls, double *smem_buf,
+                                              double *buf, int wbuf, double *smem_buf,
                                               bool need_increase, double &avg_lat, double &lat_increase)
 {
     const int n = co.acked;
@@ -490,12 +387,7 @@ __device__ __forceinline__ void mi_means_warp(const Grp<32> &g, const ConsumeOut
         }
         __syncwarp();
     } else if (n <= wbuf) {
-#ifdef PCC_MEANS_V1
-        means_from_smem(buf, ls, n, need_increase, avg_lat, lat_increase);
-#else
-        (void)ls;
         means_solo_from_buf(buf, n, need_increase, avg_lat, lat_increase);
-#endif
     } else {
         mi_means_stream(co, ring, dl, smem_buf, need_increase, avg_lat, lat_increase);
     }
