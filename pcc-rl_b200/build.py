@@ -7,7 +7,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 SRC = os.path.join(PKG_DIR, "csrc", "pcc_b200.cu")
 DEPS = [SRC, os.path.join(ROOT, "include", "pcc_b200.h")] + [
-    os.path.join(PKG_DIR, "csrc", f) for f in ("pcc_core.cuh", "pcc_coop.cuh", "pcc_warp.cuh", "pcc_packed.cuh", "pcc_multi_core.cuh", "pcc_multi_fast.cuh",
+    os.path.join(PKG_DIR, "csrc", f) for f in ("pcc_core.cuh", "pcc_coop.cuh", "pcc_warp.cuh", "pcc_packed.cuh", "pcc_multi_core.cuh", "pcc_multi_fast.cuh", "pcc_multi_warp.cuh",
                                                "pcc_flows_core.cuh", "pcc_flows.cuh")]
 LIB = os.path.join(PKG_DIR, "libpcc_b200.so")
 

@@ -26,6 +26,7 @@
 #include "pcc_warp.cuh"
 #include "pcc_multi_core.cuh"
 #include "pcc_multi_fast.cuh"
+#include "pcc_multi_warp.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -2286,21 +2287,7 @@ struct MultiDev {
     MFast *fast;         // [n] heap-free mode: timers + ring cursors; the heap region then holds Rec[cap] + sender ids[cap]
     int32_t ring_cap;    // records per env in heap-free mode (power of two)
 };
-// heap-free mode: the env's slice of the heap region reinterpreted as the shared in-flight ring
-struct DevSidRing {
-    Rec *base; uint8_t *sids; uint32_t mask;
-    __device__ __forceinline__ uint32_t capacity() const { return mask + 1u; }
-    __device__ __forceinline__ Rec load(uint32_t i) const
-    {
-        const double2 v = *reinterpret_cast<const double2 *>(base + (i & mask));
-        Rec r; r.a = v.x; r.l = v.y;
-        return r;
-    }
-    __device__ __forceinline__ void store(uint32_t i, Rec r) { *reinterpret_cast<double2 *>(base + (i & mask)) = make_double2(r.a, r.l); }
-    __device__ __forceinline__ void store_a(uint32_t i, double a) { base[i & mask].a = a; }
-    __device__ __forceinline__ int sid(uint32_t i) const { return sids[i & mask]; }
-    __device__ __forceinline__ void set_sid(uint32_t i, int sd) { sids[i & mask] = (uint8_t)sd; }
-};
+// heap-free mode: the env's slice of the heap region reinterpreted as the shared in-flight ring (DevSidRing, pcc_multi_warp.cuh)
 __device__ __forceinline__ DevSidRing multi_ring(const MultiDev &p, int64_t e)
 {
     char *b = reinterpret_cast<char *>(p.heaps + (size_t)e * p.heap_cap);
@@ -2472,13 +2459,116 @@ __global__ void pcc_mfast_step_kernel(MultiDev p, unsigned long long head_step, 
     done[e] = dn ? 1 : 0;
 }
 
+// heap-free mode, one link per warp (pcc_multi_warp.cuh): the default engine of the streaming MI.  `perm` = links in
+// descending predicted cost (the heaviest links start first), or null.
+template <int S>
+__global__ void __launch_bounds__(128) pcc_mwarp_step_kernel(MultiDev p, const int32_t *__restrict__ perm,
+                                                             unsigned long long head_step, const double *__restrict__ actions,
+                                                             double *__restrict__ obs, double *__restrict__ reward,
+                                                             uint8_t *__restrict__ done, int32_t *__restrict__ counts)
+{
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= p.n) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t e = perm ? (int64_t)perm[w] : w;
+    MEnv &me = p.envs[e];
+    MNet net = me.net;
+    MSender snd[S];
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+        snd[i] = me.snd[i];
+        snd[i].rate = apply_rate_delta(snd[i].rate, actions[(size_t)e * S + i], p.c);   // network_sim.py:409-412
+    }
+    MFast f = p.fast[e];
+    const uint64_t seed = me.seed;
+    uint64_t draws = me.draws;
+    DevSidRing ring = multi_ring(p, e);
+    double *smp = p.samples + (size_t)e * S * p.cap_s;
+    const bool ok = mwarp_run_for_dur<S>(net, snd, f, ring, smp, p.cap_s, seed, draws, net.run_dur);   // :416
+    double avg[S], inc[S];
+    mwarp_means<S>(snd, smp, p.cap_s, p.need_inc != 0, avg, inc);
+    const int H = p.H, F = p.F, HF = H * F;
+    const int slot_new = (int)(head_step % (unsigned long long)H);
+    double avg0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+        MiOut o;
+        o.sent = snd[i].sent; o.acked = snd[i].acked; o.lost = snd[i].lost; o.start = snd[i].obs_start; o.end = net.cur_time;
+        MiStats st;
+        mi_stats_finish(o, p.c, avg[i], inc[i], snd[i].conn_min, true, st);
+        double *hrow = p.hist + ((size_t)e * S + i) * HF;
+        for (int k = 0; k < F; k++) {
+            const double v = metric_value(st, p.ids[k]);
+            if (lane == (unsigned)k) hrow[slot_new * F + k] = v;
+        }
+        if (lane == 0) {
+            reward[(size_t)e * S + i] = st.reward;
+            if (counts) {
+                int32_t *c = counts + ((size_t)e * S + i) * 3;
+                c[0] = snd[i].sent; c[1] = snd[i].acked; c[2] = snd[i].lost;
+            }
+        }
+        if (i == 0) avg0 = st.avg_lat;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+        const double *hrow = p.hist + ((size_t)e * S + i) * HF;
+        double *ob = obs + ((size_t)e * S + i) * HF;
+        for (int idx = (int)lane; idx < HF; idx += 32) {
+            const int hh = idx / F, k = idx - hh * F;
+            int sl = slot_new + 1 + hh;
+            if (sl >= H) sl -= H;
+            ob[idx] = hrow[sl * F + k];
+        }
+    }
+    net.steps += 1;                                                  // :419
+    if (avg0 > 0.0) net.run_dur = 0.5 * avg0;                        // :437-438 (sender 0, as written)
+    if (lane == 0) {
+        me.net = net;
+#pragma unroll
+        for (int i = 0; i < S; i++) me.snd[i] = snd[i];
+        me.draws = draws;
+        p.fast[e] = f;
+        if (!ok) atomicAdd(&p.meta[1], 1ull);
+        done[e] = net.steps >= p.c.max_steps ? 1 : 0;                // :444
+    }
+}
+
+// predicted packets of the next MI per link (sort key, 16 bits) + identity values for the sort
+__global__ void pcc_mcost_kernel(MultiDev p, uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    const MEnv &me = p.envs[e];
+    double r = 0.0;
+    for (int i = 0; i < p.S; i++) r += me.snd[i].rate;
+    const double pk = me.net.run_dur * r;
+    keys[e] = pk >= 65535.0 ? 65535u : (uint32_t)pk;
+    vals[e] = (int32_t)e;
+}
+
 struct pcc_multi_handle_s {
     pcc_config cfg;
     MultiDev d;
     unsigned long long head;
     int mode;            // 0 undecided (before the first reset), 1 heap-free streaming MI, 2 event heap
     bool heap_forced;    // PCC_MULTI_MODE=heap
+    bool thread_forced;  // PCC_MULTI_MODE=thread: the streaming MI with one link per thread (pcc_mfast_step_kernel)
+    // link-per-warp engine: links visited in descending predicted cost, re-sorted every `sort_every` steps
+    uint32_t *sort_keys_in, *sort_keys_out;
+    int32_t *sort_vals_in, *perm;
+    void *sort_tmp;
+    size_t sort_tmp_bytes;
+    int sort_every, since_sort;
+    bool sort_now;
 };
+
+static void multi_free_sort(pcc_multi_handle_s *h)
+{
+    cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->perm); cudaFree(h->sort_tmp);
+    h->sort_keys_in = h->sort_keys_out = nullptr; h->sort_vals_in = h->perm = nullptr; h->sort_tmp = nullptr;
+}
 
 static void multi_layout(const pcc_config *cfg, int S, size_t off[6], size_t &total)
 {
@@ -2531,7 +2621,27 @@ int pcc_multi_create(pcc_multi_handle *out, const pcc_config *cfg, int32_t n_sen
     {
         const char *mm = getenv("PCC_MULTI_MODE");
         h->heap_forced = mm && !strcmp(mm, "heap");
+        h->thread_forced = mm && !strcmp(mm, "thread");
         h->mode = 0;
+        const char *se = getenv("PCC_MULTI_SORT_EVERY");
+        h->sort_every = se ? atoi(se) : 8;       // 0: no sort (links in index order)
+        h->sort_now = true;
+    }
+    if (!h->heap_forced && !h->thread_forced && h->sort_every > 0) {
+        const size_t n = (size_t)cfg->n_envs;
+        cudaError_t ce = cudaMalloc(&h->sort_keys_in, 4 * n);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->sort_keys_out, 4 * n);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->sort_vals_in, 4 * n);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->perm, 4 * n);
+        if (ce == cudaSuccess)
+            ce = cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->sort_keys_in, h->sort_keys_out,
+                                                           h->sort_vals_in, h->perm, (int)n, 0, 16);
+        if (ce == cudaSuccess) ce = cudaMalloc(&h->sort_tmp, h->sort_tmp_bytes);
+        if (ce != cudaSuccess) {
+            multi_free_sort(h);
+            delete h;
+            return fail(PCC_ECUDA, "multi create: %s", cudaGetErrorString(ce));
+        }
     }
     d.n = cfg->n_envs; d.S = n_senders; d.H = cfg->history_len; d.F = cfg->n_features;
     d.heap_cap = (int32_t)(cfg->ring_capacity * n_senders); d.cap_s = (int32_t)cfg->ring_capacity;
@@ -2545,12 +2655,18 @@ int pcc_multi_create(pcc_multi_handle *out, const pcc_config *cfg, int32_t n_sen
     if (e == cudaSuccess) e = cudaMemset(b + off[4], 0, 64);
     if (e == cudaSuccess) e = cudaMemset(b + off[5], 0, total - off[5]);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { delete h; return fail(PCC_ECUDA, "multi init: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { multi_free_sort(h); delete h; return fail(PCC_ECUDA, "multi init: %s", cudaGetErrorString(e)); }
     *out = h;
     return PCC_OK;
 }
 
-void pcc_multi_destroy(pcc_multi_handle h) { delete h; }
+void pcc_multi_destroy(pcc_multi_handle h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    multi_free_sort(h);
+    delete h;
+}
 
 int pcc_multi_seed(pcc_multi_handle h, const uint64_t *seeds_dev, void *stream)
 {
@@ -2579,6 +2695,7 @@ int pcc_multi_reset(pcc_multi_handle h, const uint8_t *mask_dev, const double *b
     pcc_multi_reset_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
         h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rates_dev, obs_dev);
     CUDA_TRY(cudaGetLastError());
+    h->sort_now = true;
     return PCC_OK;
 }
 
@@ -2590,8 +2707,32 @@ int pcc_multi_step_cwnd(pcc_multi_handle h, const double *actions_dev, const dou
     if (h->mode == 0) return fail(PCC_EINVAL, "pcc_multi_step before pcc_multi_reset");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (h->mode == 1) {
-        pcc_mfast_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
-            h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (h->thread_forced)
+            pcc_mfast_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, st>>>(
+                h->d, h->head, actions_dev, obs_dev, reward_dev, done_dev, counts_dev);
+        else {
+            const int64_t n = h->d.n;
+            if (h->perm && (h->sort_now || h->since_sort >= h->sort_every)) {
+                pcc_mcost_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d, h->sort_keys_in, h->sort_vals_in);
+                CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp, h->sort_tmp_bytes, h->sort_keys_in,
+                                                                   h->sort_keys_out, h->sort_vals_in, h->perm, (int)n, 0, 16, st));
+                h->sort_now = false;
+                h->since_sort = 0;
+            }
+            h->since_sort++;
+            const unsigned grid = (unsigned)((n + 3) / 4);
+#define PCC_MWARP_LAUNCH(S_)                                                                                     \
+            pcc_mwarp_step_kernel<S_><<<grid, 128, 0, st>>>(h->d, h->perm, h->head, actions_dev, obs_dev, reward_dev, \
+                                                            done_dev, counts_dev)
+            switch (h->d.S) {
+                case 1: PCC_MWARP_LAUNCH(1); break;
+                case 2: PCC_MWARP_LAUNCH(2); break;
+                case 3: PCC_MWARP_LAUNCH(3); break;
+                default: PCC_MWARP_LAUNCH(4); break;
+            }
+#undef PCC_MWARP_LAUNCH
+        }
         if (cwnd_dev) CUDA_TRY(cudaMemsetAsync(cwnd_dev, 0, (size_t)h->d.n * h->d.S * sizeof(int32_t), (cudaStream_t)stream));
     } else
     pcc_multi_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(

@@ -11,9 +11,10 @@ from golden_util import GOLDEN_DIR, golden_names
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["stream", "heap"])
+@pytest.fixture(params=["warp", "thread", "heap"])
 def multi_mode(request, monkeypatch):
-    """Both engines of the multi-sender path: the heap-free streaming MI (default) and the per-env event heap."""
+    """The engines of the multi-sender path: the heap-free streaming MI with one link per warp (default) or per thread,
+    and the per-env event heap."""
     monkeypatch.setenv("PCC_MULTI_MODE", request.param)
     return request.param
 
@@ -59,3 +60,32 @@ def test_cuda_config5_grid_sweep_vs_oracle(multi_mode):
             assert np.array_equal(o_obs, obs_h[i]) and np.array_equal(o_rew, rew_h[i]), (t, i)
     env.check()
     assert int(info["counts"][:, :, 0].min()) >= 0
+
+
+@pytest.mark.parametrize("S", [1, 3, 4])
+def test_cuda_multi_other_sender_counts_vs_oracle(S, multi_mode):
+    """1, 3 and 4 senders per link (the kernel is compiled per sender count), ragged link parameters incl. lossy,
+    tiny-queue and long-delay links whose MIs span several 64-draw rounds and several numpy leaves."""
+    import pcc_rl_b200
+    n, steps = 96, 40
+    g = np.random.default_rng(100 + S)
+    p = dict(bw=g.uniform(80, 2000, n), lat=np.exp(g.uniform(np.log(0.002), np.log(0.6), n)),
+             queue=g.integers(1, 60, n), loss=g.choice([0.0, 0.01, 0.05], n))
+    rates = g.uniform(40, 1500, (n, S))
+    env = pcc_rl_b200.PccMultiSenderEnv(n, n_senders=S, seed=900, ring_capacity=1 << 14)
+    env.reset(p, rates)
+    orcs = []
+    for i in range(n):
+        o = oracle.OracleEnv()
+        o.seed_philox(900 + i)
+        o.reset_multi(p["bw"][i], p["lat"][i], int(p["queue"][i]), p["loss"][i], rates[i])
+        orcs.append(o)
+    for t in range(steps):
+        a = g.normal(0, 2.0, (n, S))
+        obs, rew, done, info = env.step(a)
+        obs_h, rew_h, cnt_h = obs.cpu().numpy(), rew.cpu().numpy(), info["counts"].cpu().numpy()
+        for i in range(n):
+            o_obs, o_rew, o_done, o_cnt = orcs[i].step_multi(a[i])
+            assert np.array_equal(o_cnt, cnt_h[i]), (t, i)
+            assert np.array_equal(o_obs, obs_h[i]) and np.array_equal(o_rew, rew_h[i]), (t, i)
+    env.check()

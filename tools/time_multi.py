@@ -1,11 +1,12 @@
-"""Throughput of the multi-sender path (BASELINE config 5: bw x delay grid, 2 senders per link) for both engines.
-python tools/time_multi.py [grid_side] [steps]"""
+"""Throughput of the multi-sender path (BASELINE config 5: bw x delay grid, 2 senders per link) for its engines
+(warp = streaming MI, one link per warp; thread = the same, one link per thread; heap = per-env event heap).
+python tools/time_multi.py [grid_side] [steps] [modes]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
-for mode in ("stream", "heap"):
+for mode in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("warp", "thread", "heap")):
     os.environ["PCC_MULTI_MODE"] = mode
     import pcc_rl_b200
     p = pcc_rl_b200.grid_sweep_params(n_bw=side, n_lat=side, queue=40, loss=0.01)
