@@ -294,10 +294,21 @@ def run_config5(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
         d_.cpu()
     torch.cuda.synchronize(dev)
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    launches = env.launch_count()
     if rank != 0:
         return
     peak, peak_kind = measured_peak_gbs()
     hf = env.obs_dim
+    engine = os.environ.get("PCC_MULTI_MODE", "warp")
+    kernel_name = {"thread": "pcc_mfast_step_kernel", "heap": "pcc_multi_step_kernel"}.get(engine, "pcc_mwarp_step_kernel<2>")
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh).get("config5")
+        if tj and engine not in ("thread", "heap") and n == 4096:
+            traffic, traffic_src, kernel_name = tj["dram_bytes_per_launch"], "profiles/" + tj["source"], tj["kernel"]
+    except (OSError, ValueError, KeyError):
+        pass
     # per sender the single-sender figure (677 + 48 sent + 8 acked) without a second copy of the link parameters
     bytes_total = (677 * S - 32 * (S - 1)) * n * world * K + 48 * sent + 8 * acked
     achieved = bytes_total / (dev_ms * 1e-3) / 1e9 / world
@@ -306,16 +317,20 @@ def run_config5(args, pcc_rl_b200, D, torch, dev, rank, world, n, n_global):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "config5: " + WORKLOADS["config5"]["desc"], "links_per_gpu": n, "senders_per_link": S,
-                   "engine": os.environ.get("PCC_MULTI_MODE", "stream (heap-free)"), "actions": "N(0,2) per sender",
+                   "engine": {"thread": "streaming MI, one link per thread", "heap": "per-env event heap"}.get(
+                       engine, "streaming MI (heap-free), one link per warp, links re-sorted by predicted packets every 8 steps"),
+                   "actions": "N(0,2) per sender",
                    "l2": "no flush" if args.no_flush else "flushed between steps (256 MiB write outside the event brackets)"},
         "sender_steps_per_s": n * world * S * K / (dev_ms * 1e-3),
         "e2e": {"value": n * world * ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": 8 * n * S,
                 "d2h_bytes_per_step": n * S * (8 * hf + 8) + n, "ms_per_step": 1e3 * e2e_s / ke, "steps": ke,
                 "api": "PccMultiSenderEnv.step with pinned host actions, obs / reward / done copied back"},
-        "gpu_launches": K,
+        "gpu_launches": launches,
+        "gpu_launches_note": "this library's kernels over reset + warm-up + timed + e2e steps (step kernels + the sort's key kernel; cub's radix sort not counted)",
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                     "traffic": None, "kernel": "pcc_mfast_step_kernel", "algorithmic_bytes_per_launch": bytes_total / (K * world)},
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
+                     "algorithmic_bytes_per_launch": bytes_total / (K * world)},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:

@@ -219,8 +219,10 @@ int64_t pcc_launch_count(pcc_handle h);
  * step applies actions[i] to sender i (:409-412 generalised); every sender has its own MI, history, obs and
  * reward (:194,205 on its own MI); the MI duration follows sender 0 (:437-438 as written).  Two engines with identical
  * results, fixed at the first pcc_multi_reset: the heap-free streaming MI (default: one shared in-flight ring with a
- * sender id per record, timers merged by (time, sender), three cursors) and the per-env event heap (environment
- * PCC_MULTI_MODE=heap, and always for the cwnd / latency-noise variants below).  One env per thread.  cfg->ring_capacity
+ * sender id per record, timers merged by (time, sender), three cursors; one link per warp, links visited in
+ * descending predicted cost -- environment PCC_MULTI_MODE=thread runs it with one link per thread) and the per-env
+ * event heap, one env per thread (PCC_MULTI_MODE=heap, and always for the cwnd / latency-noise variants below).
+ * cfg->ring_capacity
  * (a power of two) sizes the in-flight ring / the heap (x n_senders events) and the per-sender RTT sample buffers;
  * Philox streams only.  Arrays: [n_envs][n_senders]... row-major. */
 typedef struct pcc_multi_handle_s *pcc_multi_handle;
@@ -235,6 +237,8 @@ int pcc_multi_step(pcc_multi_handle h, const double *actions_dev /*[n][S]*/, dou
                    double *reward_dev /*[n][S]*/, uint8_t *done_dev /*[n]*/, int32_t *counts_dev /*[n][S][3], optional*/,
                    void *stream);
 int pcc_multi_check(pcc_multi_handle h, void *stream);
+/* kernels of this library launched for the handle so far (steps, resets, cost keys of the link sort) */
+int64_t pcc_multi_launch_count(pcc_multi_handle h);
 
 /* The two variants of the event loop that the reference compiles out behind module switches:
  *   use_cwnd           USE_CWND = True  (network_sim.py:54): congestion window, Sender.can_send_packet :251-255,

@@ -68,7 +68,7 @@ EXPORTS = ["pcc_default_consts", "pcc_default_config", "pcc_ring_capacity_for", 
            "pcc_create", "pcc_destroy", "pcc_attach", "pcc_seed", "pcc_get_mt_state", "pcc_set_mt_state",
            "pcc_reset", "pcc_step", "pcc_step_host", "pcc_step_host_submit", "pcc_step_host_wait", "pcc_rollout", "pcc_check", "pcc_get_column", "pcc_launch_count",
            "pcc_last_error", "pcc_abi_version", "pcc_multi_workspace_bytes", "pcc_multi_create", "pcc_multi_destroy",
-           "pcc_multi_seed", "pcc_multi_reset", "pcc_multi_step", "pcc_multi_check",
+           "pcc_multi_seed", "pcc_multi_reset", "pcc_multi_step", "pcc_multi_check", "pcc_multi_launch_count",
            "pcc_default_variant", "pcc_multi_set_variant", "pcc_multi_step_cwnd",
            "pcc_flows_default_config", "pcc_flows_workspace_bytes", "pcc_flows_create", "pcc_flows_attach",
            "pcc_flows_destroy", "pcc_flows_give_samples", "pcc_flows_reset", "pcc_flows_get_obs", "pcc_flows_set_rates",
@@ -126,6 +126,8 @@ def load(rebuild_if_stale=True):
     L.pcc_multi_reset.argtypes = [vp, u8p, dp, dp, vp, dp, dp, dp, vp]
     L.pcc_multi_step.argtypes = [vp, dp, dp, dp, u8p, vp, vp]
     L.pcc_multi_check.argtypes = [vp, vp]
+    L.pcc_multi_launch_count.argtypes = [vp]
+    L.pcc_multi_launch_count.restype = C.c_int64
     L.pcc_default_variant.argtypes = [C.POINTER(PccVariant)]
     L.pcc_default_variant.restype = None
     L.pcc_multi_set_variant.argtypes = [vp, C.POINTER(PccVariant)]

@@ -2462,7 +2462,7 @@ __global__ void pcc_mfast_step_kernel(MultiDev p, unsigned long long head_step, 
 // heap-free mode, one link per warp (pcc_multi_warp.cuh): the default engine of the streaming MI.  `perm` = links in
 // descending predicted cost (the heaviest links start first), or null.
 template <int S>
-__global__ void __launch_bounds__(128) pcc_mwarp_step_kernel(MultiDev p, const int32_t *__restrict__ perm,
+__global__ void __launch_bounds__(128, 4) pcc_mwarp_step_kernel(MultiDev p, const int32_t *__restrict__ perm,
                                                              unsigned long long head_step, const double *__restrict__ actions,
                                                              double *__restrict__ obs, double *__restrict__ reward,
                                                              uint8_t *__restrict__ done, int32_t *__restrict__ counts)
@@ -2484,7 +2484,9 @@ __global__ void __launch_bounds__(128) pcc_mwarp_step_kernel(MultiDev p, const i
     uint64_t draws = me.draws;
     DevSidRing ring = multi_ring(p, e);
     double *smp = p.samples + (size_t)e * S * p.cap_s;
-    const bool ok = mwarp_run_for_dur<S>(net, snd, f, ring, smp, p.cap_s, seed, draws, net.run_dur);   // :416
+    __shared__ MwSendSmem send_sm[4];
+    const bool ok = mwarp_run_for_dur<S>(net, snd, f, ring, smp, p.cap_s, seed, draws, net.run_dur,
+                                         send_sm[threadIdx.x >> 5]);   // :416
     double avg[S], inc[S];
     mwarp_means<S>(snd, smp, p.cap_s, p.need_inc != 0, avg, inc);
     const int H = p.H, F = p.F, HF = H * F;
@@ -2562,6 +2564,7 @@ struct pcc_multi_handle_s {
     size_t sort_tmp_bytes;
     int sort_every, since_sort;
     bool sort_now;
+    int64_t launches;
 };
 
 static void multi_free_sort(pcc_multi_handle_s *h)
@@ -2696,6 +2699,7 @@ int pcc_multi_reset(pcc_multi_handle h, const uint8_t *mask_dev, const double *b
         h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rates_dev, obs_dev);
     CUDA_TRY(cudaGetLastError());
     h->sort_now = true;
+    h->launches++;
     return PCC_OK;
 }
 
@@ -2715,6 +2719,7 @@ int pcc_multi_step_cwnd(pcc_multi_handle h, const double *actions_dev, const dou
             const int64_t n = h->d.n;
             if (h->perm && (h->sort_now || h->since_sort >= h->sort_every)) {
                 pcc_mcost_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d, h->sort_keys_in, h->sort_vals_in);
+                h->launches++;
                 CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp, h->sort_tmp_bytes, h->sort_keys_in,
                                                                    h->sort_keys_out, h->sort_vals_in, h->perm, (int)n, 0, 16, st));
                 h->sort_now = false;
@@ -2738,6 +2743,7 @@ int pcc_multi_step_cwnd(pcc_multi_handle h, const double *actions_dev, const dou
     pcc_multi_step_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
         h->d, h->head, actions_dev, cwnd_actions_dev, obs_dev, reward_dev, done_dev, counts_dev, cwnd_dev);
     h->head++;
+    h->launches++;
     CUDA_TRY(cudaGetLastError());
     return PCC_OK;
 }
@@ -2766,6 +2772,8 @@ int pcc_multi_set_variant(pcc_multi_handle h, const pcc_variant *v)
     h->d.v.min_cwnd = v->min_cwnd; h->d.v.max_cwnd = v->max_cwnd;
     return PCC_OK;
 }
+
+int64_t pcc_multi_launch_count(pcc_multi_handle h) { return h ? h->launches : 0; }
 
 int pcc_multi_check(pcc_multi_handle h, void *stream)
 {

@@ -213,14 +213,15 @@ struct Mt19937Rng {
 PCC_HD double tail_drop_threshold(double d_bw, double max_qd)
 {
     if (d_bw + 0.0 > max_qd) return -1.0;            // even an empty queue is "full"
-    double t = max_qd - d_bw;
-    if (t < 0.0) t = 0.0;
-    while (d_bw + t > max_qd) t = nextafter(t, -1.0);            // step down until admissible
-    for (;;) {                                                   // step up while still admissible
-        const double u = nextafter(t, 1.0e300);
-        if (d_bw + u <= max_qd) t = u; else break;
+    // Non-negative doubles are ordered like their bit patterns, so the largest admissible w is found by bisection on
+    // the bits: at most 63 steps.  (Walking there one ulp at a time from max_qd - d_bw does not terminate in practice
+    // when that difference is 0 or tiny next to d_bw -- a queue of exactly one packet.)
+    uint64_t lo = 0ull, hi = 0x7FF0000000000000ull;  // 0.0 is admissible, +inf is not
+    while (hi - lo > 1ull) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (d_bw + u2d(mid) <= max_qd) lo = mid; else hi = mid;
     }
-    return t;
+    return u2d(lo);
 }
 
 // ---------------------------------------------------------------------------------------

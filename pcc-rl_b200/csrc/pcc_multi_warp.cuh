@@ -4,11 +4,13 @@
 // oracle and the reference's goldens); what changes is who does the work.  All 32 lanes carry the link's scalar state
 // in registers and execute the serial parts together (a warp-uniform instruction stream costs what one thread costs);
 // the three loops that made the thread-per-link kernel slow are spread over the lanes:
-//   * loss draws (network_sim.py:73): one Philox4x32-10 block per lane = 64 draws per round, handed to the queue
-//     recurrence as a bit mask, so the generator leaves the per-packet dependency chain;
-//   * the queue recurrence itself (:66-84) stays serial in binary64 -- it runs on every lane, lane (k mod 32) keeps
-//     the k-th record, and 32 records go to the shared in-flight ring with one coalesced 16-byte store per lane;
-//   * hop-1 / hop-2 cursors (:140-154): 32 consecutive records per round, predicate + ballot + ffs instead of a
+//   * send phase in chunks of 64 packets: the S pacing timers are merged serially (compare, select, one add per
+//     packet: network_sim.py:156-161) into shared memory; the loss draws (:73) are one Philox4x32-10 block per lane =
+//     64 draws, compared as 53-bit integers and handed on as a bit mask; the queue recurrence (:66-84) -- the only
+//     other serial part -- runs in place over the compacted packets that reach the queue (one LDS, two DADD, two
+//     DSETP and the selects per packet, as in the single-sender group_send_chunks); all lanes then rebuild the 64
+//     records and store them to the shared in-flight ring, coalesced;
+//   * hop-1 / hop-2 cursors (:140-154): 4 x 32 consecutive records per round, predicate + ballot + ffs instead of a
 //     dependent-load loop; per-sender ack / loss counts are popcounts of the ballots, the acked latencies are
 //     compacted into the sender's sample array by ballot prefix;
 //   * np.mean (sender_obs.py:119-122, 138-142): the 3 * S sums (all / first half / second half per sender) run four
@@ -19,6 +21,8 @@
 #include "pcc_coop.cuh"
 
 namespace pcc {
+
+#define PCC_MW_W 4            // windows of 32 records per scan round (loads issued together)
 
 // the env's slice of the heap region reinterpreted as the shared in-flight ring: Rec[cap] then sender ids[cap]
 struct DevSidRing {
@@ -38,10 +42,17 @@ struct DevSidRing {
     __device__ __forceinline__ const void *addr(uint32_t i) const { return base + (i & mask); }
 };
 
+// per-warp staging of a chunk of the send phase
+struct MwSendSmem {
+    double ts[64];        // merged send times of the chunk's packets
+    double xs[64];        // x of the packets that reach the queue, compact; overwritten in place by y
+    uint8_t sid[64];      // sender of packet k
+};
+
 // One MI of the link owned by this warp.  Every argument and every local is warp-uniform unless it says "lane".
 template <int S>
 __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast &f, DevSidRing &ring, double *samples,
-                                                  int cap_s, uint64_t seed, uint64_t &draws, double dur)
+                                                  int cap_s, uint64_t seed, uint64_t &draws, double dur, MwSendSmem &sm)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -82,56 +93,127 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
     _Pragma("unroll")                                                                         \
     for (int i_ = 1; i_ < S; i_++) if (ns[i_] < t) { t = ns[i_]; it = i_; }
 
-    // ---- (1) every send with t < end, timers merged by (time, sender) ------------------------------------
-    for (bool more = true; more;) {
-        uint32_t c0, c1, c2, c3;
-        philox_block(seed, (draws >> 1) + lane, c0, c1, c2, c3);     // lane: draws 2 * (B0 + lane), + 1
-        const uint32_t ev = __ballot_sync(PCC_FULL, res53(c0, c1) < lr), od = __ballot_sync(PCC_FULL, res53(c2, c3) < lr);
-        const int skip = (int)(draws & 1u);
-        uint64_t bits = interleave_bits(ev, od) >> skip;
-        const int avail = 64 - skip;
-        int k = 0;
-        Rec mine; mine.a = 0.0; mine.l = 0.0;                        // lane: record k with k mod 32 == lane
-        int mysid = 0;
-        while (k < avail) {
-            PCC_MW_NEXT_TIMER(it, t);
-            if (!(t < end)) { more = false; break; }
-            const bool loss = (bits & 1ull) != 0ull;
-            bits >>= 1;
-            Rec r;
-            PCC_MW_SEND(it, t, loss, r);
-            if ((unsigned)(k & 31) == lane) { mine = r; mysid = it; }
-            k++;
-            if ((k & 31) == 0) {                                     // 32 records staged: coalesced copy-out
-                const uint32_t p = tail + lane;
-                if ((uint32_t)(p - h2) >= cap) ok = false;           // ring overflow: fatal, reported
-                else { ring.store(p, mine); ring.set_sid(p, mysid); }
-                tail += 32u;
+    // ---- (1) every send with t < end, timers merged by (time, sender), in chunks of <= 64 packets -----------
+    // The shared queue does not care who sent a packet, so once the chunk's merged send times are known the rest is the
+    // single-sender send phase (group_send_chunks in pcc_coop.cuh, stages S1 / S3 / S4 / S5): the queue recurrence runs
+    // in place over x_k = t_k - t_(last packet before k that reached the queue), compacted over the packets that were
+    // not randomly dropped; records are rebuilt by all lanes afterwards.
+    {
+        const uint64_t thr = loss_threshold(lr);
+        const double k0 = (0.0 > w_full) ? 0.0 : d_bw;               // q' when the queue has drained (w = 0)
+        const bool full0 = 0.0 > w_full;
+        for (;;) {
+            const unsigned off = (unsigned)(draws & 1ull);
+            const int navail = 64 - (int)off;
+            // M1: the timers' merge (:156-161), serial; the loop ends the chunk at the first timer >= end
+            int cnt = 0;
+            while (cnt < navail) {
+                PCC_MW_NEXT_TIMER(it, t);
+                if (!(t < end)) break;
+                if (lane == 0) { sm.ts[cnt] = t; sm.sid[cnt] = (uint8_t)it; }
+#pragma unroll
+                for (int i = 0; i < S; i++)
+                    if (i == it) { sent[i]++; ns[i] = t + inv[i]; }
+                cnt++;
             }
-        }
-        const unsigned rem = (unsigned)(k & 31);
-        if (rem) {
-            const uint32_t p = tail + lane;
-            if (lane < rem) {
-                if ((uint32_t)(p - h2) >= cap) ok = false;
-                else { ring.store(p, mine); ring.set_sid(p, mysid); }
+            if (cnt == 0) break;
+            __syncwarp();
+            // S1: bit k of dm = packet k of the chunk is randomly dropped (:73)
+            uint32_t c0, c1, c2, c3;
+            philox_block(seed, (draws >> 1) + lane, c0, c1, c2, c3); // lane: draws 2 * (B0 + lane), + 1
+            const unsigned be = __ballot_sync(PCC_FULL, u53(c0, c1) < thr), bo = __ballot_sync(PCC_FULL, u53(c2, c3) < thr);
+            const uint64_t dm = interleave_bits(be, bo) >> off;
+            const uint64_t sentm = (cnt >= 64) ? ~0ull : ((1ull << cnt) - 1ull);
+            const uint64_t ndm = ~dm & sentm;                        // sent packets that reach the queue
+            const int cnt_nd = __popcll(ndm);
+            const bool fits = (uint32_t)(tail - h2) + (uint32_t)cnt <= cap;
+            if (!fits) ok = false;                                   // ring overflow: fatal, reported
+            // S3: x_k (:66-67 with :75-76)
+            double tk[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int k = (int)lane + 32 * u;
+                tk[u] = (k < cnt) ? sm.ts[k] : 0.0;
+                const uint64_t before = ndm & ((1ull << k) - 1ull);
+                if ((ndm >> k) & 1ull) {
+                    const double tuk = before ? sm.ts[63 - __clzll((long long)before)] : t_upd;
+                    sm.xs[__popcll(before)] = tk[u] - tuk;
+                }
             }
-            tail += rem;
+            __syncwarp();
+            // S4: y = q - x, q = f(y) in place over the compact array, on lane 0
+            double state = qd;
+            if (lane == 0) {
+#pragma unroll 4
+                for (int k = 0; k < cnt_nd; ++k) {
+                    const double y = state - sm.xs[k];               // :66-67
+                    sm.xs[k] = y;
+                    const double cpos = d_bw + y;                    // :82 if 0 < y <= w_full
+                    const bool pos = y > 0.0;
+                    const bool fullp = y > w_full;                   // :77-79 (tail_drop_threshold)
+                    const double qn = fullp ? y : cpos;
+                    state = pos ? qn : k0;
+                }
+            }
+            state = __shfl_sync(PCC_FULL, state, 0);
+            __syncwarp();
+            // S5: records (:173-175), sender ids, the chunk's carry
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int k = (int)lane + 32 * u;
+                if (k < cnt && fits) {
+                    const uint64_t before = ndm & ((1ull << k) - 1ull);
+                    const int rank = __popcll(before);
+                    const bool rdrop = ((dm >> k) & 1ull) != 0ull;
+                    double y;
+                    if (!rdrop) y = sm.xs[rank];
+                    else {
+                        // the queue as the last packet that reached it left it (:74: a random drop does not touch it)
+                        double qp = qd;
+                        if (rank > 0) {
+                            const double yp = sm.xs[rank - 1];
+                            qp = (yp > 0.0) ? ((yp > w_full) ? yp : d_bw + yp) : k0;
+                        }
+                        const double tuk = before ? sm.ts[63 - __clzll((long long)before)] : t_upd;
+                        y = qp - (tk[u] - tuk);
+                    }
+                    const bool pos = y > 0.0;
+                    const double w = pos ? y : 0.0;                  // max(0.0, y)
+                    const bool full = pos ? (y > w_full) : full0;
+                    const bool dropped = rdrop || full;
+                    const double ll = dl + w;                        // :69-70
+                    Rec r;
+                    r.a = tk[u] + ll;
+                    r.l = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
+                    ring.store(tail + (uint32_t)k, r);
+                    ring.set_sid(tail + (uint32_t)k, sm.sid[k]);
+                }
+            }
+            if (ndm) t_upd = sm.ts[63 - __clzll((long long)ndm)];
+            qd = state;
+            if (fits) tail += (uint32_t)cnt;
+            draws += (uint64_t)cnt;
+            __syncwarp();                                            // all reads of ts / xs / sid are done
+            if (cnt < navail) break;                                 // the merge stopped at a timer >= end
         }
-        draws += (uint64_t)k;
     }
     __syncwarp();
 
     // ---- (2) hop-1 events with a < end ---------------------------------------------------------------
-    for (;;) {
+    for (bool scanning = true; scanning;) {
         const uint32_t n = tail - h1;
         if (n == 0u) break;
-        const bool valid = lane < n;
-        const double a = valid ? ring.load_a(h1 + lane) : 0.0;
-        if (lane * 8u + 32u < n && (lane & 3u) == 0u) prefetch_l2_line(ring.addr(h1 + 32u + lane * 8u));
-        const unsigned stop = __ballot_sync(PCC_FULL, valid && !sgn(a) && !(a < end));
-        if (stop) { h1 += (uint32_t)(__ffs(stop) - 1); break; }
-        h1 += n < 32u ? n : 32u;
+        double a[PCC_MW_W];
+#pragma unroll
+        for (int w = 0; w < PCC_MW_W; w++) a[w] = (w * 32u + lane < n) ? ring.load_a(h1 + w * 32u + lane) : 0.0;
+        if (PCC_MW_W * 32u + lane * 8u < n) prefetch_l2_line(ring.addr(h1 + PCC_MW_W * 32u + lane * 8u));
+        uint32_t adv = n < PCC_MW_W * 32u ? n : PCC_MW_W * 32u;
+#pragma unroll
+        for (int w = PCC_MW_W - 1; w >= 0; w--) {                    // the first stop of the round, if any
+            const unsigned stop = __ballot_sync(PCC_FULL, (w * 32u + lane < n) && !sgn(a[w]) && !(a[w] < end));
+            if (stop) { adv = w * 32u + (uint32_t)(__ffs(stop) - 1); scanning = false; }
+        }
+        h1 += adv;
     }
     bool has1 = false;
     uint32_t m1 = 0; double m1a = 0.0, m1l = 0.0; bool m1d = false; int m1s = 0;
@@ -168,37 +250,46 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
 
     // ---- (3) hop-2 events with b < end ---------------------------------------------------------------
     bool at_live = false;
-    for (;;) {
+    for (bool scanning = true; scanning;) {
         const uint32_t n = tail - h2;
         if (n == 0u) break;
-        const uint32_t idx = h2 + lane;
-        const bool valid = lane < n;
-        Rec r; r.a = 0.0; r.l = 0.0;
-        int sd = 0;
-        if (valid) { r = ring.load(idx); sd = ring.sid(idx); }
-        if (lane * 8u + 32u < n && (lane & 3u) == 0u) prefetch_l2_line(ring.addr(h2 + 32u + lane * 8u));
-        const bool live = valid && !is_dead(r.a);
-        const bool c1 = ((int32_t)(idx - h1) < 0) || sgn(r.a);
-        const bool early = live && c1 && (absd(r.a) + dl < end);     // link 1: latency == dl exactly (N1)
-        const unsigned stop = __ballot_sync(PCC_FULL, live && !early);
-        const unsigned first = stop ? (unsigned)(__ffs(stop) - 1) : (n < 32u ? n : 32u);
-        const bool take = early && lane < first;
-        const bool dr = sgn(r.l);
+        Rec rr[PCC_MW_W];
+        int sdd[PCC_MW_W];
 #pragma unroll
-        for (int i = 0; i < S; i++) {
-            const unsigned ma = __ballot_sync(PCC_FULL, take && sd == i && !dr);
-            const unsigned ml = __ballot_sync(PCC_FULL, take && sd == i && dr);
-            if (take && sd == i && !dr) {
-                const int pos = nrtt[i] + __popc(ma & lt_mask);
-                if (pos < cap_s) samples[(size_t)i * cap_s + pos] = absd(r.l) + dl; else ok = false;
-            }
-            lost[i] += __popc(ml);
-            acked[i] += __popc(ma); nrtt[i] += __popc(ma);
+        for (int w = 0; w < PCC_MW_W; w++) {
+            rr[w].a = 0.0; rr[w].l = 0.0; sdd[w] = 0;
+            if (w * 32u + lane < n) { rr[w] = ring.load(h2 + w * 32u + lane); sdd[w] = ring.sid(h2 + w * 32u + lane); }
         }
-        h2 += first;
-        if (stop) {
-            at_live = __shfl_sync(PCC_FULL, (int)c1, (int)first) != 0;   // the stop is a live event at or after `end`
-            break;
+        if (PCC_MW_W * 32u + lane * 8u < n) prefetch_l2_line(ring.addr(h2 + PCC_MW_W * 32u + lane * 8u));
+#pragma unroll
+        for (int w = 0; w < PCC_MW_W; w++) {
+            if (!scanning || w * 32u >= n) break;
+            const uint32_t nw = n - w * 32u, idx = h2 + lane;
+            const Rec r = rr[w];
+            const int sd = sdd[w];
+            const bool live = lane < nw && !is_dead(r.a);
+            const bool c1 = ((int32_t)(idx - h1) < 0) || sgn(r.a);
+            const bool early = live && c1 && (absd(r.a) + dl < end); // link 1: latency == dl exactly (N1)
+            const unsigned stop = __ballot_sync(PCC_FULL, live && !early);
+            const unsigned first = stop ? (unsigned)(__ffs(stop) - 1) : (nw < 32u ? nw : 32u);
+            const bool take = early && lane < first;
+            const bool dr = sgn(r.l);
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                const unsigned ma = __ballot_sync(PCC_FULL, take && sd == i && !dr);
+                const unsigned ml = __ballot_sync(PCC_FULL, take && sd == i && dr);
+                if (take && sd == i && !dr) {
+                    const int pos = nrtt[i] + __popc(ma & lt_mask);
+                    if (pos < cap_s) samples[(size_t)i * cap_s + pos] = absd(r.l) + dl; else ok = false;
+                }
+                lost[i] += __popc(ml);
+                acked[i] += __popc(ma); nrtt[i] += __popc(ma);
+            }
+            h2 += first;
+            if (stop) {
+                at_live = __shfl_sync(PCC_FULL, (int)c1, (int)first) != 0;   // the stop is a live event at or after `end`
+                scanning = false;
+            }
         }
     }
     ok = !__any_sync(PCC_FULL, !ok);

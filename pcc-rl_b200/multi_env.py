@@ -1,7 +1,7 @@
 """PccMultiSenderEnv: N independent links, each shared by S senders (BASELINE config 5: the bw x delay grid
 sweep with 2 senders per link).  Batched counterpart of driving the reference's Network with several Sender
-objects (gym/network_sim.py:100-178); semantics in include/pcc_b200.h / DESIGN.md.  Exact, not fast: one env
-per thread with a per-env event heap.
+objects (gym/network_sim.py:100-178); semantics in include/pcc_b200.h / DESIGN.md.  Default engine: the heap-free
+streaming MI with one link per warp (csrc/pcc_multi_warp.cuh); the per-env event heap serves the variants below.
 
 The same path carries the two variants the reference hides behind module switches (network_sim.py:51-54):
 `use_cwnd=True` (USE_CWND: congestion window, a second action component per sender) and
@@ -58,7 +58,7 @@ class PccMultiSenderEnv(object):
                 self.L.pcc_default_variant(C.byref(v))
                 v.use_cwnd, v.use_latency_noise = int(self.use_cwnd), int(self.use_latency_noise)
                 _lib.check(self.L.pcc_multi_set_variant(self.h, C.byref(v)))
-            self.cwnd = torch.empty((self.n_envs, self.S), dtype=torch.int32, device=self.device)
+            self.cwnd = torch.zeros((self.n_envs, self.S), dtype=torch.int32, device=self.device)
             f64 = dict(dtype=torch.float64, device=self.device)
             self.obs = torch.empty((self.n_envs, self.S, self.obs_dim), **f64)
             self.reward = torch.empty((self.n_envs, self.S), **f64)
@@ -114,9 +114,13 @@ class PccMultiSenderEnv(object):
             ca = torch.as_tensor(cwnd_actions).to(self.device, torch.float64).reshape(self.n_envs, self.S).contiguous()
         _lib.check(self.L.pcc_multi_step_cwnd(self.h, a.data_ptr(), ca.data_ptr() if ca is not None else None,
                                               self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
-                                              self.counts.data_ptr(), self.cwnd.data_ptr(), self._stream()))
+                                              self.counts.data_ptr(), self.cwnd.data_ptr() if self.use_cwnd else None,
+                                              self._stream()))
         self._keep_a = (a, ca)
         return self.obs, self.reward, self.done.bool(), {"counts": self.counts, "cwnd": self.cwnd}
 
     def check(self):
         _lib.check(self.L.pcc_multi_check(self.h, self._stream()))
+
+    def launch_count(self):
+        return int(self.L.pcc_multi_launch_count(self.h))

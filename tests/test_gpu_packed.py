@@ -71,3 +71,34 @@ def test_packed_ragged_batch_vs_oracle(monkeypatch):
     assert np.array_equal(torch.stack(cnt).cpu().numpy(), ref["count_traj"])
     assert np.array_equal(torch.stack(rew).cpu().numpy(), ref["reward_traj"])
     assert np.array_equal(obs.cpu().numpy(), ref["obs"])
+
+
+@pytest.mark.parametrize("mode", ["warp", "packed"])
+def test_tiny_queues_vs_oracle(mode, monkeypatch):
+    """Queues of 0, 1 and 2 packets (max_queue_delay == 0 / == 1/bw: tail_drop_threshold's corner; the reset kernel
+    must terminate and every step must match the oracle), both step kernels."""
+    import torch
+    monkeypatch.setenv("PCC_B200_MODE", mode)
+    monkeypatch.setenv("PCC_B200_SOLO", "600")
+    monkeypatch.setenv("PCC_B200_QUAD", "90")
+    n, steps = 384, 60
+    g = np.random.default_rng(77)
+    bw = np.exp(g.uniform(np.log(40), np.log(5000), n))
+    p = dict(bw=bw, lat=np.exp(g.uniform(np.log(0.001), np.log(0.5), n)), queue=g.integers(0, 3, n).astype(np.int64),
+             loss=g.choice([0.0, 0.05, 0.3], n), start_rate=g.uniform(40, 1000, n))
+    seeds = np.arange(n, dtype=np.uint64) * np.uint64(104729) + np.uint64(11)
+    acts = g.normal(0, 3.0, (steps, n))
+    env = base._env(n_envs=n, auto_reset=False)
+    env.seed(seeds=seeds)
+    env.reset(params=p)
+    a_dev = torch.as_tensor(acts, device=env.device)
+    rew, cnt = [], []
+    for t in range(steps):
+        obs, r, d, info = env.step(a_dev[t])
+        rew.append(r.clone()); cnt.append(info["counts"].clone())
+    env.check()
+    ref = oracle.batch_run(p["bw"], p["lat"], p["queue"], p["loss"], p["start_rate"], seeds, steps, actions=acts,
+                           n_threads=os.cpu_count() or 1, trajectories=True)
+    assert np.array_equal(torch.stack(cnt).cpu().numpy(), ref["count_traj"])
+    assert np.array_equal(torch.stack(rew).cpu().numpy(), ref["reward_traj"])
+    assert np.array_equal(obs.cpu().numpy(), ref["obs"])

@@ -116,6 +116,19 @@ def test_twin_equals_oracle_nasty_ranges(seed):
                        "latency increase,latency ratio,send ratio")
 
 
+def tiny_queues(g):
+    """Queues of 0, 1 and 2 packets (the reference's own sampler never goes below 2, its classes take any): with one
+    packet max_queue_delay == 1/bw, so the tail-drop threshold is the ulp-sized interval around w = 0."""
+    bw = float(np.exp(g.uniform(np.log(40), np.log(5000))))
+    return (bw, float(np.exp(g.uniform(np.log(0.001), np.log(0.5)))), int(g.integers(0, 3)),
+            float(g.choice([0.0, 0.05, 0.3])), float(g.uniform(40, 1000)))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_twin_equals_oracle_tiny_queues(seed):
+    _lockstep(5000 + seed, n_eps=6, n_steps=100, sampler=tiny_queues, act_sigma=3.0)
+
+
 def test_twin_ring_wraps_u32_and_small_capacity():
     """Ring positions are u32 counters: run across the 2^32 wrap with a ring of 4096 slots."""
     small = lambda g: (g.uniform(100, 300), g.uniform(0.05, 0.2), 1 + int(np.exp(g.uniform(0, 4))),
@@ -159,6 +172,13 @@ def test_tail_drop_threshold_is_exact():
         for w in cands:
             assert (d_bw + w > max_qd) == (w > wf), (bw, queue, w, wf)
     assert L.twin_tail_drop_threshold(1.0, 0.5) == -1.0   # never admissible: every packet is tail-dropped
+    # a queue of exactly one packet: max_qd == d_bw, the admissible interval is [0, w_full] with w_full below one ulp
+    # of d_bw (walking there ulp by ulp from 0 would never end)
+    for bw in (83.3, 1054.5534236464064, 1e5):
+        d_bw = 1.0 / bw
+        wf = L.twin_tail_drop_threshold(d_bw, 1.0 / bw)
+        assert 0.0 <= wf < np.spacing(d_bw)
+        assert d_bw + wf <= d_bw and d_bw + float(np.nextafter(wf, np.inf)) > d_bw
 
 
 def test_pw_stream_push_form_equals_pull_form():

@@ -285,3 +285,26 @@ def test_twin_multi_stream_nasty_ties_and_wrap(seed):
             assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2], (seed, trial, k)
             assert o.cur_time == t.cur_time and o.run_dur == t.run_dur
         assert t.ok
+
+
+@pytest.mark.parametrize("S", [1, 3, 4])
+def test_twin_multi_stream_ragged_links_other_sender_counts(S):
+    """1, 3 and 4 senders on ragged links incl. queues of 0-2 packets and zero-packet MIs (the same generator family as
+    tests/test_gpu_multi.py::test_cuda_multi_other_sender_counts_vs_oracle)."""
+    n, steps = 48, 30
+    g = np.random.default_rng(200 + S)
+    for i in range(n):
+        bw, lat = float(g.uniform(80, 2000)), float(np.exp(g.uniform(np.log(0.002), np.log(0.6))))
+        queue, loss = int(g.integers(0, 40)) if i % 3 else int(g.integers(0, 3)), float(g.choice([0.0, 0.01, 0.05]))
+        rates = g.uniform(40, 1500, S)
+        o = oracle.OracleEnv()
+        o.seed_philox(300 + i)
+        o.reset_multi(bw, lat, queue, loss, rates)
+        tw = TwinMultiFast(S, capacity=1 << 14)
+        tw.reset(300 + i, bw, lat, queue, loss, rates)
+        for t in range(steps):
+            a = g.normal(0, 2.0, S)
+            x, y = o.step_multi(a), tw.step(a)
+            assert np.array_equal(x[3], y[3]), (S, i, t)
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]), (S, i, t)
+        assert tw.ok
