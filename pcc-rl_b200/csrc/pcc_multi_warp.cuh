@@ -40,13 +40,15 @@ struct DevSidRing {
     __device__ __forceinline__ int sid(uint32_t i) const { return sids[i & mask]; }
     __device__ __forceinline__ void set_sid(uint32_t i, int sd) { sids[i & mask] = (uint8_t)sd; }
     __device__ __forceinline__ const void *addr(uint32_t i) const { return base + (i & mask); }
+    __device__ __forceinline__ const void *sid_addr(uint32_t i) const { return sids + (i & mask); }
 };
 
 // per-warp staging of a chunk of the send phase
 struct MwSendSmem {
-    double ts[64];        // merged send times of the chunk's packets
-    double xs[64];        // x of the packets that reach the queue, compact; overwritten in place by y
-    uint8_t sid[64];      // sender of packet k
+    double ts[2][64];     // merged send times of the packets of the current / next chunk
+    double xs[64 + 8];    // x of the packets that reach the queue, compact (+ slack: the loop reads one ahead)
+    double ys[64];        // y = q - x of the same packets
+    uint8_t sid[2][64];   // sender of packet k
 };
 
 // One MI of the link owned by this warp.  Every argument and every local is warp-uniform unless it says "lane".
@@ -70,6 +72,14 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
     uint32_t tail = f.tail, h1 = f.h1, h2 = f.h2;
     double qd = net.qd, t_upd = net.t_upd;
     const double dl = net.dl, lr = net.lr, w_full = net.w_full, d_bw = net.d_bw;
+
+    // the records in flight are read by the cursors after the send phase: ask L2 for their lines now (16-byte records,
+    // 8 per line; the sender ids, 128 per line), so that DRAM latency runs under the send phase
+    {
+        const uint32_t inflight = tail - h2;
+        for (uint32_t i = lane * 8u; i < inflight; i += 256u) prefetch_l2_line(ring.addr(h2 + i));
+        for (uint32_t i = lane * 128u; i < inflight; i += 4096u) prefetch_l2_line(ring.sid_addr(h2 + i));
+    }
 
     // the SEND event of the pending timer (it, t): queue update, record (:156-178 -> :66-84)
 #define PCC_MW_SEND(it, t, loss, r)                                                           \
@@ -102,21 +112,31 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
         const uint64_t thr = loss_threshold(lr);
         const double k0 = (0.0 > w_full) ? 0.0 : d_bw;               // q' when the queue has drained (w = 0)
         const bool full0 = 0.0 > w_full;
-        for (;;) {
+        // M1: one step of the timers' merge (:156-161) into chunk buffer b_, branch-free: `mon_` says the merge is still
+        // running; it ends at the first timer >= end or when the chunk is full
+#define PCC_MW_MERGE_STEP(b_, mcnt_, mon_, navail_)                                           \
+        {                                                                                     \
+            PCC_MW_NEXT_TIMER(it, t);                                                         \
+            const bool fire = mon_ && (t < end);                                              \
+            if (lane == 0 && fire) { sm.ts[b_][mcnt_] = t; sm.sid[b_][mcnt_] = (uint8_t)it; } \
+            _Pragma("unroll")                                                                 \
+            for (int i = 0; i < S; i++) {                                                     \
+                const bool mine = fire && i == it;                                            \
+                sent[i] += mine ? 1 : 0;                                                      \
+                ns[i] = mine ? t + inv[i] : ns[i];                                            \
+            }                                                                                 \
+            mcnt_ += fire ? 1 : 0;                                                            \
+            mon_ = fire && mcnt_ != (navail_);                                                \
+        }
+        int b = 0, cnt = 0;
+        {
+            const int navail = 64 - (int)(draws & 1ull);
+            bool mon = true;
+            while (mon) PCC_MW_MERGE_STEP(0, cnt, mon, navail);
+        }
+        while (cnt > 0) {
             const unsigned off = (unsigned)(draws & 1ull);
-            const int navail = 64 - (int)off;
-            // M1: the timers' merge (:156-161), serial; the loop ends the chunk at the first timer >= end
-            int cnt = 0;
-            while (cnt < navail) {
-                PCC_MW_NEXT_TIMER(it, t);
-                if (!(t < end)) break;
-                if (lane == 0) { sm.ts[cnt] = t; sm.sid[cnt] = (uint8_t)it; }
-#pragma unroll
-                for (int i = 0; i < S; i++)
-                    if (i == it) { sent[i]++; ns[i] = t + inv[i]; }
-                cnt++;
-            }
-            if (cnt == 0) break;
+            const bool last = cnt < 64 - (int)off;                   // the merge stopped at a timer >= end
             __syncwarp();
             // S1: bit k of dm = packet k of the chunk is randomly dropped (:73)
             uint32_t c0, c1, c2, c3;
@@ -133,29 +153,36 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const int k = (int)lane + 32 * u;
-                tk[u] = (k < cnt) ? sm.ts[k] : 0.0;
+                tk[u] = (k < cnt) ? sm.ts[b][k] : 0.0;
                 const uint64_t before = ndm & ((1ull << k) - 1ull);
                 if ((ndm >> k) & 1ull) {
-                    const double tuk = before ? sm.ts[63 - __clzll((long long)before)] : t_upd;
+                    const double tuk = before ? sm.ts[b][63 - __clzll((long long)before)] : t_upd;
                     sm.xs[__popcll(before)] = tk[u] - tuk;
                 }
             }
             __syncwarp();
-            // S4: y = q - x, q = f(y) in place over the compact array, on lane 0
+            // S4 + M1: y = q - x, q = f(y) over the compact array -- every lane runs it, lane 0 stores y -- and, in the same
+            // branch-free loop, the merge of the NEXT chunk: two independent dependency chains in one instruction stream
             double state = qd;
-            if (lane == 0) {
+            int mcnt = 0;
+            {
+                const int navail2 = 64 - (int)((draws + (uint64_t)cnt) & 1ull);
+                bool mon = !last;
+                double xn = sm.xs[0];
 #pragma unroll 4
                 for (int k = 0; k < cnt_nd; ++k) {
-                    const double y = state - sm.xs[k];               // :66-67
-                    sm.xs[k] = y;
+                    const double y = state - xn;                     // :66-67
+                    xn = sm.xs[k + 1];
+                    if (lane == 0) sm.ys[k] = y;
                     const double cpos = d_bw + y;                    // :82 if 0 < y <= w_full
                     const bool pos = y > 0.0;
                     const bool fullp = y > w_full;                   // :77-79 (tail_drop_threshold)
                     const double qn = fullp ? y : cpos;
                     state = pos ? qn : k0;
+                    PCC_MW_MERGE_STEP(b ^ 1, mcnt, mon, navail2);
                 }
+                while (mon) PCC_MW_MERGE_STEP(b ^ 1, mcnt, mon, navail2);
             }
-            state = __shfl_sync(PCC_FULL, state, 0);
             __syncwarp();
             // S5: records (:173-175), sender ids, the chunk's carry
 #pragma unroll
@@ -166,15 +193,15 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
                     const int rank = __popcll(before);
                     const bool rdrop = ((dm >> k) & 1ull) != 0ull;
                     double y;
-                    if (!rdrop) y = sm.xs[rank];
+                    if (!rdrop) y = sm.ys[rank];
                     else {
                         // the queue as the last packet that reached it left it (:74: a random drop does not touch it)
                         double qp = qd;
                         if (rank > 0) {
-                            const double yp = sm.xs[rank - 1];
+                            const double yp = sm.ys[rank - 1];
                             qp = (yp > 0.0) ? ((yp > w_full) ? yp : d_bw + yp) : k0;
                         }
-                        const double tuk = before ? sm.ts[63 - __clzll((long long)before)] : t_upd;
+                        const double tuk = before ? sm.ts[b][63 - __clzll((long long)before)] : t_upd;
                         y = qp - (tk[u] - tuk);
                     }
                     const bool pos = y > 0.0;
@@ -186,16 +213,17 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
                     r.a = tk[u] + ll;
                     r.l = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
                     ring.store(tail + (uint32_t)k, r);
-                    ring.set_sid(tail + (uint32_t)k, sm.sid[k]);
+                    ring.set_sid(tail + (uint32_t)k, sm.sid[b][k]);
                 }
             }
-            if (ndm) t_upd = sm.ts[63 - __clzll((long long)ndm)];
+            if (ndm) t_upd = sm.ts[b][63 - __clzll((long long)ndm)];
             qd = state;
             if (fits) tail += (uint32_t)cnt;
             draws += (uint64_t)cnt;
-            __syncwarp();                                            // all reads of ts / xs / sid are done
-            if (cnt < navail) break;                                 // the merge stopped at a timer >= end
+            cnt = mcnt;
+            b ^= 1;
         }
+#undef PCC_MW_MERGE_STEP
     }
     __syncwarp();
 
