@@ -120,11 +120,8 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
             const bool fire = mon_ && (t < end);                                              \
             if (lane == 0 && fire) { sm.ts[b_][mcnt_] = t; sm.sid[b_][mcnt_] = (uint8_t)it; } \
             _Pragma("unroll")                                                                 \
-            for (int i = 0; i < S; i++) {                                                     \
-                const bool mine = fire && i == it;                                            \
-                sent[i] += mine ? 1 : 0;                                                      \
-                ns[i] = mine ? t + inv[i] : ns[i];                                            \
-            }                                                                                 \
+            for (int i = 0; i < S; i++)                                                       \
+                if (fire && i == it) ns[i] += inv[i];             /* t == ns[it]: t + 1/rate */ \
             mcnt_ += fire ? 1 : 0;                                                            \
             mon_ = fire && mcnt_ != (navail_);                                                \
         }
@@ -184,10 +181,13 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
                 while (mon) PCC_MW_MERGE_STEP(b ^ 1, mcnt, mon, navail2);
             }
             __syncwarp();
-            // S5: records (:173-175), sender ids, the chunk's carry
+            // S5: records (:173-175), sender ids, packets sent per sender (:159-160), the chunk's carry
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const int k = (int)lane + 32 * u;
+                const int sdk = (k < cnt) ? (int)sm.sid[b][k] : -1;
+#pragma unroll
+                for (int i = 0; i < S; i++) sent[i] += __popc(__ballot_sync(PCC_FULL, sdk == i));
                 if (k < cnt && fits) {
                     const uint64_t before = ndm & ((1ull << k) - 1ull);
                     const int rank = __popcll(before);
@@ -213,7 +213,7 @@ __device__ __forceinline__ bool mwarp_run_for_dur(MNet &net, MSender *snd, MFast
                     r.a = tk[u] + ll;
                     r.l = __longlong_as_double(__double_as_longlong(ll) | (dropped ? (long long)PCC_SIGN : 0ll));
                     ring.store(tail + (uint32_t)k, r);
-                    ring.set_sid(tail + (uint32_t)k, sm.sid[b][k]);
+                    ring.set_sid(tail + (uint32_t)k, sdk);
                 }
             }
             if (ndm) t_upd = sm.ts[b][63 - __clzll((long long)ndm)];
