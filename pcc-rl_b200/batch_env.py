@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 from . import sender_obs
-from .params import LinkRanges, sample_link_params
+from .params import LinkRanges, sample_link_params, validate_link_params
 
 
 def _require_cuda():
@@ -147,6 +147,8 @@ class PccBatchEnv(object):
         if params is None:
             pinned = self._prefetch_take(sel)
             params = pinned[0] if pinned is not None else self._sample(sel)
+        else:
+            validate_link_params(*[np.asarray(params[k])[sel] for k in ("bw", "lat", "queue", "loss", "start_rate")])
         if self.params is None:
             self.params = {k: np.array(v, copy=True) for k, v in params.items()}
         else:

@@ -12,6 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib, sender_obs
+from .params import validate_link_params
 
 
 def grid_sweep_params(bw_mbps=(1.0, 1000.0), lat_ms=(1.0, 500.0), n_bw=32, n_lat=32, queue=50, loss=0.0,
@@ -90,6 +91,7 @@ class PccMultiSenderEnv(object):
     def reset(self, params, start_rates):
         """params: dict bw, lat, queue, loss (length n_envs); start_rates: [n_envs, n_senders] packets/s."""
         torch = self.torch
+        validate_link_params(params["bw"], params["lat"], params["queue"], params["loss"], start_rates)
         dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(self.device)
         bw, lat, loss = (dev(params[k], torch.float64) for k in ("bw", "lat", "loss"))
         q = dev(params["queue"], torch.int64)

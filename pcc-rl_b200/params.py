@@ -36,3 +36,21 @@ def sample_link_params(seed, episode, global_ids, n_global, ranges=None):
     loss = r.loss[0] + (r.loss[1] - r.loss[0]) * u[:, 3]
     start_rate = (r.start_factor[0] + (r.start_factor[1] - r.start_factor[0]) * u[:, 4]) * bw
     return dict(bw=bw, lat=lat, queue=queue, loss=loss, start_rate=start_rate)
+
+
+def validate_link_params(bw, lat, queue, loss, rates):
+    """Explicit link parameters handed to reset(): the device loops assume a positive finite bandwidth and sending
+    rate (a pacing timer that does not advance would never reach the end of the MI), a non-negative delay and queue,
+    and a loss probability.  The reference never checks -- its own sampler cannot produce anything else -- but a
+    batched env should refuse garbage instead of occupying a GPU.  Raises ValueError naming the offending field."""
+    def bad(name, a, ok):
+        a = np.asarray(a)
+        m = ~ok(a)
+        if m.any():
+            i = int(np.flatnonzero(m.reshape(-1))[0])
+            raise ValueError("link parameter %s[%d] = %r is out of range" % (name, i, a.reshape(-1)[i].item()))
+    bad("bw", bw, lambda a: np.isfinite(a) & (a > 0))
+    bad("lat", lat, lambda a: np.isfinite(a) & (a >= 0))
+    bad("queue", queue, lambda a: np.asarray(a) >= 0)
+    bad("loss", loss, lambda a: (a >= 0) & (a <= 1))
+    bad("start_rate", rates, lambda a: np.isfinite(a) & (a > 0))

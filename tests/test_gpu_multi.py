@@ -88,7 +88,7 @@ def test_cuda_multi_other_sender_counts_vs_oracle(S, multi_mode):
     n, steps = 96, 40
     g = np.random.default_rng(100 + S)
     p = dict(bw=g.uniform(80, 2000, n), lat=np.exp(g.uniform(np.log(0.002), np.log(0.6), n)),
-             queue=g.integers(0, 60, n), loss=g.choice([0.0, 0.01, 0.05], n))
+             queue=g.integers(0, 60, n), loss=g.choice([0.0, 0.01, 0.05, 1.0], n))
     rates = g.uniform(40, 1500, (n, S))
     acts = g.normal(0, 2.0, (steps, n, S))
     env = pcc_rl_b200.PccMultiSenderEnv(n, n_senders=S, seed=900, ring_capacity=1 << 14)

@@ -85,7 +85,7 @@ def test_tiny_queues_vs_oracle(mode, monkeypatch):
     g = np.random.default_rng(77)
     bw = np.exp(g.uniform(np.log(40), np.log(5000), n))
     p = dict(bw=bw, lat=np.exp(g.uniform(np.log(0.001), np.log(0.5), n)), queue=g.integers(0, 3, n).astype(np.int64),
-             loss=g.choice([0.0, 0.05, 0.3], n), start_rate=g.uniform(40, 1000, n))
+             loss=g.choice([0.0, 0.05, 0.3, 1.0], n), start_rate=g.uniform(40, 1000, n))
     seeds = np.arange(n, dtype=np.uint64) * np.uint64(104729) + np.uint64(11)
     acts = g.normal(0, 3.0, (steps, n))
     env = base._env(n_envs=n, auto_reset=False)

@@ -121,7 +121,7 @@ def tiny_queues(g):
     packet max_queue_delay == 1/bw, so the tail-drop threshold is the ulp-sized interval around w = 0."""
     bw = float(np.exp(g.uniform(np.log(40), np.log(5000))))
     return (bw, float(np.exp(g.uniform(np.log(0.001), np.log(0.5)))), int(g.integers(0, 3)),
-            float(g.choice([0.0, 0.05, 0.3])), float(g.uniform(40, 1000)))
+            float(g.choice([0.0, 0.05, 0.3, 1.0])), float(g.uniform(40, 1000)))
 
 
 @pytest.mark.parametrize("seed", range(6))

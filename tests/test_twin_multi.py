@@ -295,7 +295,7 @@ def test_twin_multi_stream_ragged_links_other_sender_counts(S):
     g = np.random.default_rng(200 + S)
     for i in range(n):
         bw, lat = float(g.uniform(80, 2000)), float(np.exp(g.uniform(np.log(0.002), np.log(0.6))))
-        queue, loss = int(g.integers(0, 40)) if i % 3 else int(g.integers(0, 3)), float(g.choice([0.0, 0.01, 0.05]))
+        queue, loss = int(g.integers(0, 40)) if i % 3 else int(g.integers(0, 3)), float(g.choice([0.0, 0.01, 0.05, 1.0]))
         rates = g.uniform(40, 1500, S)
         o = oracle.OracleEnv()
         o.seed_philox(300 + i)

@@ -12,6 +12,9 @@ mkdir -p $out
 (timeout 300 python bench.py --workload config4 --steps 2048 2>/dev/null | tail -1) > $out/${tag}_bench_config4_1gpu.json
 (timeout 300 python bench.py --impl reference --steps 100 --warmup 5 2>/dev/null | tail -1) > $out/${tag}_bench_reference_arm.json
 (timeout 120 python tools/time_dropin.py 10 2>&1 | tail -2) > $out/${tag}_dropin.txt
+(timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2) > $out/${tag}_smoke.txt
+# config 5 (several senders per link): bench line, launch list, full capture of one step kernel
+bash tools/ncu_config5.sh $tag > /dev/null 2>&1
 # launch list of the bench command (per-launch times are cold-cache and serialised: shares, not absolutes)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_config3_launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline --only-device-pass > /dev/null 2>&1
@@ -23,5 +26,5 @@ if [ -f gpurun_exp_prof/libpcc_b200_prof.so ]; then
   (PCC_B200_LIB=gpurun_exp_prof/libpcc_b200_prof.so timeout 300 python tools/phase_profile_packed.py 65536 215 2>&1 | tail -30) > $out/${tag}_phase_profile_packed.txt
   (PCC_B200_LIB=gpurun_exp_prof/libpcc_b200_prof.so timeout 300 python tools/phase_profile_warp.py 4096 215 2>&1 | tail -12) > $out/${tag}_phase_profile_config2.txt
 fi
-cat $out/${tag}_tests.log $out/${tag}_dropin.txt
-for f in config3 config3_k20 config2 config4_1gpu reference_arm; do cut -c1-400 $out/${tag}_bench_$f.json; echo; done
+cat $out/${tag}_tests.log $out/${tag}_dropin.txt $out/${tag}_smoke.txt
+for f in config3 config3_k20 config2 config4_1gpu reference_arm config5; do cut -c1-400 $out/${tag}_bench_$f.json; echo; done
