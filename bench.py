@@ -622,6 +622,10 @@ def main():
             finished.append(env.column("last_episode_return"))
             env.check()
         per_step = [a.elapsed_time(b) for a, b in zip(ev_s, ev_e)]
+        if os.environ.get("PCC_BENCH_DEBUG"):
+            top = sorted(range(len(per_step)), key=lambda i: -per_step[i])[:4]
+            sys.stderr.write("slowest steps (index in the window: ms): %s; preroll + warm-up = %d steps\n"
+                             % (", ".join("%d: %.2f" % (i, per_step[i]) for i in top), pre + w))
         dev_ms = D.max_over_ranks(sum(per_step), dev)
         sent, acked, _lost = [int(x) for x in tot.cpu().tolist()]
         rets = torch.cat(finished) if finished else torch.zeros(0, dtype=torch.float64, device=dev)

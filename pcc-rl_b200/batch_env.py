@@ -249,8 +249,10 @@ class PccBatchEnv(object):
         finished = self._steps >= self.max_steps
         done = self.done.bool()
         if self.auto_reset and finished.any():
-            self.check()  # once per episode: surface ring overflows
+            # once per episode: surface ring overflows (the count on the device survives the reset).  AFTER the reset is
+            # queued: the check waits for the stream, and the GPU should not sit idle while the host prepares the reset
             self.reset(mask=finished)
+            self.check()
         return self.obs, self.reward, done, info
 
     def rollout(self, n_steps, actions=None, policy=None, want_obs=True, want_counts=True):

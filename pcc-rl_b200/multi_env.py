@@ -54,6 +54,10 @@ class PccMultiSenderEnv(object):
             self.h = C.c_void_p()
             _lib.check(self.L.pcc_multi_create(C.byref(self.h), C.byref(cfg), self.S, self.ws.data_ptr()))
             self.use_cwnd, self.use_latency_noise = bool(use_cwnd), bool(use_latency_noise)
+            # the event-heap engine reports every sender's window (Sender.cwnd, the initial 25 when USE_CWND is off); the
+            # streaming engines have none: `cwnd` stays zero and the per-step memset is skipped
+            import os
+            self._heap_engine = self.use_cwnd or self.use_latency_noise or os.environ.get("PCC_MULTI_MODE") == "heap"
             if use_cwnd or use_latency_noise:
                 v = _lib.PccVariant()
                 self.L.pcc_default_variant(C.byref(v))
@@ -116,7 +120,7 @@ class PccMultiSenderEnv(object):
             ca = torch.as_tensor(cwnd_actions).to(self.device, torch.float64).reshape(self.n_envs, self.S).contiguous()
         _lib.check(self.L.pcc_multi_step_cwnd(self.h, a.data_ptr(), ca.data_ptr() if ca is not None else None,
                                               self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
-                                              self.counts.data_ptr(), self.cwnd.data_ptr() if self.use_cwnd else None,
+                                              self.counts.data_ptr(), self.cwnd.data_ptr() if self._heap_engine else None,
                                               self._stream()))
         self._keep_a = (a, ca)
         return self.obs, self.reward, self.done.bool(), {"counts": self.counts, "cwnd": self.cwnd}
