@@ -2537,6 +2537,59 @@ __global__ void __launch_bounds__(128, 4) pcc_mwarp_step_kernel(MultiDev p, cons
     }
 }
 
+// reset of the links in `mask` (all if null), one link per warp: fresh link + senders and the two discarded warm-up MIs
+// (network_sim.py:454-484; mfast_reset of pcc_multi_fast.cuh on the warp machinery)
+template <int S>
+__global__ void __launch_bounds__(128, 4) pcc_mwarp_reset_kernel(MultiDev p, const uint8_t *__restrict__ mask,
+                                                              const double *__restrict__ bw, const double *__restrict__ delay,
+                                                              const long long *__restrict__ queue,
+                                                              const double *__restrict__ loss, const double *__restrict__ rates,
+                                                              double *__restrict__ obs)
+{
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= p.n || (mask && !mask[e])) return;                      // whole warp
+    const unsigned lane = threadIdx.x & 31u;
+    MEnv &me = p.envs[e];
+    MNet net = me.net;
+    MFast f = p.fast[e];
+    MSender snd[S];
+    const double dl = delay[e];
+    net.d_bw = 1.0 / bw[e]; net.dl = dl; net.lr = loss[e]; net.max_qd = (double)queue[e] / bw[e];
+    net.w_full = tail_drop_threshold(net.d_bw, net.max_qd);
+    net.qd = 0.0; net.t_upd = 0.0; net.cur_time = 0.0; net.run_dur = 3 * dl; net.steps = 0; net.heap_n = 0;
+    f.h1 = f.tail; f.h2 = f.tail;                                    // drop everything in flight; positions keep counting
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+        const double r = rates[(size_t)e * S + i];
+        snd[i].rate = r; snd[i].conn_min = 0.0;
+        snd[i].sent = snd[i].acked = snd[i].lost = snd[i].n_rtt = 0; snd[i].obs_start = 0.0;
+        snd[i].cwnd = 0; snd[i].inflight = 0;
+        f.next_send[i] = 1.0 / r;                                    // queue_initial_packets :107-111
+    }
+    const uint64_t seed = me.seed;
+    uint64_t draws = me.draws;
+    DevSidRing ring = multi_ring(p, e);
+    double *smp = p.samples + (size_t)e * S * p.cap_s;
+    __shared__ MwSendSmem send_sm[4];
+    MwSendSmem &sm = send_sm[threadIdx.x >> 5];
+    bool ok = mwarp_run_for_dur<S>(net, snd, f, ring, smp, p.cap_s, seed, draws, net.run_dur, sm);   // :478
+    ok = mwarp_run_for_dur<S>(net, snd, f, ring, smp, p.cap_s, seed, draws, net.run_dur, sm) && ok;  // :479
+    if (lane == 0) {
+        me.net = net;
+#pragma unroll
+        for (int i = 0; i < S; i++) me.snd[i] = snd[i];
+        me.draws = draws;
+        p.fast[e] = f;
+        if (!ok) atomicAdd(&p.meta[1], 1ull);
+    }
+    const int HF = p.H * p.F;
+    for (int k = (int)lane; k < S * HF; k += 32) {
+        const double v = metric_empty(p.ids[(k % HF) % p.F]);
+        p.hist[(size_t)e * S * HF + k] = v;
+        if (obs) obs[(size_t)e * S * HF + k] = v;
+    }
+}
+
 // predicted packets of the next MI per link (sort key, 16 bits) + identity values for the sort
 __global__ void pcc_mcost_kernel(MultiDev p, uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
 {
@@ -2691,7 +2744,19 @@ int pcc_multi_reset(pcc_multi_handle h, const uint8_t *mask_dev, const double *b
     const int want = (h->heap_forced || h->d.v.use_cwnd || h->d.v.use_noise) ? 2 : 1;
     if (h->mode == 0) h->mode = want;
     else if (h->mode != want) return fail(PCC_EINVAL, "the variant switches changed after the first reset (create a new handle)");
-    if (h->mode == 1)
+    if (h->mode == 1 && !h->thread_forced) {
+        const unsigned grid = (unsigned)((h->d.n + 3) / 4);
+#define PCC_MWARP_RESET(S_)                                                                                      \
+        pcc_mwarp_reset_kernel<S_><<<grid, 128, 0, (cudaStream_t)stream>>>(h->d, mask_dev, bw_dev, delay_dev,           \
+            (const long long *)queue_dev, loss_dev, start_rates_dev, obs_dev)
+        switch (h->d.S) {
+            case 1: PCC_MWARP_RESET(1); break;
+            case 2: PCC_MWARP_RESET(2); break;
+            case 3: PCC_MWARP_RESET(3); break;
+            default: PCC_MWARP_RESET(4); break;
+        }
+#undef PCC_MWARP_RESET
+    } else if (h->mode == 1)
         pcc_mfast_reset_kernel<<<(unsigned)((h->d.n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(
             h->d, mask_dev, bw_dev, delay_dev, (const long long *)queue_dev, loss_dev, start_rates_dev, obs_dev);
     else

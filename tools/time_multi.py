@@ -13,7 +13,13 @@ for mode in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("warp", "thread",
     n, S = side * side, 2
     g = np.random.default_rng(7)
     env = pcc_rl_b200.PccMultiSenderEnv(n, n_senders=S, seed=500, ring_capacity=1 << 13)
-    env.reset(p, g.uniform(40, 1000, (n, S)))
+    r0 = g.uniform(40, 1000, (n, S))
+    env.reset(p, r0)
+    torch.cuda.synchronize()
+    rs, re_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rs.record(); env.reset(p, r0); re_.record()
+    torch.cuda.synchronize()
+    reset_ms = rs.elapsed_time(re_)
     acts = torch.randn((steps + 5, n, S), dtype=torch.float64, device=env.device) * 2.0
     for t in range(5):
         env.step(acts[t])
@@ -26,5 +32,5 @@ for mode in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("warp", "thread",
     torch.cuda.synchronize()
     env.check()
     ms = s.elapsed_time(e) / steps
-    print("%-6s grid %dx%d, %d senders: %.3f ms/step = %.3f M env-steps/s (%.3f M sender-steps/s)"
-          % (mode, side, side, S, ms, n / ms / 1e3, n * S / ms / 1e3))
+    print("%-6s grid %dx%d, %d senders: %.3f ms/step = %.3f M env-steps/s (%.3f M sender-steps/s); reset of every link %.2f ms"
+          % (mode, side, side, S, ms, n / ms / 1e3, n * S / ms / 1e3, reset_ms))
