@@ -684,6 +684,8 @@ def main():
     a_np = h_act.numpy()
     nb = [{k: v.numpy() for k, v in b.items()} for b in bufs]
 
+    e2e_trace = [] if os.environ.get("PCC_BENCH_DEBUG") else None
+
     def e2e_run(first, count, pipelined):
         acc, tk = 0.0, [None, None]
         for t in range(first, first + count):
@@ -692,7 +694,11 @@ def main():
                 if tk[sl] is not None:
                     env.step_host_wait(tk[sl])
                     acc += float(nb[sl]["r"][0])           # the result is really read on the host
+                if e2e_trace is not None:
+                    e2e_trace.append(time.perf_counter())
                 tk[sl] = env.step_host_submit(a_np[t], nb[sl]["o"], nb[sl]["r"], nb[sl]["d"])
+                if e2e_trace is not None:
+                    e2e_trace.append(time.perf_counter())
             else:
                 env.step_host(a_np[t], nb[sl]["o"], nb[sl]["r"], nb[sl]["d"])
                 acc += float(nb[sl]["r"][0])
@@ -712,6 +718,12 @@ def main():
     e2e_run(W, K, True)
     barrier()
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    if e2e_trace is not None:
+        tr = e2e_trace[-2 * K:]
+        sys.stderr.write("e2e pipelined, per step [wait-done -> submit-returned, submit-returned -> next wait-done] ms: %s\n"
+                         % " ".join("%.2f/%.2f" % (1e3 * (tr[2 * i + 1] - tr[2 * i]), 1e3 * ((tr[2 * i + 2] if 2 * i + 2 < len(tr) else tr[-1]) - tr[2 * i + 1]))
+                                    for i in range(min(K, 24))))
+        e2e_trace = None
     ks = min(K, 50)
     barrier()
     t0 = time.perf_counter()
