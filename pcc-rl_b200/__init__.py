@@ -27,4 +27,8 @@ def __getattr__(name):  # lazy: importing network_sim touches gym registration
         import importlib
         mod = importlib.import_module("." + ("distributed" if name == "distributed" else "network_sim"), __name__)
         return mod.SimulatedNetworkEnv if name == "SimulatedNetworkEnv" else mod
+    if name in ("ShimNetworkEnv", "shim_env"):   # opens a TCP socket when constructed (gym/online/shim_env.py)
+        import importlib
+        mod = importlib.import_module(".shim_env", __name__)
+        return mod.ShimNetworkEnv if name == "ShimNetworkEnv" else mod
     raise AttributeError(name)
