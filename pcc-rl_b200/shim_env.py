@@ -35,13 +35,15 @@ class ShimLink(object):
         self.sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
         self.sock.setblocking(1)
         self.sock.bind((host, port))
+        # the reference starts listening in its first step(); listening from the start only means that a sender which
+        # connects earlier waits in the backlog instead of being refused
+        self.sock.listen()
         self.port = self.sock.getsockname()[1]
         self.conn, self.addr = None, None
 
     def accept(self):
         if self.conn is None:
             print("Listening for connection from network sender")
-            self.sock.listen()
             self.conn, self.addr = self.sock.accept()
 
     def exchange(self, rate):

@@ -12,7 +12,16 @@ from pcc_rl_b200.flow_monitor import format_sample_line
 
 def _sender(port, records, rates_seen, fragment=0, pair_first=False):
     """Plays the UDT sender's shim (udt-plugins/training/shim.py:31-42): read the rate, answer with one record line."""
-    s = socket.create_connection(("localhost", port))
+    s = None
+    for _ in range(300):                          # like the real sender: keep trying until the env listens
+        try:
+            s = socket.create_connection(("localhost", port), timeout=30)
+            break
+        except OSError:
+            import time
+            time.sleep(0.1)
+    assert s is not None
+    s.settimeout(30)
     try:
         for k, rec in enumerate(records):
             rates_seen.append(s.recv(1024).decode())
@@ -50,7 +59,8 @@ def test_shim_link_reads_whole_records_and_last_complete_line():
     recs = _records(g, 6, 400)                       # records of several KB: more than one recv(1024)
     link = ShimLink(port=0)                          # an ephemeral port instead of 9787
     seen = []
-    th = threading.Thread(target=_sender, args=(link.port, recs, seen), kwargs=dict(fragment=700, pair_first=True))
+    link.sock.settimeout(30)
+    th = threading.Thread(target=_sender, args=(link.port, recs, seen), kwargs=dict(fragment=700, pair_first=True), daemon=True)
     th.start()
     try:
         for k, rec in enumerate(recs):
@@ -65,16 +75,18 @@ def test_shim_link_reads_whole_records_and_last_complete_line():
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(120)
 def test_shim_env_vs_oracle_history_and_reference_rate_formula():
     """60 MIs through the socket, a reset in the middle: observations == the oracle's SenderHistory, rates == the
     reference's apply_action / set_rate (shim_env.py:82-96), reward and done as the reference returns them."""
     import pcc_rl_b200
     g = np.random.default_rng(5)
     recs = _records(g, 60, 200)
+    socket.setdefaulttimeout(30)
     env = pcc_rl_b200.ShimNetworkEnv(port=0)
     assert env.observation_space.shape == (30,) and env.action_space.shape == (1,)
-    seen = []
-    th = threading.Thread(target=_sender, args=(env.link.port, recs, seen))
+    seen = []                     # a test must fail, not wait, if the other side dies
+    th = threading.Thread(target=_sender, args=(env.link.port, recs, seen), daemon=True)
     th.start()
     orc = oracle.OracleFlows(1)
     try:
@@ -102,5 +114,6 @@ def test_shim_env_vs_oracle_history_and_reference_rate_formula():
         assert len(seen) == 60 and float(seen[-1]) == rate
         env.mon.check()
     finally:
+        socket.setdefaulttimeout(None)
         th.join(timeout=10)
         env.close()
