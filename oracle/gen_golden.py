@@ -1,6 +1,7 @@
 """Generates tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE -- TEST INFRASTRUCTURE.
 
-Run in the build container (needs /root/reference):   python oracle/gen_golden.py
+Run in the build container (needs /root/reference):   python oracle/gen_golden.py   (all of round 1's fixtures)
+                                                      python oracle/gen_golden.py queue1   (round 2: one-packet queues)
 The fixtures are data (inputs + the reference's outputs); no reference source is copied.
 
 Two families:
@@ -205,5 +206,19 @@ def main():
     gen_multi(ns, "3s_tinyqueue", 35, 200.0, 0.03, 2, 0.05, [150.0, 150.0, 150.0], 80, macts(80, 3))
 
 
+def main_queue1():
+    """Round 2: a queue of exactly ONE packet (max_queue_delay == 1/bw) -- legal for the reference's classes (its sampler
+    draws 1 + int(exp(U(0, 8))) >= 2, the scripted stream below makes int(exp(.)) = 0), and the corner where the tail-drop
+    threshold of pcc_core.cuh sits within one ulp of w = 0.  Own action stream: the fixtures above stay byte-identical."""
+    ns = rh.load_reference()
+    g = random.Random(43)
+    acts = lambda n, s=1.0: [g.gauss(0.0, s) for _ in range(n)]
+    gen_philox(ns, "queue1_overdrive", 41, [(150.0, 0.05, 1, 0.01, 1.5)], 100, [3.0] * 40 + acts(60, 3.0))
+    gen_philox(ns, "queue1_highbw_shortlat", 42, [(1054.5534236464064, 0.0023996703096765487, 1, 0.05, 0.72)], 80,
+               acts(80, 2.0))
+    macts = lambda n, S, s=2.0: [[g.gauss(0.0, s) for _ in range(S)] for _ in range(n)]
+    gen_multi(ns, "2s_queue1", 43, 300.0, 0.04, 1, 0.02, [200.0, 350.0], 80, macts(80, 2))
+
+
 if __name__ == "__main__":
-    main()
+    main_queue1() if sys.argv[1:] == ["queue1"] else main()
