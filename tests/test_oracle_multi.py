@@ -79,3 +79,41 @@ def test_oracle_multi_sender_matches_patched_reference(seed, n_senders):
                 del ns.Sender.__lt__
             except AttributeError:
                 pass
+
+
+@pytest.mark.parametrize("n_senders", [1, 3, 4])
+def test_oracle_multi_ragged_corners_match_patched_reference(n_senders):
+    """The corners the round-2 GPU tests lean on the oracle for (tests/test_gpu_multi.py, 1 / 3 / 4 senders on ragged
+    links): queues of 0, 1 and 2 packets, loss 0 / 0.05 / 1, very short and long delays -- the oracle against the live
+    reference classes."""
+    ns = rh.load_reference()
+    g = np.random.default_rng(50 + n_senders)
+    real_random, had_lt = ns.random, getattr(ns.Sender, "__lt__", None)
+    feats = oracle.DEFAULT_FEATURES.split(",")
+    try:
+        for trial in range(8):
+            bw = float(g.uniform(80, 2000))
+            lat = float(np.exp(g.uniform(np.log(0.002), np.log(0.3))))
+            queue = int(g.integers(0, 3)) if trial % 2 == 0 else int(g.integers(0, 60))
+            loss = float(g.choice([0.0, 0.05, 1.0]))
+            rates = [float(g.uniform(40, 1500)) for _ in range(n_senders)]
+            ref = RefMulti(ns, PhiloxStream(300 + trial), bw, lat, queue, loss, rates, feats)
+            o = oracle.OracleEnv()
+            o.seed_philox(300 + trial)
+            o.reset_multi(bw, lat, queue, loss, rates)
+            assert o.cur_time == ref.net.cur_time
+            for t in range(40):
+                acts = g.normal(0, 2.0, n_senders)
+                want = ref.step([float(a) for a in acts])
+                obs, rew, done, cnt = o.step_multi(acts)
+                for i in range(n_senders):
+                    assert tuple(cnt[i]) == want[i][2], (trial, t, i, queue, loss)
+                    assert rew[i] == want[i][1] and np.array_equal(obs[i], want[i][0]), (trial, t, i, queue, loss)
+                assert o.cur_time == ref.net.cur_time and o.run_dur == ref.run_dur
+    finally:
+        ns.random = real_random
+        if had_lt is None:
+            try:
+                del ns.Sender.__lt__
+            except AttributeError:
+                pass

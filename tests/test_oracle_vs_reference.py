@@ -76,3 +76,40 @@ def test_live_reference_lockstep_philox_envs():
                     assert (s.sent, s.acked, s.lost) == tuple(c2)
     finally:
         ns.random = real
+
+
+def test_live_reference_one_and_two_packet_queues():
+    """Scripted link parameters with queue = 1 and 2 packets (1 + int(exp(x)) with exp(x) < 1 resp. < 2), the corner
+    of pcc_core.cuh's tail-drop threshold: the oracle against the live reference env, 12 links x 80 steps."""
+    import math
+    from philox_py import PhiloxStream
+    ns = rh.load_reference()
+    g = np.random.default_rng(21)
+    real = ns.random
+    try:
+        with rh.quiet_tmp_cwd():
+            for i in range(12):
+                shim = rh.StreamShim([PhiloxStream(2000 + i)])
+                ns.random = shim
+                shim.script = [100.0, 0.1, 0.0, 0.0, 1.0]
+                env = ns.SimulatedNetworkEnv()
+                o = oracle.OracleEnv()
+                o.seed_philox(2000 + i)
+                queue = 1 + (i % 2)
+                bw = float(np.exp(g.uniform(np.log(40), np.log(5000))))
+                lat = float(np.exp(g.uniform(np.log(0.002), np.log(0.5))))
+                loss, factor = float(g.choice([0.0, 0.02, 0.3])), float(g.uniform(0.3, 3.0))
+                shim.script = [bw, lat, math.log(queue - 1 + 0.5), loss, factor]
+                obs0 = env.reset()
+                l, s = env.links[0], env.senders[0]
+                assert int(round(l.max_queue_delay * l.bw)) == queue
+                assert np.array_equal(o.reset(bw, lat, queue, loss, s.starting_rate), obs0)
+                for t in range(80):
+                    a = float(g.normal(0, 3.0))
+                    obs, r, d, _ = env.step([a])
+                    o2, r2, d2, c2, _ = o.step(a)
+                    assert (s.sent, s.acked, s.lost) == tuple(c2), (i, t)
+                    assert np.array_equal(obs, o2) and float(r) == r2, (i, t)
+                    assert env.net.cur_time == o.cur_time and float(env.run_dur) == o.run_dur
+    finally:
+        ns.random = real
